@@ -1,0 +1,246 @@
+/*
+ * otto_covisit.h - C ABI of the B200-native covisitation hot path (libotto_covisit.so).
+ *
+ * The reference (gunesevitan/otto-multi-objective-recommender-system) has no FFI, plugin or operator
+ * table: its boundary for this path is files + one helper + a CLI.  Each entry point
+ * below names the reference code whose work it replaces; the Python mirror of the reference scripts
+ * lives in otto_multi_objective_recommender_system_b200/ and binds these symbols with ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all buffers
+ *     (torch.Tensor.data_ptr() in our host code); the library allocates nothing on the device
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*); functions that
+ *     return a count through a *_host pointer synchronise that stream before returning
+ *   - return value 0 = ok, negative = error (OTTO_E*), message via otto_last_error(); no exceptions
+ *     cross the ABI; calls are thread-compatible (one stream per call, no global mutable state except
+ *     the thread-local error string)
+ *   - aids are int32 in [0, n_aids), n_aids <= 2^30; ts are int32 seconds; type is uint8 in {0,1,2}
+ *     (dtypes of utilities/dataset_writer_pickle.py:57-60 after the /1000 the consumers apply)
+ */
+#ifndef OTTO_COVISIT_H_
+#define OTTO_COVISIT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OTTO_OK 0
+#define OTTO_EINVAL (-22)      /* bad argument */
+#define OTTO_ENOSPC (-28)      /* caller buffer / workspace too small */
+#define OTTO_ECUDA (-5)        /* CUDA runtime error */
+#define OTTO_EOVERFLOW (-75)   /* an in-SM hash table overflowed: lower split_ub and rebuild */
+#define OTTO_EUNSORTED (-71)   /* frame is not sorted by (session, ts) */
+
+#define OTTO_WEIGHT_UNIT 0     /* buy2buy: wgt = number of sessions holding the pair            */
+#define OTTO_WEIGHT_TYPE 1     /* carts-orders: wgt = sum of type_weight[type_y]                 */
+#define OTTO_WEIGHT_TIME 2     /* clicks: wgt = sum of 1 + 3 (ts_x - ts_min) / (ts_max - ts_min) */
+
+#define OTTO_MAX_TAIL 32       /* tail_n <= 32: one event per lane */
+#define OTTO_MAX_K 32
+#define OTTO_MAX_SEGMENTS 8    /* pair segments per bin = GPUs of one box */
+#define OTTO_MAX_TABLES 8
+#define OTTO_MAX_SOURCES 8
+#define OTTO_MAX_TARGETS 4
+
+/* Session-sorted CSR of events, most recent first inside a session:
+ * order (session asc, ts desc, original row asc) - exactly the row order after the builder's
+ * sort_values(['session','ts'], ascending=[True, False]).
+ * Produced by otto_ingest_desc(). */
+typedef struct {
+  int64_t n_sessions;
+  int64_t n_events;
+  const int32_t* session_offsets; /* [n_sessions + 1] */
+  const int32_t* aid;             /* [n_events] */
+  const int32_t* ts;              /* [n_events] */
+  const uint8_t* type;            /* [n_events] */
+} OttoEvents;
+
+/* The matrix recipe (generic form §8a "CovisitSpec"). */
+typedef struct {
+  int32_t n_aids;
+  int32_t weight_mode;       /* OTTO_WEIGHT_* */
+  int32_t type_weight[3];    /* OTTO_WEIGHT_TYPE: {1, 6, 3} (baseline/aid_weight.py:34) */
+  uint32_t event_type_mask;  /* bit t set = events of type t enter the tail (buy2buy: 0b110) */
+  uint32_t x_type_mask;      /* pair-level filters on type_x / type_y (0b111 for the graded variants) */
+  uint32_t y_type_mask;
+  int32_t window_s;          /* keep |ts_x - ts_y| <  window_s (strict) */
+  int32_t tail_n;            /* most recent events per session that enter the self-join (30) */
+  int32_t k;                 /* rows kept per aid_x (15 / 20) */
+  int32_t ts_min;            /* OTTO_WEIGHT_TIME constants: 1659304800, 1662328791 */
+  int32_t ts_max;
+  int32_t split_ub;          /* rows whose pair upper bound exceeds this are split into y-hash sub-bins; 0 = default */
+} OttoCovisitSpec;
+
+/* Sizes the caller needs to allocate the build workspace for a given input shape. */
+typedef struct {
+  int64_t tail_capacity;     /* events of the tail CSR: min(n_events, n_sessions * tail_n) */
+  int64_t max_bins;          /* upper bound on bins = n_aids + sub-bins */
+  int64_t workspace_bytes;   /* bytes of the fixed workspace (everything except the pair records) */
+} OttoBuildSizes;
+
+/* Counters a build publishes (host struct, filled by otto_covisit_count / otto_covisit_reduce). */
+typedef struct {
+  int64_t tail_events;       /* E30: events that entered the self-join */
+  int64_t pairs;             /* P: pairs after in-session dedupe (records this rank emits) */
+  int64_t bins;              /* B: aid_x rows + sub-bins */
+  int64_t split_rows;        /* aid_x rows that were split into sub-bins */
+  int64_t distinct;          /* D: distinct (aid_x, aid_y) accumulated by this rank (after reduce) */
+  int64_t pair_checksum;     /* sum of counts over all accumulated entries (== pairs received) */
+  int64_t table_overflow;    /* != 0: a hash table overflowed (result invalid) */
+} OttoBuildStats;
+
+/* Pair records of one producer for a contiguous range of bins (multi-GPU: one segment per sender). */
+typedef struct {
+  const void* records;       /* 8-byte records {uint32 aid_y, uint32 v} */
+  const uint64_t* offsets;   /* offsets[b - bin_lo] .. offsets[b - bin_lo + 1] bound bin b's records */
+} OttoPairSegment;
+
+/* Per-aid top-K table, fixed stride: row aid_x holds len[aid_x] <= k entries, best first
+ * (wgt desc, aid_y asc); the file form top_<k>_<stem>_<part>.pqt (covisitation/inference.py:87-111)
+ * is these rows compacted. */
+typedef struct {
+  int32_t n_aids;
+  int32_t k;
+  int32_t* aid_y;            /* [n_aids * k], -1 padded */
+  float* wgt;                /* [n_aids * k] */
+  int32_t* len;              /* [n_aids] */
+  uint32_t* cnt;             /* optional [n_aids * k]: exact pair count (NULL to skip) */
+  uint64_t* tsum;            /* optional [n_aids * k]: exact sum(ts_x - ts_min), time mode (NULL to skip) */
+} OttoTopK;
+
+const char* otto_last_error(void);
+int otto_version(void);
+
+/* ---- ingest: frame columns -> CSR (replaces the sort + chunk writers of
+ *      utilities/split_dataset_writer_parquet.py:13-33 and builder step 2) ---- */
+
+/* Checks that (session, ts) is non-decreasing; *sorted_host = 1/0. Synchronises. */
+int otto_frame_is_sorted(const int32_t* session, const int32_t* ts, int64_t n_events, int32_t* flag_dev,
+                         int32_t* sorted_host, void* stream);
+
+/* From a frame sorted by (session, ts) ascending with run-length offsets (ascending CSR), writes the
+ * most-recent-first CSR columns: inside each session ts descending, ties in original row order. */
+int otto_ingest_desc(const int32_t* session_offsets, int64_t n_sessions, const int32_t* aid, const int32_t* ts,
+                     const uint8_t* type, int64_t n_events, int32_t* aid_out, int32_t* ts_out, uint8_t* type_out,
+                     void* stream);
+
+/* ---- build (the missing builder) ----
+ *
+ * Phases (all on one stream, one rank):
+ *   count_begin   tail CSR (steps 1-3) + per-aid pair upper bounds
+ *   [multi-GPU: all-reduce the upper bounds so that every rank forms identical bins]
+ *   count_finish  bins, in-session dedupe (steps 4-5, winner masks), exact per-bin pair counts + scan
+ *   scatter       8-byte pair records {aid_y, v} grouped by bin (step 6 in integer form)
+ *   [multi-GPU: all-to-all of the per-owner bin ranges]
+ *   reduce        accumulate per (aid_x, aid_y) + top-k per aid_x (steps 7-8) -> OttoTopK
+ * otto_covisit_build runs all of them for one GPU. */
+
+int otto_covisit_sizes(int64_t n_sessions, int64_t n_events, const OttoCovisitSpec* spec, OttoBuildSizes* out_host);
+
+int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                             int64_t workspace_bytes, void* stream);
+/* Fills stats_host->{tail_events,pairs,bins,split_rows}; synchronises when stats_host != NULL. */
+int otto_covisit_count_finish(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                              int64_t workspace_bytes, OttoBuildStats* stats_host, void* stream);
+/* count_begin + count_finish */
+int otto_covisit_count(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
+                       OttoBuildStats* stats_host, void* stream);
+
+/* Device views into the workspace (valid after the phase that writes them):
+ *   pair_ub     uint32 [n_aids]      after count_begin (all-reduce target for multi-GPU)
+ *   bin_base    uint32 [n_aids + 1]  first bin of each aid_x row, after count_finish
+ *   bin_x       uint32 [bins]        bin -> aid_x
+ *   bin_offsets uint64 [bins + 1]    record offsets of this rank's bins */
+int otto_covisit_views(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
+                       uint64_t** bin_offsets, uint32_t** bin_base, uint32_t** bin_x, uint32_t** pair_ub);
+
+/* Writes the pair records, grouped by bin, into `records` (>= stats.pairs * 8 bytes). */
+int otto_covisit_scatter(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
+                         void* records, int64_t records_capacity, void* stream);
+
+/* For bins [bin_lo, bin_hi) = rows [aid_lo, aid_hi): accumulate the records of all segments per
+ * (aid_x, aid_y), select the top k per aid_x and write those rows of `out`.  A segment's offsets are
+ * indexed by (bin - bin_lo) and may carry any base (offsets[0] is subtracted).  Fills
+ * stats_host->{distinct,pair_checksum,table_overflow}; synchronises when stats_host != NULL. */
+int64_t otto_covisit_reduce_scratch_bytes(const OttoCovisitSpec* spec, int64_t n_bins, int64_t n_aids_range);
+int otto_covisit_reduce(const OttoCovisitSpec* spec, const uint32_t* bin_base, const uint32_t* bin_x, int64_t bin_lo,
+                        int64_t bin_hi, int32_t aid_lo, int32_t aid_hi, const OttoPairSegment* segments_host,
+                        int32_t n_segments, void* scratch, int64_t scratch_bytes, const OttoTopK* out,
+                        OttoBuildStats* stats_host, void* stream);
+
+/* One-shot single-GPU build; the pair records and the reduce scratch are carved from the workspace after
+ * the fixed part.  Returns OTTO_ENOSPC (stats_host->pairs / bins set) when the workspace cannot hold
+ * them; otto_covisit_build_bytes gives the size to retry with. */
+int otto_covisit_build(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
+                       const OttoTopK* out, OttoBuildStats* stats_host, void* stream);
+int64_t otto_covisit_build_bytes(int64_t n_sessions, int64_t n_events, const OttoCovisitSpec* spec, int64_t pairs,
+                                 int64_t bins);
+
+/* Compacts a fixed-stride table into file rows (aid_x, aid_y, wgt) sorted aid_x asc, best first.
+ * row_offsets [n_aids + 1] = exclusive scan of len (int64). */
+int otto_topk_row_offsets(const OttoTopK* table, int64_t* row_offsets, int64_t* n_rows_host, void* scratch,
+                          int64_t scratch_bytes, void* stream);
+int otto_topk_to_rows(const OttoTopK* table, const int64_t* row_offsets, int32_t* aid_x, int32_t* aid_y, float* wgt,
+                      void* stream);
+/* Inverse: file rows (grouped by aid_x, ranked) -> fixed-stride table; what covisitation_df_to_dict
+ * (covisitation/inference.py:19-35) builds as a dict of lists. */
+int otto_rows_to_topk(const int32_t* aid_x, const int32_t* aid_y, const float* wgt, int64_t n_rows,
+                      const OttoTopK* table, void* stream);
+
+/* ---- candidate generation (ranker/covisitation_candidate_generation.py:108-141,
+ *      covisitation/inference.py:204-247) ---- */
+
+/* Test / validation sessions in FILE order (ts ascending), as groupby('session').agg(list) sees them. */
+typedef struct {
+  int64_t n_sessions;
+  int64_t n_events;
+  const int32_t* session_offsets; /* [n_sessions + 1] */
+  const int32_t* aid;
+  const uint8_t* type;
+} OttoSessions;
+
+#define OTTO_HIST_RECENCY 0   /* unique aids, most recent first: list(dict.fromkeys(aids[::-1])) */
+#define OTTO_HIST_TYPE_LE1 1  /* np.unique(aids[types <= 1]) ascending */
+#define OTTO_HIST_TYPE_GE1 2  /* np.unique(aids[types >= 1]) ascending */
+#define OTTO_HIST_TYPE_EQ0 3  /* np.unique(aids[types == 0]) ascending */
+
+typedef struct {
+  int32_t n_tables;
+  const int32_t* table_aid_y[OTTO_MAX_TABLES]; /* fixed-stride tables [n_aids * table_k[i]] */
+  const int32_t* table_len[OTTO_MAX_TABLES];   /* [n_aids] */
+  int32_t table_k[OTTO_MAX_TABLES];
+  int32_t n_aids;
+  int32_t n_sources;                           /* a source = one table gathered over one history set */
+  int32_t source_table[OTTO_MAX_SOURCES];
+  int32_t source_hist[OTTO_MAX_SOURCES];       /* OTTO_HIST_* */
+  int32_t n_targets;                           /* clicks, carts, orders */
+  int32_t target_n_sources[OTTO_MAX_TARGETS];
+  int32_t target_sources[OTTO_MAX_TARGETS][OTTO_MAX_SOURCES]; /* concatenation order */
+  int32_t top_n;                               /* Counter.most_common(top_n): 100 (ranker) / 20 (standalone) */
+  int32_t drop_history;                        /* 1: drop aids that are in the session (after truncation) */
+} OttoCandidateSpec;
+
+typedef struct {
+  int32_t* aid;    /* [n_targets][n_sessions][top_n], -1 padded, count desc then first-seen asc */
+  int32_t* score;  /* [n_targets][n_sessions][top_n] vote counts */
+  int32_t* len;    /* [n_targets][n_sessions] */
+} OttoCandidates;
+
+int64_t otto_candidates_scratch_bytes(const OttoSessions* sessions_shape_host, const OttoCandidateSpec* spec);
+int otto_candidates(const OttoSessions* sessions, const OttoCandidateSpec* spec, void* scratch, int64_t scratch_bytes,
+                    const OttoCandidates* out, void* stream);
+
+/* covisitation/inference.py:238-243: history + votes[:n - |H|] + popular[:n - len]; sessions whose
+ * unique-aid count is >= n keep their first n history aids (the reference sends them to its recency
+ * branch, :128-131; flagged in long_session so the caller can route them). */
+int otto_assemble_predictions(const OttoSessions* sessions, const OttoCandidates* cand, int32_t n_targets, int32_t top_n,
+                              const int32_t* popular /* [n_targets][n] */, int32_t n, int32_t* pred /* [n_targets][n_sessions][n] */,
+                              uint8_t* long_session /* [n_sessions] */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTTO_COVISIT_H_ */

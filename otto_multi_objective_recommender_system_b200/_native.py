@@ -1,0 +1,125 @@
+"""ctypes binding of libotto_covisit.so (include/otto_covisit.h).
+
+There is no CPU fallback: if the CUDA library is missing, loading raises and every product entry point
+fails loudly.  Build it with `python -c "import __graft_entry__ as g; g.build()"` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import pathlib
+
+_HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libotto_covisit.so"
+
+OTTO_OK = 0
+OTTO_EINVAL, OTTO_ENOSPC, OTTO_ECUDA, OTTO_EOVERFLOW, OTTO_EUNSORTED = -22, -28, -5, -75, -71
+WEIGHT_UNIT, WEIGHT_TYPE, WEIGHT_TIME = 0, 1, 2
+MAX_TAIL, MAX_K, MAX_SEGMENTS, MAX_TABLES, MAX_SOURCES, MAX_TARGETS = 32, 32, 8, 8, 8, 4
+HIST_RECENCY, HIST_TYPE_LE1, HIST_TYPE_GE1, HIST_TYPE_EQ0 = 0, 1, 2, 3
+
+vp = C.c_void_p
+i32, i64, u32 = C.c_int32, C.c_int64, C.c_uint32
+
+
+class OttoEvents(C.Structure):
+    _fields_ = [("n_sessions", i64), ("n_events", i64), ("session_offsets", vp), ("aid", vp), ("ts", vp),
+                ("type", vp)]
+
+
+class OttoCovisitSpec(C.Structure):
+    _fields_ = [("n_aids", i32), ("weight_mode", i32), ("type_weight", i32 * 3), ("event_type_mask", u32),
+                ("x_type_mask", u32), ("y_type_mask", u32), ("window_s", i32), ("tail_n", i32), ("k", i32),
+                ("ts_min", i32), ("ts_max", i32), ("split_ub", i32)]
+
+
+class OttoBuildSizes(C.Structure):
+    _fields_ = [("tail_capacity", i64), ("max_bins", i64), ("workspace_bytes", i64)]
+
+
+class OttoBuildStats(C.Structure):
+    _fields_ = [("tail_events", i64), ("pairs", i64), ("bins", i64), ("split_rows", i64), ("distinct", i64),
+                ("pair_checksum", i64), ("table_overflow", i64)]
+
+    def as_dict(self) -> dict:
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class OttoPairSegment(C.Structure):
+    _fields_ = [("records", vp), ("offsets", vp)]
+
+
+class OttoTopK(C.Structure):
+    _fields_ = [("n_aids", i32), ("k", i32), ("aid_y", vp), ("wgt", vp), ("len", vp), ("cnt", vp), ("tsum", vp)]
+
+
+class OttoSessions(C.Structure):
+    _fields_ = [("n_sessions", i64), ("n_events", i64), ("session_offsets", vp), ("aid", vp), ("type", vp)]
+
+
+class OttoCandidateSpec(C.Structure):
+    _fields_ = [("n_tables", i32), ("table_aid_y", vp * MAX_TABLES), ("table_len", vp * MAX_TABLES),
+                ("table_k", i32 * MAX_TABLES), ("n_aids", i32), ("n_sources", i32),
+                ("source_table", i32 * MAX_SOURCES), ("source_hist", i32 * MAX_SOURCES), ("n_targets", i32),
+                ("target_n_sources", i32 * MAX_TARGETS), ("target_sources", (i32 * MAX_SOURCES) * MAX_TARGETS),
+                ("top_n", i32), ("drop_history", i32)]
+
+
+class OttoCandidates(C.Structure):
+    _fields_ = [("aid", vp), ("score", vp), ("len", vp)]
+
+
+P = C.POINTER
+_SIGNATURES = {
+    "otto_last_error": (C.c_char_p, []),
+    "otto_version": (C.c_int, []),
+    "otto_frame_is_sorted": (C.c_int, [vp, vp, i64, vp, P(i32), vp]),
+    "otto_ingest_desc": (C.c_int, [vp, i64, vp, vp, vp, i64, vp, vp, vp, vp]),
+    "otto_covisit_sizes": (C.c_int, [i64, i64, P(OttoCovisitSpec), P(OttoBuildSizes)]),
+    "otto_covisit_count_begin": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, vp]),
+    "otto_covisit_count_finish": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(OttoBuildStats), vp]),
+    "otto_covisit_count": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(OttoBuildStats), vp]),
+    "otto_covisit_views": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(vp), P(vp), P(vp), P(vp)]),
+    "otto_covisit_scatter": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, vp, i64, vp]),
+    "otto_covisit_reduce_scratch_bytes": (i64, [P(OttoCovisitSpec), i64, i64]),
+    "otto_covisit_reduce": (C.c_int, [P(OttoCovisitSpec), vp, vp, i64, i64, i32, i32, P(OttoPairSegment), i32, vp,
+                                      i64, P(OttoTopK), P(OttoBuildStats), vp]),
+    "otto_covisit_build": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(OttoTopK), P(OttoBuildStats), vp]),
+    "otto_covisit_build_bytes": (i64, [i64, i64, P(OttoCovisitSpec), i64, i64]),
+    "otto_topk_row_offsets": (C.c_int, [P(OttoTopK), vp, P(i64), vp, i64, vp]),
+    "otto_topk_to_rows": (C.c_int, [P(OttoTopK), vp, vp, vp, vp, vp]),
+    "otto_rows_to_topk": (C.c_int, [vp, vp, vp, i64, P(OttoTopK), vp]),
+    # CANDIDATES-PLACEHOLDER
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class OttoError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libotto_covisit error {code}: {message}")
+        self.code = code
+
+
+def lib() -> C.CDLL:
+    """The loaded library; raises if it was never built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} is missing: the CUDA library has not been built. "
+                "Run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc); there is no CPU fallback.")
+        l = C.CDLL(os.fspath(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != OTTO_OK:
+        raise OttoError(code, lib().otto_last_error().decode("utf-8", "replace"))

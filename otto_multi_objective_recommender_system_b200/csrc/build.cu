@@ -1,0 +1,630 @@
+// C-ABI entry points of the covisitation build (include/otto_covisit.h) and the small kernels around
+// the two hot ones (pairgen.cuh, reduce.cuh): ingest, tail CSR, per-aid pair upper bounds, bins.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "pairgen.cuh"
+#include "reduce.cuh"
+#include "scan.cuh"
+
+static thread_local char g_error[512] = "";
+void otto_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* otto_last_error(void) { return g_error; }
+extern "C" int otto_version(void) { return 100; }
+
+// ------------------------------------------------------------------ ingest
+
+__global__ void frame_sorted_kernel(const int32_t* __restrict__ session, const int32_t* __restrict__ ts, int64_t n,
+                                    int32_t* flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i + 1 >= n) return;
+  const int32_t s0 = session[i], s1 = session[i + 1];
+  if (s0 > s1 || (s0 == s1 && ts[i] > ts[i + 1])) *flag = 1;
+}
+
+extern "C" int otto_frame_is_sorted(const int32_t* session, const int32_t* ts, int64_t n_events, int32_t* flag_dev,
+                                    int32_t* sorted_host, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(flag_dev, 0, sizeof(int32_t), st));
+  if (n_events > 1) {
+    frame_sorted_kernel<<<(unsigned)ceil_div(n_events, 256), 256, 0, st>>>(session, ts, n_events, flag_dev);
+    LAUNCH_CHECK();
+  }
+  int32_t flag = 0;
+  CUDA_TRY(cudaMemcpyAsync(&flag, flag_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *sorted_host = flag ? 0 : 1;
+  return OTTO_OK;
+}
+
+// One warp per session: reverse the ascending session so that ts is descending, keeping runs of equal
+// ts in their original order (what the stable ts-descending sort of builder step 2 produces).
+__global__ void __launch_bounds__(256)
+    ingest_desc_kernel(const int32_t* __restrict__ off, int64_t n_sessions, const int32_t* __restrict__ aid,
+                       const int32_t* __restrict__ ts, const uint8_t* __restrict__ type, int32_t* __restrict__ aid_out,
+                       int32_t* __restrict__ ts_out, uint8_t* __restrict__ type_out) {
+  const int64_t s = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (s >= n_sessions) return;
+  const uint32_t lane = lane_id();
+  const int32_t beg = off[s], end = off[s + 1];
+  for (int32_t p = beg + (int32_t)lane; p < end; p += 32) {
+    const int32_t t = ts[p];
+    int32_t a = p, r = p + 1;  // run [a, r) of equal ts around p
+    while (a > beg && ts[a - 1] == t) --a;
+    while (r < end && ts[r] == t) ++r;
+    const int32_t dst = beg + (end - r) + (p - a);
+    aid_out[dst] = aid[p];
+    ts_out[dst] = t;
+    type_out[dst] = type[p];
+  }
+}
+
+extern "C" int otto_ingest_desc(const int32_t* session_offsets, int64_t n_sessions, const int32_t* aid,
+                                const int32_t* ts, const uint8_t* type, int64_t n_events, int32_t* aid_out,
+                                int32_t* ts_out, uint8_t* type_out, void* stream) {
+  (void)n_events;
+  if (n_sessions <= 0) return OTTO_OK;
+  ingest_desc_kernel<<<(unsigned)ceil_div(n_sessions, 8), 256, 0, (cudaStream_t)stream>>>(
+      session_offsets, n_sessions, aid, ts, type, aid_out, ts_out, type_out);
+  LAUNCH_CHECK();
+  return OTTO_OK;
+}
+
+// ------------------------------------------------------------------ workspace layout
+
+struct Layout {
+  int64_t S, E, Ecap, A, Bmax;
+  int64_t tail_off, tail_aw, tail_ts, winmask, pair_ub, bin_base, bin_x, hist, bin_off, cursor, scan, stats, total;
+};
+
+static int32_t effective_split_ub(const OttoCovisitSpec* spec) { return spec->split_ub > 0 ? spec->split_ub : 32768; }
+
+static int check_spec(const OttoCovisitSpec* spec) {
+  if (!spec) { otto_set_error("spec is NULL"); return OTTO_EINVAL; }
+  if (spec->n_aids <= 0 || spec->n_aids > (1 << 30)) { otto_set_error("n_aids must be in (0, 2^30]"); return OTTO_EINVAL; }
+  if (spec->tail_n < 1 || spec->tail_n > OTTO_MAX_TAIL) { otto_set_error("tail_n must be in [1, 32]"); return OTTO_EINVAL; }
+  if (spec->k < 1 || spec->k > OTTO_MAX_K) { otto_set_error("k must be in [1, 32]"); return OTTO_EINVAL; }
+  if (spec->window_s <= 0) { otto_set_error("window_s must be positive"); return OTTO_EINVAL; }
+  if (spec->weight_mode < 0 || spec->weight_mode > 2) { otto_set_error("bad weight_mode"); return OTTO_EINVAL; }
+  if (spec->weight_mode == OTTO_WEIGHT_TIME) {
+    if (spec->ts_max <= spec->ts_min || (int64_t)spec->ts_max - spec->ts_min >= (1 << 24)) {
+      otto_set_error("time weights need 0 < ts_max - ts_min < 2^24");
+      return OTTO_EINVAL;
+    }
+  }
+  if (spec->weight_mode == OTTO_WEIGHT_TYPE)
+    for (int i = 0; i < 3; ++i)
+      if (spec->type_weight[i] < 0 || spec->type_weight[i] > 4096) { otto_set_error("type_weight must be in [0, 4096]"); return OTTO_EINVAL; }
+  if ((spec->event_type_mask & 7u) == 0) { otto_set_error("event_type_mask selects nothing"); return OTTO_EINVAL; }
+  return OTTO_OK;
+}
+
+static Layout make_layout(int64_t S, int64_t E, const OttoCovisitSpec* spec) {
+  Layout L;
+  L.S = S;
+  L.E = E;
+  L.A = spec->n_aids;
+  L.Ecap = E < S * spec->tail_n ? E : S * spec->tail_n;
+  if (L.Ecap < 1) L.Ecap = 1;
+  L.Bmax = L.A + (L.Ecap * (spec->tail_n - 1)) / effective_split_ub(spec) + 1;
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t at = o; o = align_up(o + bytes, 256); return at; };
+  L.tail_off = take((S + 2) * 4);
+  L.tail_aw = take(L.Ecap * 4);
+  L.tail_ts = take(L.Ecap * 4);
+  L.winmask = take(L.Ecap * 4);
+  L.pair_ub = take((L.A + 1) * 4);
+  L.bin_base = take((L.A + 2) * 4);
+  L.bin_x = take(L.Bmax * 4);
+  L.hist = take((L.Bmax + 1) * 4);
+  L.bin_off = take((L.Bmax + 2) * 8);
+  L.cursor = take((L.Bmax + 1) * 8);
+  int64_t scan_elems = scan_scratch_elems(S + 1);
+  if (scan_scratch_elems(L.Bmax + 1) > scan_elems) scan_elems = scan_scratch_elems(L.Bmax + 1);
+  L.scan = take(scan_elems * 8);
+  L.stats = take(256);
+  L.total = o;
+  return L;
+}
+
+extern "C" int otto_covisit_sizes(int64_t n_sessions, int64_t n_events, const OttoCovisitSpec* spec,
+                                  OttoBuildSizes* out_host) {
+  int rc = check_spec(spec);
+  if (rc) return rc;
+  if (n_sessions < 0 || n_events < 0 || n_events >= (1ll << 31)) { otto_set_error("n_events must be < 2^31"); return OTTO_EINVAL; }
+  const Layout L = make_layout(n_sessions, n_events, spec);
+  out_host->tail_capacity = L.Ecap;
+  out_host->max_bins = L.Bmax;
+  out_host->workspace_bytes = L.total;
+  return OTTO_OK;
+}
+
+// ------------------------------------------------------------------ tail CSR + upper bounds
+
+// events of each session that enter the self-join: the first tail_n of the (type-filtered) desc session
+__global__ void tail_count_kernel(const int32_t* __restrict__ off, const uint8_t* __restrict__ type, int64_t S,
+                                  uint32_t mask, int32_t tail_n, uint32_t* __restrict__ cnt) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int32_t beg = off[s], end = off[s + 1];
+  int32_t n = 0;
+  if ((mask & 7u) == 7u) {
+    n = min(end - beg, tail_n);
+  } else {
+    for (int32_t p = beg; p < end && n < tail_n; ++p) n += (mask >> type[p]) & 1u;
+  }
+  cnt[s] = (uint32_t)n;
+}
+
+// One warp per session: copy the tail events into the tail CSR and add (n - 1) to the pair upper bound
+// of every tail aid (each tail event can pair with at most n - 1 others).
+__global__ void __launch_bounds__(256)
+    tail_copy_kernel(const int32_t* __restrict__ off, const int32_t* __restrict__ aid, const int32_t* __restrict__ ts,
+                     const uint8_t* __restrict__ type, int64_t S, uint32_t mask, const uint32_t* __restrict__ tail_off,
+                     uint32_t* __restrict__ tail_aw, int32_t* __restrict__ tail_ts, uint32_t* __restrict__ pair_ub) {
+  const int64_t s = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (s >= S) return;
+  const uint32_t lane = lane_id(), lt = lanemask_lt();
+  const uint32_t tb = tail_off[s];
+  const uint32_t n = tail_off[s + 1] - tb;
+  if (n == 0) return;
+  const int32_t beg = off[s], end = off[s + 1];
+  uint32_t taken = 0;
+  for (int32_t p = beg; p < end && taken < n; p += 32) {
+    const int32_t q = p + (int32_t)lane;
+    uint32_t ty = 0;
+    bool ok = false;
+    if (q < end) {
+      ty = type[q];
+      ok = (mask >> ty) & 1u;
+    }
+    const uint32_t m = __ballot_sync(FULL_MASK, ok);
+    const uint32_t r = taken + __popc(m & lt);
+    if (ok && r < n) {
+      const int32_t a = aid[q];
+      tail_aw[tb + r] = (uint32_t)a | (ty << 30);
+      tail_ts[tb + r] = ts[q];
+      if (n > 1) atomicAdd(&pair_ub[a], n - 1);
+    }
+    taken += __popc(m);
+  }
+}
+
+// sub-bins per aid_x row: ceil(ub / split_ub), at least 1
+__global__ void bins_count_kernel(const uint32_t* __restrict__ pair_ub, int64_t A, uint32_t split_ub,
+                                  uint32_t* __restrict__ nb, unsigned long long* stats) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= A) return;
+  const uint32_t ub = pair_ub[x];
+  const uint32_t n = ub <= split_ub ? 1u : (ub + split_ub - 1) / split_ub;
+  nb[x] = n;
+  if (n > 1) atomicAdd(&stats[3], 1ull);
+}
+
+__global__ void bins_fill_kernel(const uint32_t* __restrict__ bin_base, int64_t A, uint32_t* __restrict__ bin_x) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= A) return;
+  for (uint32_t b = bin_base[x]; b < bin_base[x + 1]; ++b) bin_x[b] = (uint32_t)x;
+}
+
+__global__ void init_cursor_kernel(const unsigned long long* __restrict__ bin_off, const uint32_t* __restrict__ bin_base,
+                                   int64_t A, unsigned long long* __restrict__ cursor) {
+  const int64_t B = bin_base[A];
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x)
+    cursor[b] = bin_off[b];
+}
+
+// stats[0] tail events, [1] pairs, [2] bins ([3] split rows is counted by bins_count_kernel)
+__global__ void count_stats_kernel(const uint32_t* tail_off, int64_t S, const uint32_t* bin_base, int64_t A,
+                                   const unsigned long long* bin_off, unsigned long long* stats) {
+  const uint32_t B = bin_base[A];
+  stats[0] = tail_off[S];
+  stats[1] = bin_off[B];
+  stats[2] = B;
+}
+
+// scan over a device-resident length: hist[0..B) with B = bin_base[A] only known on the device.  We scan the
+// full Bmax-sized array instead (entries >= B are zero), which keeps the host out of the loop.
+
+#define WS(type, field) ((type*)((char*)workspace + L.field))
+
+static int check_ws(const Layout& L, void* workspace, int64_t workspace_bytes) {
+  if (!workspace || workspace_bytes < L.total) {
+    otto_set_error("workspace too small: need %lld bytes, got %lld", (long long)L.total, (long long)workspace_bytes);
+    return OTTO_ENOSPC;
+  }
+  if (((uintptr_t)workspace & 255) != 0) { otto_set_error("workspace must be 256-byte aligned"); return OTTO_EINVAL; }
+  return OTTO_OK;
+}
+
+extern "C" int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                                        int64_t workspace_bytes, void* stream) {
+  int rc = check_spec(spec);
+  if (rc) return rc;
+  if (!ev) { otto_set_error("events is NULL"); return OTTO_EINVAL; }
+  const Layout L = make_layout(ev->n_sessions, ev->n_events, spec);
+  if ((rc = check_ws(L, workspace, workspace_bytes))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t S = L.S;
+  CUDA_TRY(cudaMemsetAsync(WS(uint32_t, pair_ub), 0, (L.A + 1) * 4, st));
+  CUDA_TRY(cudaMemsetAsync(WS(char, stats), 0, 256, st));
+  CUDA_TRY(cudaMemsetAsync(WS(uint32_t, tail_off), 0, (S + 2) * 4, st));
+  if (S > 0) {
+    tail_count_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(ev->session_offsets, ev->type, S,
+                                                                   spec->event_type_mask, spec->tail_n,
+                                                                   WS(uint32_t, tail_off));
+    LAUNCH_CHECK();
+  }
+  if ((rc = exclusive_scan<uint32_t, uint32_t>(WS(uint32_t, tail_off), S, WS(uint32_t, tail_off), WS(uint32_t, scan), st)))
+    return rc;
+  if (S > 0) {
+    tail_copy_kernel<<<(unsigned)ceil_div(S, 8), 256, 0, st>>>(ev->session_offsets, ev->aid, ev->ts, ev->type, S,
+                                                               spec->event_type_mask, WS(uint32_t, tail_off),
+                                                               WS(uint32_t, tail_aw), WS(int32_t, tail_ts),
+                                                               WS(uint32_t, pair_ub));
+    LAUNCH_CHECK();
+  }
+  return OTTO_OK;
+}
+
+static PairGenParams make_pairgen(const Layout& L, const OttoCovisitSpec* spec, void* workspace) {
+  PairGenParams p;
+  p.tail_off = WS(uint32_t, tail_off);
+  p.tail_aw = WS(uint32_t, tail_aw);
+  p.tail_ts = WS(int32_t, tail_ts);
+  p.winmask = WS(uint32_t, winmask);
+  p.bin_base = WS(uint32_t, bin_base);
+  p.hist = WS(uint32_t, hist);
+  p.cursor = WS(unsigned long long, cursor);
+  p.records = nullptr;
+  p.n_sessions = L.S;
+  p.window = (uint32_t)spec->window_s;
+  p.x_type_mask = spec->x_type_mask;
+  p.y_type_mask = spec->y_type_mask;
+  p.weight_mode = spec->weight_mode;
+  p.ts_min = spec->ts_min;
+  for (int i = 0; i < 3; ++i) p.type_weight[i] = (uint32_t)spec->type_weight[i];
+  return p;
+}
+
+extern "C" int otto_covisit_count_finish(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                                         int64_t workspace_bytes, OttoBuildStats* stats_host, void* stream) {
+  int rc = check_spec(spec);
+  if (rc) return rc;
+  const Layout L = make_layout(ev->n_sessions, ev->n_events, spec);
+  if ((rc = check_ws(L, workspace, workspace_bytes))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t A = L.A;
+  // bins: nb[x] lands in bin_base, scanned in place
+  CUDA_TRY(cudaMemsetAsync(WS(uint32_t, bin_base), 0, (A + 2) * 4, st));
+  bins_count_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(WS(uint32_t, pair_ub), A,
+                                                                (uint32_t)effective_split_ub(spec),
+                                                                WS(uint32_t, bin_base), WS(unsigned long long, stats));
+  LAUNCH_CHECK();
+  if ((rc = exclusive_scan<uint32_t, uint32_t>(WS(uint32_t, bin_base), A, WS(uint32_t, bin_base), WS(uint32_t, scan), st)))
+    return rc;
+  bins_fill_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(WS(uint32_t, bin_base), A, WS(uint32_t, bin_x));
+  LAUNCH_CHECK();
+  // pass 1: winner masks + per-bin pair counts
+  CUDA_TRY(cudaMemsetAsync(WS(uint32_t, hist), 0, (L.Bmax + 1) * 4, st));
+  if (L.S > 0) {
+    PairGenParams p = make_pairgen(L, spec, workspace);
+    const int64_t warps = ceil_div(L.S, 32);
+    pairgen_kernel<false><<<(unsigned)ceil_div(warps, PAIRGEN_WARPS), PAIRGEN_WARPS * 32, 0, st>>>(p);
+    LAUNCH_CHECK();
+  }
+  if ((rc = exclusive_scan<uint32_t, unsigned long long>(WS(uint32_t, hist), L.Bmax, WS(unsigned long long, bin_off),
+                                                         WS(unsigned long long, scan), st)))
+    return rc;
+  count_stats_kernel<<<1, 1, 0, st>>>(WS(uint32_t, tail_off), L.S, WS(uint32_t, bin_base), A,
+                                      WS(unsigned long long, bin_off), WS(unsigned long long, stats));
+  LAUNCH_CHECK();
+  if (stats_host) {
+    unsigned long long h[4];
+    CUDA_TRY(cudaMemcpyAsync(h, WS(char, stats), sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    stats_host->tail_events = (int64_t)h[0];
+    stats_host->pairs = (int64_t)h[1];
+    stats_host->bins = (int64_t)h[2];
+    stats_host->split_rows = (int64_t)h[3];
+  }
+  return OTTO_OK;
+}
+
+extern "C" int otto_covisit_count(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                                  int64_t workspace_bytes, OttoBuildStats* stats_host, void* stream) {
+  int rc = otto_covisit_count_begin(ev, spec, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  return otto_covisit_count_finish(ev, spec, workspace, workspace_bytes, stats_host, stream);
+}
+
+extern "C" int otto_covisit_views(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                                  int64_t workspace_bytes, uint64_t** bin_offsets, uint32_t** bin_base,
+                                  uint32_t** bin_x, uint32_t** pair_ub) {
+  int rc = check_spec(spec);
+  if (rc) return rc;
+  const Layout L = make_layout(ev->n_sessions, ev->n_events, spec);
+  if ((rc = check_ws(L, workspace, workspace_bytes))) return rc;
+  if (bin_offsets) *bin_offsets = WS(uint64_t, bin_off);
+  if (bin_base) *bin_base = WS(uint32_t, bin_base);
+  if (bin_x) *bin_x = WS(uint32_t, bin_x);
+  if (pair_ub) *pair_ub = WS(uint32_t, pair_ub);
+  return OTTO_OK;
+}
+
+extern "C" int otto_covisit_scatter(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                                    int64_t workspace_bytes, void* records, int64_t records_capacity, void* stream) {
+  int rc = check_spec(spec);
+  if (rc) return rc;
+  const Layout L = make_layout(ev->n_sessions, ev->n_events, spec);
+  if ((rc = check_ws(L, workspace, workspace_bytes))) return rc;
+  if (!records && records_capacity > 0) { otto_set_error("records is NULL"); return OTTO_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  init_cursor_kernel<<<592, 256, 0, st>>>(WS(unsigned long long, bin_off), WS(uint32_t, bin_base), L.A,
+                                          WS(unsigned long long, cursor));
+  LAUNCH_CHECK();
+  if (L.S > 0) {
+    PairGenParams p = make_pairgen(L, spec, workspace);
+    p.records = (uint2*)records;
+    const int64_t warps = ceil_div(L.S, 32);
+    pairgen_kernel<true><<<(unsigned)ceil_div(warps, PAIRGEN_WARPS), PAIRGEN_WARPS * 32, 0, st>>>(p);
+    LAUNCH_CHECK();
+  }
+  return OTTO_OK;
+}
+
+// ------------------------------------------------------------------ reduce
+
+struct ScratchLayout {
+  int64_t p_key, p_sum, p_cnt, p_len, list_m, list_l, counters, stats, total;
+};
+
+static ScratchLayout make_scratch(int k, int64_t n_bins, int64_t n_aids_range) {
+  ScratchLayout s;
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t at = o; o = align_up(o + bytes, 256); return at; };
+  int64_t extra = n_bins - n_aids_range;
+  if (extra < 0) extra = 0;
+  const int64_t slots = 2 * extra + 2;
+  s.p_key = take(slots * k * 8);
+  s.p_sum = take(slots * k * 8);
+  s.p_cnt = take(slots * k * 4);
+  s.p_len = take(slots * 4);
+  s.list_m = take((n_bins + 1) * 4);
+  s.list_l = take((n_bins + 1) * 4);
+  s.counters = take(64);
+  s.stats = take(64);
+  s.total = o;
+  return s;
+}
+
+extern "C" int64_t otto_covisit_reduce_scratch_bytes(const OttoCovisitSpec* spec, int64_t n_bins, int64_t n_aids_range) {
+  if (check_spec(spec)) return -1;
+  return make_scratch(spec->k, n_bins, n_aids_range).total;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return OTTO_OK;
+}
+
+template <bool TIME>
+static int launch_reduce(const ReduceParams& p, int n_sm, cudaStream_t st) {
+  int rc;
+  constexpr size_t small_smem = (size_t)SMALL_WARPS * (32 * 8 * 2 + SMALL_SLOTS * 4 * 3 + 32 * 4);
+  if ((rc = set_smem(reduce_small_kernel<TIME>, small_smem))) return rc;
+  const int64_t n_bins = p.bin_hi - p.bin_lo;
+  int64_t small_blocks = ceil_div(n_bins, SMALL_WARPS);
+  if (small_blocks > (int64_t)n_sm * 32) small_blocks = (int64_t)n_sm * 32;
+  reduce_small_kernel<TIME><<<(unsigned)small_blocks, SMALL_WARPS * 32, small_smem, st>>>(p);
+  LAUNCH_CHECK();
+  {
+    auto kern = reduce_block_kernel<TIME, 128, 2048, unsigned long long, false>;
+    constexpr size_t smem = reduce_block_smem<TIME, 128, 2048, unsigned long long>();
+    if ((rc = set_smem(kern, smem))) return rc;
+    kern<<<n_sm * 6, 128, smem, st>>>(p);
+    LAUNCH_CHECK();
+  }
+  {
+    auto kern = reduce_block_kernel<TIME, 256, LARGE_SLOTS, unsigned long long, true>;
+    constexpr size_t smem = reduce_block_smem<TIME, 256, LARGE_SLOTS, unsigned long long>();
+    if ((rc = set_smem(kern, smem))) return rc;
+    kern<<<n_sm * 3, 256, smem, st>>>(p);
+    LAUNCH_CHECK();
+  }
+  merge_split_rows_kernel<<<n_sm * 4, 256, 0, st>>>(p);
+  LAUNCH_CHECK();
+  return OTTO_OK;
+}
+
+extern "C" int otto_covisit_reduce(const OttoCovisitSpec* spec, const uint32_t* bin_base, const uint32_t* bin_x,
+                                   int64_t bin_lo, int64_t bin_hi, int32_t aid_lo, int32_t aid_hi,
+                                   const OttoPairSegment* segments_host, int32_t n_segments, void* scratch,
+                                   int64_t scratch_bytes, const OttoTopK* out, OttoBuildStats* stats_host,
+                                   void* stream) {
+  int rc = check_spec(spec);
+  if (rc) return rc;
+  if (n_segments < 1 || n_segments > OTTO_MAX_SEGMENTS) { otto_set_error("n_segments must be in [1, 8]"); return OTTO_EINVAL; }
+  if (!out || out->k != spec->k || out->n_aids != spec->n_aids) { otto_set_error("output table shape does not match the spec"); return OTTO_EINVAL; }
+  if (bin_hi < bin_lo || aid_hi < aid_lo) { otto_set_error("empty or inverted range"); return OTTO_EINVAL; }
+  const ScratchLayout SL = make_scratch(spec->k, bin_hi - bin_lo, aid_hi - aid_lo);
+  if (!scratch || scratch_bytes < SL.total) {
+    otto_set_error("reduce scratch too small: need %lld bytes", (long long)SL.total);
+    return OTTO_ENOSPC;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  ReduceParams p;
+  memset(&p, 0, sizeof(p));
+  for (int s = 0; s < n_segments; ++s) p.seg[s] = segments_host[s];
+  p.n_seg = n_segments;
+  p.bin_x = bin_x;
+  p.bin_base = bin_base;
+  p.bin_lo = bin_lo;
+  p.bin_hi = bin_hi;
+  p.aid_lo = aid_lo;
+  p.aid_hi = aid_hi;
+  p.k = spec->k;
+  p.time_mode = spec->weight_mode == OTTO_WEIGHT_TIME;
+  p.w_scale = p.time_mode ? 3.0 / (double)(spec->ts_max - spec->ts_min) : 0.0;
+  p.out_y = out->aid_y;
+  p.out_w = out->wgt;
+  p.out_len = out->len;
+  p.out_cnt = out->cnt;
+  p.out_tsum = out->tsum;
+  char* sc = (char*)scratch;
+  p.p_key = (uint64_t*)(sc + SL.p_key);
+  p.p_sum = (uint64_t*)(sc + SL.p_sum);
+  p.p_cnt = (uint32_t*)(sc + SL.p_cnt);
+  p.p_len = (int32_t*)(sc + SL.p_len);
+  p.list_m = (uint32_t*)(sc + SL.list_m);
+  p.list_l = (uint32_t*)(sc + SL.list_l);
+  p.counters = (uint32_t*)(sc + SL.counters);
+  p.stats = (unsigned long long*)(sc + SL.stats);
+  CUDA_TRY(cudaMemsetAsync(p.counters, 0, 64, st));
+  CUDA_TRY(cudaMemsetAsync(p.stats, 0, 64, st));
+  int dev = 0, n_sm = 148;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  if (bin_hi > bin_lo) {
+    rc = p.time_mode ? launch_reduce<true>(p, n_sm, st) : launch_reduce<false>(p, n_sm, st);
+    if (rc) return rc;
+  }
+  if (stats_host) {
+    unsigned long long h[3];
+    CUDA_TRY(cudaMemcpyAsync(h, p.stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    stats_host->distinct = (int64_t)h[0];
+    stats_host->pair_checksum = (int64_t)h[1];
+    stats_host->table_overflow = (int64_t)h[2];
+    if (h[2]) {
+      otto_set_error("a shared-memory hash table overflowed; lower split_ub");
+      return OTTO_EOVERFLOW;
+    }
+  }
+  return OTTO_OK;
+}
+
+// ------------------------------------------------------------------ one-shot build
+
+extern "C" int otto_covisit_build(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                                  int64_t workspace_bytes, const OttoTopK* out, OttoBuildStats* stats_host,
+                                  void* stream) {
+  OttoBuildStats local;
+  memset(&local, 0, sizeof(local));
+  OttoBuildStats* stp = stats_host ? stats_host : &local;
+  int rc = otto_covisit_count(ev, spec, workspace, workspace_bytes, stp, stream);
+  if (rc) return rc;
+  const Layout L = make_layout(ev->n_sessions, ev->n_events, spec);
+  const ScratchLayout SL = make_scratch(spec->k, stp->bins, L.A);
+  const int64_t rec_at = align_up(L.total, 256);
+  const int64_t scratch_at = align_up(rec_at + stp->pairs * 8, 256);
+  const int64_t need = scratch_at + SL.total;
+  if (workspace_bytes < need) {
+    otto_set_error("workspace too small for %lld pair records: need %lld bytes", (long long)stp->pairs, (long long)need);
+    return OTTO_ENOSPC;
+  }
+  char* ws = (char*)workspace;
+  if ((rc = otto_covisit_scatter(ev, spec, workspace, workspace_bytes, ws + rec_at, stp->pairs, stream))) return rc;
+  OttoPairSegment seg;
+  seg.records = ws + rec_at;
+  seg.offsets = WS(uint64_t, bin_off);
+  return otto_covisit_reduce(spec, WS(uint32_t, bin_base), WS(uint32_t, bin_x), 0, stp->bins, 0, spec->n_aids, &seg, 1,
+                             ws + scratch_at, SL.total, out, stp, stream);
+}
+
+// bytes otto_covisit_build needs once the pair count is known
+extern "C" int64_t otto_covisit_build_bytes(int64_t n_sessions, int64_t n_events, const OttoCovisitSpec* spec,
+                                            int64_t pairs, int64_t bins) {
+  if (check_spec(spec)) return -1;
+  const Layout L = make_layout(n_sessions, n_events, spec);
+  const ScratchLayout SL = make_scratch(spec->k, bins, L.A);
+  return align_up(align_up(L.total, 256) + pairs * 8, 256) + SL.total;
+}
+
+// ------------------------------------------------------------------ table <-> file rows
+
+__global__ void len_to_i64_kernel(const int32_t* __restrict__ len, int64_t n, unsigned long long* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (unsigned long long)len[i];
+}
+
+extern "C" int otto_topk_row_offsets(const OttoTopK* table, int64_t* row_offsets, int64_t* n_rows_host, void* scratch,
+                                     int64_t scratch_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t A = table->n_aids;
+  if (scratch_bytes < scan_scratch_elems(A) * 8) { otto_set_error("scan scratch too small"); return OTTO_ENOSPC; }
+  len_to_i64_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(table->len, A, (unsigned long long*)row_offsets);
+  LAUNCH_CHECK();
+  int rc = exclusive_scan<unsigned long long, unsigned long long>((unsigned long long*)row_offsets, A,
+                                                                  (unsigned long long*)row_offsets,
+                                                                  (unsigned long long*)scratch, st);
+  if (rc) return rc;
+  if (n_rows_host) {
+    CUDA_TRY(cudaMemcpyAsync(n_rows_host, row_offsets + A, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return OTTO_OK;
+}
+
+__global__ void topk_to_rows_kernel(const int32_t* __restrict__ ty, const float* __restrict__ tw,
+                                    const int32_t* __restrict__ len, const int64_t* __restrict__ row_off, int64_t A, int k,
+                                    int32_t* __restrict__ ax, int32_t* __restrict__ ay, float* __restrict__ w) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A * k) return;
+  const int64_t x = i / k;
+  const int r = (int)(i % k);
+  if (r < len[x]) {
+    const int64_t at = row_off[x] + r;
+    ax[at] = (int32_t)x;
+    ay[at] = ty[i];
+    w[at] = tw[i];
+  }
+}
+
+extern "C" int otto_topk_to_rows(const OttoTopK* table, const int64_t* row_offsets, int32_t* aid_x, int32_t* aid_y,
+                                 float* wgt, void* stream) {
+  const int64_t n = (int64_t)table->n_aids * table->k;
+  topk_to_rows_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      table->aid_y, table->wgt, table->len, row_offsets, table->n_aids, table->k, aid_x, aid_y, wgt);
+  LAUNCH_CHECK();
+  return OTTO_OK;
+}
+
+// rows grouped by aid_x (any group order), ranked inside a group by file order
+__global__ void rows_to_topk_kernel(const int32_t* __restrict__ ax, const int32_t* __restrict__ ay,
+                                    const float* __restrict__ w, int64_t n, int32_t A, int k, int32_t* __restrict__ ty,
+                                    float* __restrict__ tw, int32_t* __restrict__ len) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t x = ax[i];
+  if (x < 0 || x >= A) return;
+  if (i > 0 && ax[i - 1] == x) return;  // only the first row of a group walks it
+  int r = 0;
+  for (int64_t j = i; j < n && ax[j] == x && r < k; ++j, ++r) {
+    ty[(int64_t)x * k + r] = ay[j];
+    if (tw) tw[(int64_t)x * k + r] = w ? w[j] : 0.f;
+  }
+  len[x] = r;
+}
+
+extern "C" int otto_rows_to_topk(const int32_t* aid_x, const int32_t* aid_y, const float* wgt, int64_t n_rows,
+                                 const OttoTopK* table, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = (int64_t)table->n_aids * table->k;
+  CUDA_TRY(cudaMemsetAsync(table->aid_y, 0xff, n * 4, st));
+  if (table->wgt) CUDA_TRY(cudaMemsetAsync(table->wgt, 0, n * 4, st));
+  CUDA_TRY(cudaMemsetAsync(table->len, 0, (int64_t)table->n_aids * 4, st));
+  if (n_rows > 0) {
+    rows_to_topk_kernel<<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(aid_x, aid_y, wgt, n_rows, table->n_aids,
+                                                                          table->k, table->aid_y, table->wgt, table->len);
+    LAUNCH_CHECK();
+  }
+  return OTTO_OK;
+}

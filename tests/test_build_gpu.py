@@ -1,0 +1,226 @@
+"""GPU parity tests of the covisitation build: CUDA path (through the C ABI) vs the pandas oracle."""
+import json
+import pathlib
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from oracle import covisit_oracle as co
+import parity_helpers as H
+
+pytestmark = pytest.mark.gpu
+GOLDEN = pathlib.Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def cv(native_lib):
+    from otto_multi_objective_recommender_system_b200 import covisit
+    return covisit
+
+
+def synth_frame(n_sessions, n_aids, seed=42, kind="train"):
+    from otto_multi_objective_recommender_system_b200 import synth
+    return synth.generate(synth.SynthSpec(kind, n_sessions, n_aids, seed=seed))
+
+
+def frame_from_df(df, n_aids=None):
+    from otto_multi_objective_recommender_system_b200.synth import EventFrame
+    return EventFrame.from_pandas(df, n_aids)
+
+
+def run_build(cv, frame, spec, exact=True):
+    csr = cv.ingest(frame, "desc", device="cuda:0")
+    table, stats = cv.build_topk(csr, spec, exact=exact)
+    got = table.to_pandas()
+    if exact:
+        ax = got["aid_x"].to_numpy()
+        # exact integer side outputs, same row order as to_rows()
+        mask = torch.arange(table.k, device="cuda:0")[None, :] < table.len[:, None]
+        got["cnt"] = table.cnt[mask].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+        got["tsum"] = table.tsum[mask].cpu().numpy()
+        assert len(ax) == int(mask.sum())
+    return got, stats, table
+
+
+def check_against_oracle(cv, frame, spec, what):
+    df = frame.to_pandas()
+    ospec = H.oracle_spec(spec)
+    got, stats, table = run_build(cv, frame, spec)
+    acc = co.accumulate(df, ospec, exact=True)
+    assert stats["pairs"] == int(acc["cnt"].sum()), f"{what}: pair count P"
+    assert stats["distinct"] == len(acc), f"{what}: distinct count D"
+    assert stats["table_overflow"] == 0
+    if spec.weight_mode == cv.N.WEIGHT_TIME:
+        # bit-exact on the integer accumulators and on the GPU's own weight definition ...
+        want = H.gpu_formula_topk(acc, ospec)
+        H.assert_int_table_equal(got, want, what + " (integer form)")
+        assert np.array_equal(got["cnt"].to_numpy(), want["cnt"].to_numpy()), what
+        assert np.array_equal(got["tsum"].to_numpy(), want["tsum"].to_numpy()), what
+        # ... and within 1e-5 of pandas' float32 running sums, top-K identical up to near-ties
+        H.assert_time_table_close(got, acc, spec.k, what)
+    else:
+        H.assert_int_table_equal(got, co.topk(acc, spec.k), what)
+    # table invariants
+    ln = table.len.cpu().numpy()
+    ay = table.aid_y.cpu().numpy()
+    assert ((ay >= 0).sum(axis=1) == ln).all(), f"{what}: padding"
+    return got, stats
+
+
+VARIANTS = ["CLICKS", "CARTS_ORDERS", "BUY2BUY"]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("shape", [(64, 40, 1), (3000, 500, 7), (20000, 3000, 42)])
+def test_build_matches_oracle(cv, variant, shape):
+    frame = synth_frame(shape[0], shape[1], seed=shape[2])
+    check_against_oracle(cv, frame, getattr(cv, variant), f"{variant} {shape}")
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_build_matches_committed_golden_vectors(cv, variant):
+    g = json.load(open(GOLDEN / "oracle_small.json"))
+    df = pd.DataFrame(g["frame"]).astype({"session": np.int32, "aid": np.int32, "ts": np.int32, "type": np.int8})
+    spec = getattr(cv, variant)
+    got, _, _ = run_build(cv, frame_from_df(df, 120), spec, exact=False)
+    w = g["tables"][{"CLICKS": "clicks", "CARTS_ORDERS": "carts_orders", "BUY2BUY": "buy2buy"}[variant]]
+    assert got["aid_x"].tolist() == w["aid_x"]
+    if variant == "CLICKS":
+        np.testing.assert_allclose(got["wgt"].to_numpy(), np.array(w["wgt"], np.float32), rtol=H.RTOL_TIME)
+    else:
+        assert got["aid_y"].tolist() == w["aid_y"]
+        assert got["wgt"].tolist() == w["wgt"]
+
+
+def test_session_747_fixture(cv):
+    ev = json.load(open(GOLDEN / "session_747.json"))["events"]
+    df = pd.DataFrame({"session": 747, "aid": [e["aid"] for e in ev], "ts": [e["ts"] for e in ev],
+                       "type": [e["type"] for e in ev]})
+    # remap the 7-digit aids to a dense range so the table stays small
+    ids = {a: i for i, a in enumerate(sorted(df["aid"].unique()))}
+    df["aid"] = df["aid"].map(ids)
+    frame = frame_from_df(df, len(ids))
+    for variant in VARIANTS:
+        got, stats = check_against_oracle(cv, frame, getattr(cv, variant), f"747 {variant}")
+    got, stats, _ = run_build(cv, frame, cv.CLICKS)
+    assert stats["pairs"] == 204          # hand-derived in tests/test_oracle.py
+    got, stats, _ = run_build(cv, frame, cv.BUY2BUY)
+    assert stats["pairs"] == 6 and (got["wgt"] == 1.0).all()
+
+
+@pytest.mark.parametrize("split_ub", [16, 64, 1000])
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_split_rows_and_merge(cv, variant, split_ub):
+    """Small split_ub forces hot rows into aid_y-hash sub-bins and through the merge kernel."""
+    from dataclasses import replace
+    frame = synth_frame(4000, 300, seed=11)
+    spec = replace(getattr(cv, variant), split_ub=split_ub)
+    got, stats = check_against_oracle(cv, frame, spec, f"{variant} split_ub={split_ub}")
+    if split_ub <= 64 and variant != "BUY2BUY":
+        assert stats["split_rows"] > 0
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_hot_rows_large_bins_multipass(cv, variant):
+    """Few aids and many sessions: every row holds tens of thousands of records, which exercises the
+    block kernels and the multi-pass path (no split: split_ub is huge)."""
+    from dataclasses import replace
+    frame = synth_frame(30000, 24, seed=5)
+    spec = replace(getattr(cv, variant), split_ub=1 << 30)
+    check_against_oracle(cv, frame, spec, f"{variant} hot rows")
+
+
+def test_edge_sessions(cv):
+    """Lengths 1, 2, 30, 31, 32, 33, 500; ts ties across the tail boundary; window edge |dt| == W."""
+    rng = np.random.default_rng(0)
+    rows = []
+    sid = 0
+    for length in [1, 2, 30, 31, 32, 33, 64, 500, 1, 29, 30, 31]:
+        ts = np.sort(rng.integers(1659304800, 1659304800 + 3 * 86400, size=length))
+        if length >= 31:
+            ts[-31:-28] = ts[-30]        # a tie run straddling the 30-event cut
+        aid = rng.integers(0, 50, size=length)
+        typ = rng.choice([0, 1, 2], size=length, p=[0.6, 0.25, 0.15])
+        rows += [(sid, a, t, y) for a, t, y in zip(aid, ts, typ)]
+        sid += 1
+    # window edge: two events exactly 86400 s apart (out) and 86399 s apart (in)
+    rows += [(sid, 1, 1659400000, 0), (sid, 2, 1659400000 + 86400, 0)]
+    rows += [(sid + 1, 3, 1659400000, 1), (sid + 1, 4, 1659400000 + 86399, 2)]
+    # all events share one ts and one aid appears many times
+    rows += [(sid + 2, a, 1659500000, 1) for a in [5, 6, 5, 7, 5, 6, 8] * 6]
+    df = pd.DataFrame(rows, columns=["session", "aid", "ts", "type"])
+    frame = frame_from_df(df, 50)
+    for variant in VARIANTS:
+        check_against_oracle(cv, frame, getattr(cv, variant), f"edge {variant}")
+
+
+def test_generic_spec_type_masks(cv):
+    """x_types / y_types pair filters of the generic CovisitSpec (unpinned stems such as click_cart)."""
+    from dataclasses import replace
+    frame = synth_frame(3000, 200, seed=21)
+    spec = replace(cv.CARTS_ORDERS, x_types=(0,), y_types=(1, 2), k=10)
+    check_against_oracle(cv, frame, spec, "x=clicks y=carts/orders")
+    spec = replace(cv.CLICKS, event_types=(0, 1), tail_n=12, window_s=3600, k=7)
+    check_against_oracle(cv, frame, spec, "clicks+carts tail 12 1h")
+
+
+def test_empty_and_tiny_inputs(cv):
+    df = pd.DataFrame({"session": [5], "aid": [3], "ts": [1659304800], "type": [0]})
+    got, stats, table = run_build(cv, frame_from_df(df, 8), cv.CLICKS)
+    assert len(got) == 0 and stats["pairs"] == 0 and int(table.len.sum()) == 0
+    # buy2buy on a frame without carts/orders: every tail is empty
+    df = pd.DataFrame({"session": [1, 1, 2, 2], "aid": [1, 2, 3, 4], "ts": [1659304800 + i for i in range(4)], "type": [0] * 4})
+    got, stats, _ = run_build(cv, frame_from_df(df, 8), cv.BUY2BUY)
+    assert len(got) == 0 and stats["tail_events"] == 0
+
+
+def test_ingest_desc_order_matches_stable_sort(cv):
+    frame = synth_frame(5000, 400, seed=9)
+    df = frame.to_pandas()
+    want = df.sort_values(["session", "ts"], ascending=[True, False], kind="stable").reset_index(drop=True)
+    csr = cv.ingest(frame, "desc", device="cuda:0")
+    assert np.array_equal(csr.aid.cpu().numpy(), want["aid"].to_numpy())
+    assert np.array_equal(csr.ts.cpu().numpy(), want["ts"].to_numpy())
+    assert np.array_equal(csr.type.cpu().numpy(), want["type"].to_numpy().astype(np.uint8))
+    # shuffled input is sorted first (stable by (session, ts)): same CSR as sorting on the host
+    perm = np.random.default_rng(1).permutation(len(df))
+    sh = df.iloc[perm].reset_index(drop=True)
+    want2 = sh.sort_values(["session", "ts"], kind="stable").sort_values(["session", "ts"], ascending=[True, False], kind="stable")
+    csr2 = cv.ingest(frame_from_df(sh, 400), "desc", device="cuda:0")
+    assert np.array_equal(csr2.aid.cpu().numpy(), want2["aid"].to_numpy())
+
+
+def test_build_is_deterministic(cv):
+    frame = synth_frame(8000, 800, seed=2)
+    csr = cv.ingest(frame, "desc", device="cuda:0")
+    a, _ = cv.build_topk(csr, cv.CLICKS, exact=True)
+    b, _ = cv.build_topk(csr, cv.CLICKS, exact=True)
+    for f in ("aid_y", "wgt", "len"):
+        assert torch.equal(getattr(a, f), getattr(b, f)), f
+
+
+def test_rows_round_trip(cv):
+    frame = synth_frame(2000, 300, seed=4)
+    csr = cv.ingest(frame, "desc", device="cuda:0")
+    t, _ = cv.build_topk(csr, cv.CARTS_ORDERS)
+    ax, ay, w = t.to_rows()
+    t2 = cv.TopKTable.from_rows(ax, ay, w, t.n_aids, t.k)
+    assert torch.equal(t.len, t2.len) and torch.equal(t.aid_y, t2.aid_y)
+    m = t.aid_y >= 0
+    assert torch.equal(t.wgt[m], t2.wgt[m])
+
+
+def test_linearity_over_session_halves(cv):
+    """P(all) = P(first half) + P(second half): sessions are independent (size-independent property)."""
+    frame = synth_frame(6000, 500, seed=13)
+    csr = cv.ingest(frame, "desc", device="cuda:0")
+    half = csr.n_sessions // 2
+    stats = []
+    for part in (csr, csr.slice_sessions(0, half), csr.slice_sessions(half, csr.n_sessions)):
+        b = cv.CovisitBuilder(part, cv.CARTS_ORDERS)
+        b.build()
+        stats.append(b.stats.as_dict())
+    assert stats[0]["pairs"] == stats[1]["pairs"] + stats[2]["pairs"]
+    assert stats[0]["pair_checksum"] == stats[1]["pair_checksum"] + stats[2]["pair_checksum"]
