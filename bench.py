@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Benchmark of the covisitation hot path (contract: see README / DESIGN.md §Measurement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--scale F] [--variant clicks|carts_orders|buy2buy]
+  python bench.py --impl reference ...     # the CPU path (pandas oracle port) on the box's host cores
+
+A step = one full build of one covisitation matrix (tail CSR -> pair-gen -> scatter -> accumulate ->
+top-K) over the whole synthetic OTTO-shaped event CSR, already resident in HBM.  `value` = events / s.
+`e2e` = the same metric through the public API from pinned HOST frame columns: H2D copy + ingest +
+build + D2H of the top-K rows inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "covisit_build_events_per_s"
+UNIT = "events/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of full OTTO scale (sessions and aids)")
+    ap.add_argument("--variant", default="clicks", choices=["clicks", "carts_orders", "buy2buy"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=float, default=0.01, help="fraction of full scale for the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--split-ub", type=int, default=0)
+    return ap.parse_args()
+
+
+def workload_name(args) -> str:
+    return (f"synthetic OTTO-shaped train frame at scale {args.scale:g} "
+            f"({args.variant} covisitation, tail 30, top-k per aid)")
+
+
+# ----------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False).name
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU arms
+
+def _oracle_spec(variant):
+    from oracle import covisit_oracle as co
+    return {"clicks": co.CLICKS, "carts_orders": co.CARTS_ORDERS, "buy2buy": co.BUY2BUY}[variant]
+
+
+def _cpu_chunk(args):
+    df, variant = args
+    from oracle import covisit_oracle as co
+    return co.accumulate(df, _oracle_spec(variant))
+
+
+def cpu_build(df, variant: str, workers: int):
+    """The pandas restatement (oracle port).  workers > 1: 100k-session chunks (the reference's chunk files)
+    accumulated in a process pool, then combined and cut to top-K, as the chunked builder does."""
+    from oracle import covisit_oracle as co
+    spec = _oracle_spec(variant)
+    if workers <= 1:
+        return co.build(df, spec)
+    import multiprocessing as mp
+    import numpy as np
+    sessions = np.sort(df["session"].unique())
+    per = max(1, -(-len(sessions) // workers))
+    parts = []
+    for lo in range(0, len(sessions), per):
+        ids = sessions[lo: lo + per]
+        parts.append((df.loc[(df["session"] >= ids[0]) & (df["session"] <= ids[-1])], variant))
+    with mp.get_context("fork").Pool(workers) as pool:
+        accs = pool.map(_cpu_chunk, parts)
+    acc = None
+    for a in accs:
+        s = a.set_index(["aid_x", "aid_y"])["wgt"]
+        acc = s if acc is None else acc.add(s, fill_value=0)
+    return co.topk(acc.astype("float32").reset_index(), spec.k)
+
+
+def cpu_baseline(args, workers: int) -> dict:
+    from otto_multi_objective_recommender_system_b200 import synth
+    frame = synth.generate(synth.SynthSpec.scaled("train", args.cpu_sample))
+    df = frame.to_pandas()
+    t0 = time.perf_counter()
+    cpu_build(df, args.variant, workers)
+    dt = time.perf_counter() - t0
+    return {"value": len(df) / dt, "unit": UNIT, "cores": workers, "kind": "port", "seconds": dt,
+            "sample": f"pandas oracle (oracle/covisit_oracle.py), {args.variant}, {args.cpu_sample:g} of full scale = "
+                      f"{len(df)} events, one build"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU path on the host cores.  The reference repo has no builder to run (SURVEY.md
+    §0.1), so this is the oracle port, with every host core, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from otto_multi_objective_recommender_system_b200 import synth
+    workers = os.cpu_count() or 1
+    frame = synth.generate(synth.SynthSpec.scaled("train", args.cpu_sample))
+    df = frame.to_pandas()
+    steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+    for _ in range(warmup):
+        cpu_build(df, args.variant, workers)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_build(df, args.variant, workers)
+    dt = (time.perf_counter() - t0) / steps
+    value = len(df) / dt
+    sample = (f"pandas oracle port, {workers} worker processes, {args.variant}, {args.cpu_sample:g} of full scale = "
+              f"{len(df)} events per step")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(args), "cpu_sample": args.cpu_sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ----------------------------------------------------------------------------- B200 arm
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    g.build()
+    from otto_multi_objective_recommender_system_b200 import _native as N
+    from otto_multi_objective_recommender_system_b200 import covisit, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = N.lib()
+    spec = {"clicks": covisit.CLICKS, "carts_orders": covisit.CARTS_ORDERS, "buy2buy": covisit.BUY2BUY}[args.variant]
+    if args.split_ub:
+        from dataclasses import replace
+        spec = replace(spec, split_ub=args.split_ub)
+
+    # ---- synthetic frame on the device (weak scaling: every rank holds `scale` of full OTTO) ----
+    sspec = synth.SynthSpec.scaled("train", args.scale, seed=42 + rank)
+    frame = synth.generate(sspec, device=dev)
+    csr = covisit.ingest(frame, "desc", device=dev)
+    E, S, A = csr.n_events, csr.n_sessions, csr.n_aids
+    builder = covisit.CovisitBuilder(csr, spec)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    phases = ["count_begin", "count_finish", "scatter", "reduce"]
+
+    def step(marks=None):
+        m = [ev() for _ in range(5)] if marks is not None else None
+        if m: m[0].record()
+        builder.count_begin()
+        if m: m[1].record()
+        builder.count_finish()
+        if m: m[2].record()
+        builder.scatter()
+        if m: m[3].record()
+        builder.reduce(sync=True)
+        if m: m[4].record()
+        if marks is not None:
+            marks.append(m)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    stats = builder.stats.as_dict()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.otto_launch_count()
+    marks = []
+    t_start, t_end = ev(), ev()
+    barrier()
+    t_start.record()
+    for _ in range(args.steps):
+        step(marks)
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (lib.otto_launch_count() - launches0) // max(1, args.steps)
+    ms_total = t_start.elapsed_time(t_end)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        ev_total = torch.tensor([E], device=dev, dtype=torch.int64)
+        dist.all_reduce(ev_total)
+        events_all = int(ev_total.item())
+    else:
+        events_all = E
+    ms_step = ms_total / args.steps
+    value = events_all / (ms_step * 1e-3)
+    phase_ms = {p: statistics.mean(m[i].elapsed_time(m[i + 1]) for m in marks) for i, p in enumerate(phases)}
+
+    # ---- roofline of the dominant phase (algorithmic bytes: DESIGN.md §Kernels) ----
+    E30, P, B, D = stats["tail_events"], stats["pairs"], stats["bins"], stats["distinct"]
+    K = spec.k
+    alg = {
+        "count_begin": 4 * (S + 1) + 9 * E30 + 4 * (S + 1) + 8 * E30,     # read offsets + tail events, write tail CSR
+        "count_finish": 4 * (S + 1) + 8 * E30 + 4 * E30,                  # read tail CSR, write winner masks
+        "scatter": 4 * (S + 1) + 12 * E30 + 8 * P,                        # read tail CSR + masks, write records
+        "reduce": 8 * P + 8 * (B + 1) + 8 * A * K + 4 * A,                # read records + offsets, write table
+    }
+    kernel_of = {"count_begin": "tail_copy_kernel", "count_finish": "pairgen_kernel<count>",
+                 "scatter": "pairgen_kernel<scatter>", "reduce": "reduce_{small,block}_kernel"}
+    peaks = {}
+    try:
+        peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    dom = max(phase_ms, key=phase_ms.get)
+    achieved = alg[dom] / (phase_ms[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": kernel_of[dom], "phase": dom, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes": alg[dom], "phase_ms": phase_ms,
+                "phase_gbs": {p: alg[p] / (phase_ms[p] * 1e-3) / 1e9 for p in phases},
+                "whole_build": {"algorithmic_bytes": sum(alg.values()),
+                                "achieved": sum(alg.values()) / (ms_step * 1e-3) / 1e9,
+                                "frac": sum(alg.values()) / (ms_step * 1e-3) / 1e9 / peak}}
+
+    # ---- end to end from pinned host columns ----
+    e2e = None
+    if args.e2e_steps > 0:
+        host = synth.EventFrame(*(t.cpu().pin_memory() for t in (frame.session, frame.aid, frame.ts, frame.type)),
+                                n_aids=A)
+        h2d = sum(t.numel() * t.element_size() for t in (host.session, host.aid, host.ts, host.type))
+        del frame
+        d2h = 0
+
+        def e2e_step():
+            nonlocal d2h
+            f = synth.EventFrame(host.session.to(dev, non_blocking=True), host.aid.to(dev, non_blocking=True),
+                                 host.ts.to(dev, non_blocking=True), host.type.to(dev, non_blocking=True), A)
+            c = covisit.ingest(f, "desc", device=dev)
+            b = covisit.CovisitBuilder(c, spec)
+            b.workspace = builder.workspace          # reuse device buffers, as a long-running service would
+            b.records, b.scratch, b.table = builder.records, builder.scratch, builder.table
+            t = b.build()
+            ax, ay, w = t.to_rows()
+            out = [x.cpu() for x in (ax, ay, w)]
+            d2h = sum(x.numel() * x.element_size() for x in out)
+            return out
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": events_all / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt * 1e3, "steps": args.e2e_steps}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu = cpu_baseline(args, 1)
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32/u64 accumulate, f32 weights", "data": "synthetic",
+            "config": {"workload": workload_name(args), "sessions": S, "events": E, "aids": A, "tail_events": E30,
+                       "pairs": P, "distinct_pairs": D, "bins": B, "split_rows": stats["split_rows"], "k": K,
+                       "l2": "inputs larger than L2 (event CSR and pair records are GBs)",
+                       "events_all_ranks": events_all},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -113,6 +113,8 @@ typedef struct {
 
 const char* otto_last_error(void);
 int otto_version(void);
+/* Kernels this library has launched so far in this process (bench.py reports the per-step delta). */
+uint64_t otto_launch_count(void);
 
 /* ---- ingest: frame columns -> CSR (replaces the sort + chunk writers of
  *      utilities/split_dataset_writer_parquet.py:13-33 and builder step 2) ---- */

@@ -73,6 +73,7 @@ P = C.POINTER
 _SIGNATURES = {
     "otto_last_error": (C.c_char_p, []),
     "otto_version": (C.c_int, []),
+    "otto_launch_count": (C.c_uint64, []),
     "otto_frame_is_sorted": (C.c_int, [vp, vp, i64, vp, P(i32), vp]),
     "otto_ingest_desc": (C.c_int, [vp, i64, vp, vp, vp, i64, vp, vp, vp, vp]),
     "otto_covisit_sizes": (C.c_int, [i64, i64, P(OttoCovisitSpec), P(OttoBuildSizes)]),

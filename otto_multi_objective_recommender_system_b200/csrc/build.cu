@@ -17,6 +17,8 @@ void otto_set_error(const char* fmt, ...) {
 }
 extern "C" const char* otto_last_error(void) { return g_error; }
 extern "C" int otto_version(void) { return 100; }
+unsigned long long g_otto_launches = 0;
+extern "C" uint64_t otto_launch_count(void) { return g_otto_launches; }
 
 // ------------------------------------------------------------------ ingest
 
@@ -418,7 +420,7 @@ static int set_smem(K kernel, size_t bytes) {
 template <bool TIME>
 static int launch_reduce(const ReduceParams& p, int n_sm, cudaStream_t st) {
   int rc;
-  constexpr size_t small_smem = (size_t)SMALL_WARPS * (32 * 8 * 2 + SMALL_SLOTS * 4 * 3 + 32 * 4);
+  constexpr size_t small_smem = (size_t)SMALL_WARPS * SMALL_PER_WARP;
   if ((rc = set_smem(reduce_small_kernel<TIME>, small_smem))) return rc;
   const int64_t n_bins = p.bin_hi - p.bin_lo;
   int64_t small_blocks = ceil_div(n_bins, SMALL_WARPS);

@@ -22,7 +22,12 @@ void otto_set_error(const char* fmt, ...);
     }                                                                                          \
   } while (0)
 
-#define LAUNCH_CHECK() CUDA_TRY(cudaGetLastError())
+extern unsigned long long g_otto_launches;   // kernels launched by this library (reported by bench.py)
+#define LAUNCH_CHECK()              \
+  do {                              \
+    ++g_otto_launches;              \
+    CUDA_TRY(cudaGetLastError());   \
+  } while (0)
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

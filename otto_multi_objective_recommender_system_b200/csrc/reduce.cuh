@@ -10,10 +10,17 @@
 //   time  wgt = float(count + 3 * tsum / (ts_max - ts_min))   (fp64 -> fp32)
 //   type / unit  wgt = float(sum)                               (exact below 2^24)
 // Selection key = (float bits of wgt) << 32 | ~aid_y, so a plain max implements (wgt desc, aid_y asc).
-// Three size classes share the code: a warp with a small table per bin, a 128-thread block, and a
-// 256-thread block that falls back to several aid_y-hash passes when a bin exceeds its table.
-// Slices of split rows write partial top-K lists; merge_split_rows() picks the final K (slices hold
-// disjoint aid_y, so the merge is a pure selection).
+//
+// Top-K selection (round-1 profile: K rounds of warp arg-max cost 46 warp-instructions per record at 8
+// active lanes).  Now: every thread takes the max key of its slots; the K-th largest of a warp's 32 lane
+// maxima is a lower bound T on the K-th largest key of the bin (>= K entries reach it); a second sweep
+// pushes the entries >= T (about 1.5 K of them) into a small candidate list that one warp rank-sorts.
+// If an adversarial layout overflows the list, the old exact K-round selection runs instead.
+//
+// Three size classes share the code: a warp with a 512-slot table per bin, a 128-thread block (2048
+// slots) and a 256-thread block (4096 slots) that falls back to several aid_y-hash passes when a bin
+// exceeds its table.  Slices of split rows write partial top-K lists; merge_split_rows() picks the final
+// K (slices hold disjoint aid_y, so the merge is a pure selection).
 #pragma once
 #include "common.cuh"
 
@@ -41,7 +48,7 @@ struct ReduceParams {
   uint32_t* list_m;
   uint32_t* list_l;
   uint32_t* counters;        // [0] n_m  [1] n_l  [2] next_m  [3] next_l
-  unsigned long long* stats; // [0] distinct  [1] checksum  [2] overflow
+  unsigned long long* stats; // [0] distinct  [1] checksum  [2] overflow  [3] slow-path selections
 };
 
 constexpr uint32_t SMALL_MAX = 256;    // records: warp kernel, 512-slot table
@@ -80,12 +87,8 @@ struct Table {
     for (uint32_t probe = 0; probe <= mask; ++probe) {
       const uint32_t prev = atomicCAS(&keys[h], KEY_EMPTY, y);
       if (prev == KEY_EMPTY || prev == y) {
-        if (TIME) {
-          atomicAdd(&cnt[h], 1u);
-          atomicAdd(&sum[h], (SumT)v);
-        } else {
-          atomicAdd(&sum[h], (SumT)v);
-        }
+        if (TIME) atomicAdd(&cnt[h], 1u);
+        atomicAdd(&sum[h], (SumT)v);
         return true;
       }
       h = (h + 1) & mask;
@@ -111,19 +114,42 @@ struct Cands {
   uint32_t* cnt;
 };
 
-// One warp selects the top k slots of table slots [lo, hi) into dst[0..k): entries come out best first.
-// Returns (warp-uniform) how many were found; also counts occupied slots and their payload into stats.
-template <bool TIME, typename SumT>
-__device__ __forceinline__ int warp_select_table(Table<TIME, SumT>& t, uint32_t lo, uint32_t hi, int k, double w_scale,
-                                                 Cands dst, int dst_base, uint32_t& n_occupied, uint64_t& payload) {
+// K-th largest of the 32 lane values (0 if fewer than k lanes are non-zero). Keys are distinct or 0.
+__device__ __forceinline__ uint64_t warp_kth_largest(uint64_t v, int k) {
   const uint32_t lane = lane_id();
+  int rank = 0;
+#pragma unroll 8
+  for (int l = 0; l < 32; ++l) {
+    const uint64_t o = shfl_u64(v, l);
+    rank += (o > v) || (o == v && l < (int)lane);
+  }
+  const uint32_t m = __ballot_sync(FULL_MASK, rank == k - 1);
+  return shfl_u64(v, __ffs(m) - 1);
+}
+
+// One warp: ranks the n_c candidates (distinct non-zero keys, unordered) and hands every candidate with
+// rank < k to `emit(rank, key, cnt, sum)`.  Returns min(n_c, k).
+template <typename Emit>
+__device__ __forceinline__ int warp_rank_emit(const Cands& c, int n_c, int k, Emit emit) {
+  const uint32_t lane = lane_id();
+  for (int i = lane; i < n_c; i += 32) {
+    const uint64_t mine = c.key[i];
+    int rank = 0;
+    for (int j = 0; j < n_c; ++j) rank += c.key[j] > mine;
+    if (rank < k) emit(rank, mine, c.cnt[i], c.sum[i]);
+  }
+  return n_c < k ? n_c : k;
+}
+
+// ---- exact K-round selection (slow path, kept for candidate-list overflow) ----
+template <bool TIME, typename SumT>
+__device__ __forceinline__ int warp_select_table_slow(Table<TIME, SumT>& t, uint32_t lo, uint32_t hi, uint32_t stride_lanes,
+                                                      int k, double w_scale, Cands dst, int dst_base) {
+  const uint32_t lane = lane_id();
+  (void)stride_lanes;
   uint64_t best = 0;
   uint32_t best_h = 0;
   for (uint32_t h = lo + lane; h < hi; h += 32) {
-    if (t.keys[h] != KEY_EMPTY) {
-      ++n_occupied;
-      payload += TIME ? (uint64_t)t.cnt[h] : (uint64_t)t.sum[h];
-    }
     const uint64_t kk = t.key(h, w_scale);
     if (kk > best) { best = kk; best_h = h; }
   }
@@ -143,90 +169,79 @@ __device__ __forceinline__ int warp_select_table(Table<TIME, SumT>& t, uint32_t 
       }
     }
   }
-  for (int r = found + (int)lane; r < k; r += 32) dst.key[dst_base + r] = 0;
   __syncwarp();
   return found;
 }
 
-// One warp selects the top k of src[0..n_src) into dst[0..k); consumed src keys are zeroed.
-__device__ __forceinline__ int warp_select_cands(Cands src, int n_src, int k, Cands dst) {
-  const uint32_t lane = lane_id();
-  uint64_t best = 0;
-  int best_i = 0;
-  for (int i = lane; i < n_src; i += 32) {
-    const uint64_t kk = src.key[i];
-    if (kk > best) { best = kk; best_i = i; }
-  }
-  int found = 0;
-  for (; found < k; ++found) {
-    const uint64_t m = warp_max_u64(best);
-    if (m == 0) break;
-    if (best == m) {
-      dst.key[found] = m;
-      dst.sum[found] = src.sum[best_i];
-      dst.cnt[found] = src.cnt[best_i];
-      src.key[best_i] = 0;
-      best = 0;
-      for (int i = lane; i < n_src; i += 32) {
-        const uint64_t kk = src.key[i];
-        if (kk > best) { best = kk; best_i = i; }
-      }
-    }
-  }
-  for (int r = found + (int)lane; r < k; r += 32) dst.key[r] = 0;
-  __syncwarp();
-  return found;
+// Writes one finished entry of bin b: a table row (ordinary bin) or a partial list (slice of a split row).
+struct BinOut {
+  bool whole;      // ordinary bin: write the table row
+  int64_t row;     // x * k   or   slot * k
+  uint32_t x;
+};
+
+__device__ __forceinline__ BinOut bin_out(const ReduceParams& p, int64_t b) {
+  BinOut o;
+  o.x = p.bin_x[b];
+  const uint32_t bb0 = p.bin_base[o.x];
+  o.whole = (p.bin_base[o.x + 1] - bb0) == 1;
+  o.row = o.whole ? (int64_t)o.x * p.k : partial_slot(p, o.x, (uint32_t)(b - bb0)) * p.k;
+  return o;
 }
 
-// Writes a finished bin: a table row (ordinary bin) or a partial list (slice of a split row).
-__device__ __forceinline__ void warp_emit(const ReduceParams& p, int64_t b, Cands c, int found) {
-  const uint32_t lane = lane_id();
-  const uint32_t x = p.bin_x[b];
-  const uint32_t bb0 = p.bin_base[x];
-  const uint32_t nbx = p.bin_base[x + 1] - bb0;
-  if (nbx == 1) {
-    const int64_t row = (int64_t)x * p.k;
-    for (int r = lane; r < p.k; r += 32) {
-      const bool ok = r < found;
-      const uint64_t kk = ok ? c.key[r] : 0;
-      p.out_y[row + r] = ok ? (int32_t)(~(uint32_t)kk) : -1;
-      p.out_w[row + r] = ok ? __uint_as_float((uint32_t)(kk >> 32)) : 0.f;
-      if (p.out_cnt) p.out_cnt[row + r] = ok ? c.cnt[r] : 0u;
-      if (p.out_tsum) p.out_tsum[row + r] = ok ? c.sum[r] : 0ull;
-    }
-    if (lane == 0) p.out_len[x] = found;
+__device__ __forceinline__ void emit_entry(const ReduceParams& p, const BinOut& o, int r, uint64_t kk, uint32_t cnt,
+                                           uint64_t sum) {
+  if (o.whole) {
+    p.out_y[o.row + r] = (int32_t)(~(uint32_t)kk);
+    p.out_w[o.row + r] = __uint_as_float((uint32_t)(kk >> 32));
+    if (p.out_cnt) p.out_cnt[o.row + r] = cnt;
+    if (p.out_tsum) p.out_tsum[o.row + r] = sum;
   } else {
-    const int64_t slot = partial_slot(p, x, (uint32_t)(b - bb0));
-    for (int r = lane; r < found; r += 32) {
-      p.p_key[slot * p.k + r] = c.key[r];
-      p.p_sum[slot * p.k + r] = c.sum[r];
-      p.p_cnt[slot * p.k + r] = c.cnt[r];
+    p.p_key[o.row + r] = kk;
+    p.p_sum[o.row + r] = sum;
+    p.p_cnt[o.row + r] = cnt;
+  }
+}
+
+// pads the row beyond `found` and stores the length (one warp)
+__device__ __forceinline__ void emit_finish(const ReduceParams& p, const BinOut& o, int found) {
+  const uint32_t lane = lane_id();
+  if (o.whole) {
+    for (int r = found + (int)lane; r < p.k; r += 32) {
+      p.out_y[o.row + r] = -1;
+      p.out_w[o.row + r] = 0.f;
+      if (p.out_cnt) p.out_cnt[o.row + r] = 0u;
+      if (p.out_tsum) p.out_tsum[o.row + r] = 0ull;
     }
-    if (lane == 0) p.p_len[slot] = found;
+    if (lane == 0) p.out_len[o.x] = found;
+  } else if (lane == 0) {
+    p.p_len[o.row / p.k] = found;
   }
 }
 
 // ---- small bins: one warp per bin ----
 constexpr int SMALL_WARPS = 8;
 constexpr uint32_t SMALL_SLOTS = 512;
+constexpr int SMALL_CANDS = 96;
+// per warp: cand key[96] sum[96] (u64) | table sum[512] keys[512] cnt[512] (u32) | cand cnt[96] | counter
+constexpr uint32_t SMALL_PER_WARP = SMALL_CANDS * 16 + SMALL_SLOTS * 12 + SMALL_CANDS * 4 + 16;
 
 template <bool TIME>
 __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const ReduceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  // per-warp carve: cand key[32] sum[32] (u64), table sum[512] keys[512] cnt[512] cand cnt[32] (u32)
-  constexpr uint32_t PER_WARP = 32 * 8 * 2 + SMALL_SLOTS * 4 * 3 + 32 * 4;
-  unsigned char* base = smem_raw + warp * PER_WARP;
+  unsigned char* base = smem_raw + warp * SMALL_PER_WARP;
   Cands c;
   c.key = (uint64_t*)base;
-  c.sum = c.key + 32;
+  c.sum = c.key + SMALL_CANDS;
   Table<TIME, uint32_t> t;
-  t.sum = (uint32_t*)(c.sum + 32);
+  t.sum = (uint32_t*)(c.sum + SMALL_CANDS);
   t.keys = t.sum + SMALL_SLOTS;
   t.cnt = t.keys + SMALL_SLOTS;
   c.cnt = t.cnt + SMALL_SLOTS;
+  uint32_t* n_cand = c.cnt + SMALL_CANDS;
 
-  uint32_t st_occ = 0;
+  uint32_t st_occ = 0, st_slow = 0;
   uint64_t st_pay = 0;
   bool overflow = false;
   const int64_t n_warps = (int64_t)gridDim.x * SMALL_WARPS;
@@ -239,14 +254,16 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const Re
       }
       continue;
     }
+    const BinOut o = bin_out(p, b);
     if (n == 0) {
-      warp_emit(p, b, c, 0);
+      emit_finish(p, o, 0);
       continue;
     }
     uint32_t slots = 32;
     while (slots < 2 * n) slots <<= 1;
     t.mask = slots - 1;
     t.clear(lane, 32);
+    if (lane == 0) *n_cand = 0;
     __syncwarp();
     for (int s = 0; s < p.n_seg; ++s) {
       const uint64_t o0 = p.seg[s].offsets[0];
@@ -258,29 +275,67 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const Re
       }
     }
     __syncwarp();
-    const int found = warp_select_table<TIME, uint32_t>(t, 0, slots, p.k, p.w_scale, c, 0, st_occ, st_pay);
-    warp_emit(p, b, c, found);
+    // sweep 1: lane maxima -> threshold
+    uint64_t best = 0;
+    for (uint32_t h = lane; h < slots; h += 32) {
+      if (t.keys[h] != KEY_EMPTY) {
+        ++st_occ;
+        st_pay += TIME ? (uint64_t)t.cnt[h] : (uint64_t)t.sum[h];
+        const uint64_t kk = t.key(h, p.w_scale);
+        best = kk > best ? kk : best;
+      }
+    }
+    const uint64_t thr = warp_kth_largest(best, p.k);
+    // sweep 2: candidates
+    for (uint32_t h = lane; h < slots; h += 32) {
+      if (t.keys[h] != KEY_EMPTY) {
+        const uint64_t kk = t.key(h, p.w_scale);
+        if (kk >= thr) {
+          const uint32_t at = atomicAdd(n_cand, 1u);
+          if (at < SMALL_CANDS) {
+            c.key[at] = kk;
+            c.sum[at] = (uint64_t)t.sum[h];
+            c.cnt[at] = TIME ? t.cnt[h] : 0u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    int n_c = (int)*n_cand;
+    if (n_c > SMALL_CANDS) {  // adversarial layout: exact K-round selection straight from the table
+      ++st_slow;
+      n_c = warp_select_table_slow<TIME, uint32_t>(t, 0, slots, 32, p.k, p.w_scale, c, 0);
+    }
+    const int found = warp_rank_emit(c, n_c, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) {
+      emit_entry(p, o, r, kk, cnt, sum);
+    });
+    emit_finish(p, o, found);
     __syncwarp();
   }
   // one stats update per warp
-  for (int o = 16; o > 0; o >>= 1) {
-    st_occ += __shfl_xor_sync(FULL_MASK, st_occ, o);
-    st_pay += shfl_u64(st_pay, lane ^ o);
+  for (int off = 16; off > 0; off >>= 1) {
+    st_occ += __shfl_xor_sync(FULL_MASK, st_occ, off);
+    st_slow += __shfl_xor_sync(FULL_MASK, st_slow, off);
+    st_pay += shfl_u64(st_pay, lane ^ off);
   }
   if (lane == 0 && (st_occ || st_pay)) {
     atomicAdd(&p.stats[0], (unsigned long long)st_occ);
     atomicAdd(&p.stats[1], (unsigned long long)st_pay);
+    if (st_slow) atomicAdd(&p.stats[3], (unsigned long long)(st_slow / 32));
   }
   if (overflow) atomicOr(&p.stats[2], 1ull);
 }
 
 // ---- medium / large bins: one block per bin, work taken from a list through an atomic cursor ----
+constexpr int BLOCK_CANDS = 256;
+
 template <bool TIME, int THREADS, uint32_t SLOTS, typename SumT, bool LARGE>
 __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int WARPS = THREADS / 32;
-  constexpr int NC = (WARPS + 1) * OTTO_MAX_K;  // per-warp lists + the running best list
-  __shared__ uint32_t s_item;
+  constexpr int NC = BLOCK_CANDS + OTTO_MAX_K;     // candidates + room for the carried best list
+  __shared__ uint32_t s_item, s_ncand;
+  __shared__ uint64_t s_thr[WARPS];
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   // carve: cand key[NC] sum[NC] | best key[K] sum[K] (u64) | table sum | keys | cnt | cand cnt | best cnt
   Cands c, best;
@@ -297,7 +352,7 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
 
   const uint32_t* list = LARGE ? p.list_l : p.list_m;
   const uint32_t n_items = p.counters[LARGE ? 1 : 0];
-  uint32_t st_occ = 0;
+  uint32_t st_occ = 0, st_slow = 0;
   uint64_t st_pay = 0;
   bool overflow = false;
   while (true) {
@@ -315,9 +370,12 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
       if (slots > SLOTS) slots = SLOTS;
     }
     t.mask = slots - 1;
-    int n_best = 0;
+    const BinOut o = bin_out(p, b);
+    int n_best = 0;  // meaningful in warp 0
     for (uint32_t pass = 0; pass < n_pass; ++pass) {
+      const bool last = pass + 1 == n_pass;
       t.clear(threadIdx.x, THREADS);
+      if (threadIdx.x == 0) s_ncand = 0;
       __syncthreads();
       for (int s = 0; s < p.n_seg; ++s) {
         const uint64_t o0 = p.seg[s].offsets[0];
@@ -330,48 +388,107 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
         }
       }
       __syncthreads();
-      // each warp: top k of its slice of the table
-      const uint32_t per = slots / WARPS;
-      warp_select_table<TIME, SumT>(t, warp * per, (warp + 1) * per, p.k, p.w_scale, c, warp * OTTO_MAX_K, st_occ, st_pay);
-      // the running best of earlier passes joins as one more list
-      if (warp == 0) {
-        for (int r = lane; r < p.k; r += 32) {
-          const bool ok = r < n_best;
-          c.key[WARPS * OTTO_MAX_K + r] = ok ? best.key[r] : 0;
-          c.sum[WARPS * OTTO_MAX_K + r] = ok ? best.sum[r] : 0;
-          c.cnt[WARPS * OTTO_MAX_K + r] = ok ? best.cnt[r] : 0;
+      // sweep 1: thread maxima -> per-warp thresholds -> block threshold
+      uint64_t tbest = 0;
+      for (uint32_t h = threadIdx.x; h < slots; h += THREADS) {
+        if (t.keys[h] != KEY_EMPTY) {
+          ++st_occ;
+          st_pay += TIME ? (uint64_t)t.cnt[h] : (uint64_t)t.sum[h];
+          const uint64_t kk = t.key(h, p.w_scale);
+          tbest = kk > tbest ? kk : tbest;
+        }
+      }
+      const uint64_t wthr = warp_kth_largest(tbest, p.k);
+      if (lane == 0) s_thr[warp] = wthr;
+      __syncthreads();
+      uint64_t thr = 0;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) thr = s_thr[w] > thr ? s_thr[w] : thr;
+      // sweep 2: candidates
+      for (uint32_t h = threadIdx.x; h < slots; h += THREADS) {
+        if (t.keys[h] != KEY_EMPTY) {
+          const uint64_t kk = t.key(h, p.w_scale);
+          if (kk >= thr) {
+            const uint32_t at = atomicAdd(&s_ncand, 1u);
+            if (at < BLOCK_CANDS) {
+              c.key[at] = kk;
+              c.sum[at] = (uint64_t)t.sum[h];
+              c.cnt[at] = TIME ? t.cnt[h] : 0u;
+            }
+          }
         }
       }
       __syncthreads();
+      int n_c = (int)s_ncand;
+      if (n_c > BLOCK_CANDS) {
+        // adversarial layout: exact K-round selection per warp slice, lists land in c at warp * K
+        if (lane == 0 && warp == 0) ++st_slow;
+        const uint32_t per = slots / WARPS;
+        const int f = warp_select_table_slow<TIME, SumT>(t, warp * per, (warp + 1) * per, 32, p.k, p.w_scale, c,
+                                                         warp * OTTO_MAX_K);
+        for (int r = f + (int)lane; r < OTTO_MAX_K; r += 32) c.key[warp * OTTO_MAX_K + r] = 0;
+        __syncthreads();
+        // compact the non-zero keys to the front (one warp; WARPS * 32 <= BLOCK_CANDS)
+        if (warp == 0) {
+          int w = 0;
+          for (int i0 = 0; i0 < WARPS * OTTO_MAX_K; i0 += 32) {
+            const int i = i0 + lane;
+            const uint64_t kk = c.key[i];
+            const uint64_t ss = c.sum[i];
+            const uint32_t cc = c.cnt[i];
+            const uint32_t m = __ballot_sync(FULL_MASK, kk != 0);
+            __syncwarp();
+            if (kk != 0) {
+              const int at = w + __popc(m & lanemask_lt());
+              c.key[at] = kk; c.sum[at] = ss; c.cnt[at] = cc;
+            }
+            w += __popc(m);
+            __syncwarp();
+          }
+          n_c = w;
+        }
+      }
       if (warp == 0) {
-        // lists are OTTO_MAX_K apart but only k long: compact view via zero keys beyond k
-        for (int i = lane; i < NC; i += 32)
-          if ((i % OTTO_MAX_K) >= p.k) c.key[i] = 0;
+        n_c = __shfl_sync(FULL_MASK, n_c, 0);
+        // entries carried from earlier passes join the candidates
+        for (int r = lane; r < n_best; r += 32) {
+          c.key[n_c + r] = best.key[r];
+          c.sum[n_c + r] = best.sum[r];
+          c.cnt[n_c + r] = best.cnt[r];
+        }
         __syncwarp();
-        n_best = warp_select_cands(c, NC, p.k, best);
+        n_c += n_best;
+        if (last) {
+          const int found = warp_rank_emit(c, n_c, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) {
+            emit_entry(p, o, r, kk, cnt, sum);
+          });
+          emit_finish(p, o, found);
+        } else {
+          n_best = warp_rank_emit(c, n_c, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) {
+            best.key[r] = kk; best.sum[r] = sum; best.cnt[r] = cnt;
+          });
+          __syncwarp();
+        }
       }
       __syncthreads();
     }
-    if (warp == 0) {
-      n_best = __shfl_sync(FULL_MASK, n_best, 0);
-      warp_emit(p, b, best, n_best);
-    }
-    __syncthreads();
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    st_occ += __shfl_xor_sync(FULL_MASK, st_occ, o);
-    st_pay += shfl_u64(st_pay, lane ^ o);
+  for (int off = 16; off > 0; off >>= 1) {
+    st_occ += __shfl_xor_sync(FULL_MASK, st_occ, off);
+    st_slow += __shfl_xor_sync(FULL_MASK, st_slow, off);
+    st_pay += shfl_u64(st_pay, lane ^ off);
   }
   if (lane == 0 && (st_occ || st_pay)) {
     atomicAdd(&p.stats[0], (unsigned long long)st_occ);
     atomicAdd(&p.stats[1], (unsigned long long)st_pay);
+    if (st_slow) atomicAdd(&p.stats[3], (unsigned long long)st_slow);
   }
   if (overflow) atomicOr(&p.stats[2], 1ull);
 }
 
 template <bool TIME, int THREADS, uint32_t SLOTS, typename SumT>
 constexpr size_t reduce_block_smem() {
-  constexpr int NC = (THREADS / 32 + 1) * OTTO_MAX_K;
+  constexpr int NC = BLOCK_CANDS + OTTO_MAX_K;
   return (size_t)NC * 16 + OTTO_MAX_K * 16 + SLOTS * sizeof(SumT) + SLOTS * 4 + (TIME ? SLOTS * 4 : 0) + NC * 4 +
          OTTO_MAX_K * 4;
 }

@@ -108,6 +108,7 @@ static inline int exclusive_scan(const TIn* in, int64_t n, TOut* out, TOut* scra
   tile_sums<TIn, TOut><<<(unsigned)n_tiles, THREADS, 0, st>>>(in, n, scratch);
   scan_sums<TOut><<<1, THREADS, 0, st>>>(scratch, n_tiles);
   apply<TIn, TOut><<<(unsigned)n_tiles, THREADS, 0, st>>>(in, n, scratch, n_tiles, out);
+  g_otto_launches += 2;  // three kernels, one check
   LAUNCH_CHECK();
   return OTTO_OK;
 }
