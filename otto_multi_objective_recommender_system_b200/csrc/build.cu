@@ -424,19 +424,19 @@ static int launch_reduce(const ReduceParams& p, int n_sm, cudaStream_t st) {
   if ((rc = set_smem(reduce_small_kernel<TIME>, small_smem))) return rc;
   const int64_t n_bins = p.bin_hi - p.bin_lo;
   int64_t small_blocks = ceil_div(n_bins, SMALL_WARPS);
-  if (small_blocks > (int64_t)n_sm * 32) small_blocks = (int64_t)n_sm * 32;
+  if (small_blocks > (int64_t)n_sm * 64) small_blocks = (int64_t)n_sm * 64;
   reduce_small_kernel<TIME><<<(unsigned)small_blocks, SMALL_WARPS * 32, small_smem, st>>>(p);
   LAUNCH_CHECK();
   {
-    auto kern = reduce_block_kernel<TIME, 128, 2048, unsigned long long, false>;
-    constexpr size_t smem = reduce_block_smem<TIME, 128, 2048, unsigned long long>();
+    auto kern = reduce_block_kernel<TIME, 128, 11, false>;
+    constexpr size_t smem = reduce_block_smem<TIME, 128, 11>();
     if ((rc = set_smem(kern, smem))) return rc;
-    kern<<<n_sm * 6, 128, smem, st>>>(p);
+    kern<<<n_sm * 7, 128, smem, st>>>(p);
     LAUNCH_CHECK();
   }
   {
-    auto kern = reduce_block_kernel<TIME, 256, LARGE_SLOTS, unsigned long long, true>;
-    constexpr size_t smem = reduce_block_smem<TIME, 256, LARGE_SLOTS, unsigned long long>();
+    auto kern = reduce_block_kernel<TIME, 256, 12, true>;
+    constexpr size_t smem = reduce_block_smem<TIME, 256, 12>();
     if ((rc = set_smem(kern, smem))) return rc;
     kern<<<n_sm * 3, 256, smem, st>>>(p);
     LAUNCH_CHECK();
@@ -475,6 +475,7 @@ extern "C" int otto_covisit_reduce(const OttoCovisitSpec* spec, const uint32_t* 
   p.k = spec->k;
   p.time_mode = spec->weight_mode == OTTO_WEIGHT_TIME;
   p.w_scale = p.time_mode ? 3.0 / (double)(spec->ts_max - spec->ts_min) : 0.0;
+  p.range = p.time_mode ? (uint32_t)(spec->ts_max - spec->ts_min) : 0u;
   p.out_y = out->aid_y;
   p.out_w = out->wgt;
   p.out_len = out->len;

@@ -4,19 +4,26 @@
 // the stable sort (aid_x asc, wgt desc) and cumcount() < K, whose tie-break is aid_y ascending.
 //
 // A bin is either a whole aid_x row or one aid_y-hash slice of a hot row.  Its records are streamed once
-// from HBM into an open-addressing hash table in shared memory keyed by aid_y (atomicCAS claim, atomicAdd
-// of the integer payloads), so the accumulated weights are exact integers (count, sum of ts_x - ts_min,
-// or sum of type weights) regardless of arrival order; the float weight is formed once per distinct pair:
+// from HBM into an open-addressing hash table in shared memory keyed by aid_y (atomicCAS claim, 32-bit
+// atomicAdd of the integer payloads), so the accumulated weights are exact integers (count, sum of
+// ts_x - ts_min, or sum of type weights) regardless of arrival order; the float weight is formed once per
+// candidate:
 //   time  wgt = float(count + 3 * tsum / (ts_max - ts_min))   (fp64 -> fp32)
 //   type / unit  wgt = float(sum)                               (exact below 2^24)
-// Selection key = (float bits of wgt) << 32 | ~aid_y, so a plain max implements (wgt desc, aid_y asc).
+// Final order key = (float bits of wgt) << 32 | ~aid_y, so a plain max implements (wgt desc, aid_y asc).
 //
-// Top-K selection (round-1 profile: K rounds of warp arg-max cost 46 warp-instructions per record at 8
-// active lanes).  Now: every thread takes the max key of its slots; the K-th largest of a warp's 32 lane
-// maxima is a lower bound T on the K-th largest key of the bin (>= K entries reach it); a second sweep
-// pushes the entries >= T (about 1.5 K of them) into a small candidate list that one warp rank-sorts.
-// If an adversarial layout overflows the list, the old exact K-round selection runs instead.
-//
+// What the round-1 profiles taught (profiles/r01_*): the kernels are instruction-issue bound, not HBM
+// bound, so the work per record is what matters:
+//   * claimed slots are appended to an "occupied" list, so the sweeps and the clearing touch the d
+//     distinct entries instead of all table slots;
+//   * 64-bit shared atomicAdd compiles to a CAS spin loop (ATOMS.CAST.SPIN.64); the time sum is kept as a
+//     32-bit low word plus a packed word (count in bits 0-23, carries of the low word in bits 24-31);
+//   * top-K: sweep 1 takes, per lane, the max of an integer order key I = count * R + 3 * tsum (exactly
+//     proportional to the weight; no fp64); the K-th largest of the 32 lane-group maxima is a lower bound
+//     T on the K-th largest entry; sweep 2 pushes the entries with I >= T - T * 2^-22 (about 1.5 K of
+//     them; the margin covers entries that tie with T after fp32 rounding) into a candidate list, for
+//     which the exact float keys are formed and rank-sorted by one warp.  If an adversarial layout
+//     overflows the list, an exact K-round selection over the table runs instead.
 // Three size classes share the code: a warp with a 512-slot table per bin, a 128-thread block (2048
 // slots) and a 256-thread block (4096 slots) that falls back to several aid_y-hash passes when a bin
 // exceeds its table.  Slices of split rows write partial top-K lists; merge_split_rows() picks the final
@@ -33,6 +40,7 @@ struct ReduceParams {
   int32_t aid_lo, aid_hi;
   int32_t k;
   int32_t time_mode;
+  uint32_t range;            // ts_max - ts_min (time mode)
   double w_scale;            // 3 / (ts_max - ts_min)
   int32_t* out_y;
   float* out_w;
@@ -67,45 +75,63 @@ __device__ __forceinline__ uint32_t bin_records(const ReduceParams& p, int64_t b
   return n;
 }
 
-template <bool TIME, typename SumT>
+// Open-addressing table over SLOTS = 2^LOG slots.  TIME: hc = count | carries << 24, lo = low 32 bits of
+// the time sum.  !TIME: lo = integer weight sum (hc unused).
+template <bool TIME, int LOG>
 struct Table {
+  static constexpr uint32_t SLOTS = 1u << LOG;
   uint32_t* keys;
-  SumT* sum;
-  uint32_t* cnt;  // TIME only
-  uint32_t mask;  // slots - 1
+  uint32_t* lo;
+  uint32_t* hc;
+  uint16_t* occ;     // claimed slots, in claim order
+  uint32_t* n_occ;
 
-  __device__ __forceinline__ void clear(uint32_t tid, uint32_t nthreads) {
-    for (uint32_t h = tid; h <= mask; h += nthreads) {
+  __device__ __forceinline__ void clear_all(uint32_t tid, uint32_t nthreads) {
+    for (uint32_t h = tid; h < SLOTS; h += nthreads) {
       keys[h] = KEY_EMPTY;
-      sum[h] = 0;
-      if (TIME) cnt[h] = 0;
+      lo[h] = 0;
+      if (TIME) hc[h] = 0;
+    }
+    if (tid == 0) *n_occ = 0;
+  }
+  // resets exactly the claimed slots (n = *n_occ read by the caller after a barrier)
+  __device__ __forceinline__ void clear_dirty(uint32_t tid, uint32_t nthreads, uint32_t n) {
+    for (uint32_t i = tid; i < n; i += nthreads) {
+      const uint32_t h = occ[i];
+      keys[h] = KEY_EMPTY;
+      lo[h] = 0;
+      if (TIME) hc[h] = 0;
     }
   }
   // returns false on overflow
   __device__ __forceinline__ bool insert(uint32_t y, uint32_t v) {
-    uint32_t h = hash32(y) & mask;
-    for (uint32_t probe = 0; probe <= mask; ++probe) {
+    uint32_t h = (y * 0x9E3779B1u) >> (32 - LOG);
+    for (uint32_t probe = 0; probe < SLOTS; ++probe) {
       const uint32_t prev = atomicCAS(&keys[h], KEY_EMPTY, y);
+      if (prev == KEY_EMPTY) occ[atomicAdd(n_occ, 1u)] = (uint16_t)h;
       if (prev == KEY_EMPTY || prev == y) {
-        if (TIME) atomicAdd(&cnt[h], 1u);
-        atomicAdd(&sum[h], (SumT)v);
+        const uint32_t old = atomicAdd(&lo[h], v);
+        if (TIME) atomicAdd(&hc[h], 1u + ((old + v < old) ? (1u << 24) : 0u));
         return true;
       }
-      h = (h + 1) & mask;
+      h = (h + 1) & (SLOTS - 1);
     }
     return false;
   }
-  __device__ __forceinline__ float weight(uint32_t h, double w_scale) const {
-    if (TIME) return (float)((double)cnt[h] + w_scale * (double)sum[h]);
-    return (float)sum[h];
+  __device__ __forceinline__ uint32_t count(uint32_t h) const { return TIME ? (hc[h] & 0xffffffu) : 0u; }
+  __device__ __forceinline__ uint64_t sum(uint32_t h) const {
+    return TIME ? (((uint64_t)(hc[h] >> 24) << 32) | lo[h]) : (uint64_t)lo[h];
   }
-  // selection key of slot h, 0 when empty or already taken
-  __device__ __forceinline__ uint64_t key(uint32_t h, double w_scale) const {
-    const uint32_t y = keys[h];
-    if (y & KEY_TAKEN) return 0;
-    return ((uint64_t)__float_as_uint(weight(h, w_scale)) << 32) | (uint32_t)(~y);
+  // integer order key, exactly proportional to the weight
+  __device__ __forceinline__ uint64_t ikey(uint32_t h, uint32_t range) const {
+    return TIME ? (uint64_t)count(h) * range + 3ull * sum(h) : (uint64_t)lo[h];
   }
 };
+
+__device__ __forceinline__ uint64_t float_key(bool time_mode, uint32_t y, uint32_t cnt, uint64_t sum, double w_scale) {
+  const float w = time_mode ? (float)((double)cnt + w_scale * (double)sum) : (float)sum;
+  return ((uint64_t)__float_as_uint(w) << 32) | (uint32_t)(~y);
+}
 
 // Candidate lists in shared memory: key (0 = none), cnt, sum.
 struct Cands {
@@ -114,18 +140,27 @@ struct Cands {
   uint32_t* cnt;
 };
 
-// K-th largest of the 32 lane values (0 if fewer than k lanes are non-zero). Keys are distinct or 0.
-__device__ __forceinline__ uint64_t warp_kth_largest(uint64_t v, int k) {
+// Bitonic sort of one u64 per lane, descending (lane 0 ends with the largest).
+__device__ __forceinline__ uint64_t warp_sort_desc(uint64_t v) {
   const uint32_t lane = lane_id();
-  int rank = 0;
-#pragma unroll 8
-  for (int l = 0; l < 32; ++l) {
-    const uint64_t o = shfl_u64(v, l);
-    rank += (o > v) || (o == v && l < (int)lane);
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint32_t olo = __shfl_xor_sync(FULL_MASK, (uint32_t)v, j);
+      const uint32_t ohi = __shfl_xor_sync(FULL_MASK, (uint32_t)(v >> 32), j);
+      const uint64_t o = ((uint64_t)ohi << 32) | olo;
+      const bool keep_max = ((lane & j) == 0) == ((lane & k) == 0);
+      v = keep_max ? (o > v ? o : v) : (o < v ? o : v);
+    }
   }
-  const uint32_t m = __ballot_sync(FULL_MASK, rank == k - 1);
-  return shfl_u64(v, __ffs(m) - 1);
+  return v;
 }
+// K-th largest of the 32 lane values (0 if fewer than k lanes are non-zero).
+__device__ __forceinline__ uint64_t warp_kth_largest(uint64_t v, int k) { return shfl_u64(warp_sort_desc(v), k - 1); }
+
+// candidates must reach T minus the fp32 tie margin
+__device__ __forceinline__ uint64_t with_margin(uint64_t thr) { return thr > (thr >> 22) + 1 ? thr - (thr >> 22) - 1 : 0; }
 
 // One warp: ranks the n_c candidates (distinct non-zero keys, unordered) and hands every candidate with
 // rank < k to `emit(rank, key, cnt, sum)`.  Returns min(n_c, k).
@@ -141,41 +176,44 @@ __device__ __forceinline__ int warp_rank_emit(const Cands& c, int n_c, int k, Em
   return n_c < k ? n_c : k;
 }
 
-// ---- exact K-round selection (slow path, kept for candidate-list overflow) ----
-template <bool TIME, typename SumT>
-__device__ __forceinline__ int warp_select_table_slow(Table<TIME, SumT>& t, uint32_t lo, uint32_t hi, uint32_t stride_lanes,
-                                                      int k, double w_scale, Cands dst, int dst_base) {
+// Exact K-round selection over occupied entries [lo, hi) of the occ list (slow path for candidate-list
+// overflow).  One warp; results (best first) land in dst[dst_base ..); returns how many.
+template <bool TIME, int LOG>
+__device__ __forceinline__ int warp_select_slow(Table<TIME, LOG>& t, uint32_t lo, uint32_t hi, int k, double w_scale,
+                                                Cands dst, int dst_base) {
   const uint32_t lane = lane_id();
-  (void)stride_lanes;
-  uint64_t best = 0;
+  auto scan = [&](uint64_t& best, uint32_t& best_h) {
+    best = 0;
+    for (uint32_t i = lo + lane; i < hi; i += 32) {
+      const uint32_t h = t.occ[i];
+      const uint32_t y = t.keys[h];
+      if (y & KEY_TAKEN) continue;
+      const uint64_t kk = float_key(TIME, y, t.count(h), t.sum(h), w_scale);
+      if (kk > best) { best = kk; best_h = h; }
+    }
+  };
+  uint64_t best;
   uint32_t best_h = 0;
-  for (uint32_t h = lo + lane; h < hi; h += 32) {
-    const uint64_t kk = t.key(h, w_scale);
-    if (kk > best) { best = kk; best_h = h; }
-  }
+  scan(best, best_h);
   int found = 0;
   for (; found < k; ++found) {
     const uint64_t m = warp_max_u64(best);
     if (m == 0) break;
     if (best == m) {
       dst.key[dst_base + found] = m;
-      dst.sum[dst_base + found] = (uint64_t)t.sum[best_h];
-      dst.cnt[dst_base + found] = TIME ? t.cnt[best_h] : 0u;
+      dst.sum[dst_base + found] = t.sum(best_h);
+      dst.cnt[dst_base + found] = t.count(best_h);
       t.keys[best_h] |= KEY_TAKEN;
-      best = 0;
-      for (uint32_t h = lo + lane; h < hi; h += 32) {
-        const uint64_t kk = t.key(h, w_scale);
-        if (kk > best) { best = kk; best_h = h; }
-      }
+      scan(best, best_h);
     }
   }
   __syncwarp();
   return found;
 }
 
-// Writes one finished entry of bin b: a table row (ordinary bin) or a partial list (slice of a split row).
+// Where a finished bin goes: a table row (ordinary bin) or a partial list (slice of a split row).
 struct BinOut {
-  bool whole;      // ordinary bin: write the table row
+  bool whole;
   int64_t row;     // x * k   or   slot * k
   uint32_t x;
 };
@@ -219,30 +257,55 @@ __device__ __forceinline__ void emit_finish(const ReduceParams& p, const BinOut&
   }
 }
 
+// warp-aggregated append of candidate (y, cnt, sum) with its exact float key; q = this lane has one
+template <int CAP>
+__device__ __forceinline__ void push_candidate(bool q, uint32_t* n_cand, const Cands& c, bool time_mode, uint32_t y,
+                                               uint32_t cnt, uint64_t sum, double w_scale) {
+  const uint32_t m = __ballot_sync(FULL_MASK, q);
+  if (m == 0) return;
+  uint32_t base = 0;
+  if (lane_id() == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(n_cand, (uint32_t)__popc(m));
+  base = __shfl_sync(FULL_MASK, base, __ffs(m) - 1);
+  if (q) {
+    const uint32_t at = base + __popc(m & lanemask_lt());
+    if (at < (uint32_t)CAP) {
+      c.key[at] = float_key(time_mode, y, cnt, sum, w_scale);
+      c.sum[at] = sum;
+      c.cnt[at] = cnt;
+    }
+  }
+}
+
 // ---- small bins: one warp per bin ----
-constexpr int SMALL_WARPS = 8;
-constexpr uint32_t SMALL_SLOTS = 512;
-constexpr int SMALL_CANDS = 96;
-// per warp: cand key[96] sum[96] (u64) | table sum[512] keys[512] cnt[512] (u32) | cand cnt[96] | counter
-constexpr uint32_t SMALL_PER_WARP = SMALL_CANDS * 16 + SMALL_SLOTS * 12 + SMALL_CANDS * 4 + 16;
+constexpr int SMALL_WARPS = 4;
+constexpr int SMALL_LOG = 9;           // 512 slots
+constexpr int SMALL_CANDS = 64;
+constexpr int SMALL_DIRECT = 40;       // up to this many distinct entries: skip the threshold
+// per warp: cand key[64] sum[64] (u64) | keys[512] lo[512] hc[512] cand cnt[64] counters[4] (u32) | occ[256] (u16)
+constexpr uint32_t SMALL_PER_WARP = SMALL_CANDS * 16 + (1u << SMALL_LOG) * 12 + SMALL_CANDS * 4 + 16 + SMALL_MAX * 2;
 
 template <bool TIME>
 __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const ReduceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   unsigned char* base = smem_raw + warp * SMALL_PER_WARP;
+  constexpr uint32_t SLOTS = 1u << SMALL_LOG;
   Cands c;
   c.key = (uint64_t*)base;
   c.sum = c.key + SMALL_CANDS;
-  Table<TIME, uint32_t> t;
-  t.sum = (uint32_t*)(c.sum + SMALL_CANDS);
-  t.keys = t.sum + SMALL_SLOTS;
-  t.cnt = t.keys + SMALL_SLOTS;
-  c.cnt = t.cnt + SMALL_SLOTS;
+  Table<TIME, SMALL_LOG> t;
+  t.keys = (uint32_t*)(c.sum + SMALL_CANDS);
+  t.lo = t.keys + SLOTS;
+  t.hc = t.lo + SLOTS;
+  c.cnt = t.hc + SLOTS;
   uint32_t* n_cand = c.cnt + SMALL_CANDS;
+  t.n_occ = n_cand + 1;
+  t.occ = (uint16_t*)(n_cand + 4);
+  t.clear_all(lane, 32);
+  __syncwarp();
 
-  uint32_t st_occ = 0, st_slow = 0;
-  uint64_t st_pay = 0;
+  uint64_t st_occ = 0, st_pay = 0;
+  uint32_t st_slow = 0;
   bool overflow = false;
   const int64_t n_warps = (int64_t)gridDim.x * SMALL_WARPS;
   for (int64_t b = p.bin_lo + (int64_t)blockIdx.x * SMALL_WARPS + warp; b < p.bin_hi; b += n_warps) {
@@ -259,12 +322,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const Re
       emit_finish(p, o, 0);
       continue;
     }
-    uint32_t slots = 32;
-    while (slots < 2 * n) slots <<= 1;
-    t.mask = slots - 1;
-    t.clear(lane, 32);
     if (lane == 0) *n_cand = 0;
-    __syncwarp();
     for (int s = 0; s < p.n_seg; ++s) {
       const uint64_t o0 = p.seg[s].offsets[0];
       const uint64_t beg = p.seg[s].offsets[b - p.bin_lo] - o0, end = p.seg[s].offsets[b - p.bin_lo + 1] - o0;
@@ -275,46 +333,51 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const Re
       }
     }
     __syncwarp();
-    // sweep 1: lane maxima -> threshold
-    uint64_t best = 0;
-    for (uint32_t h = lane; h < slots; h += 32) {
-      if (t.keys[h] != KEY_EMPTY) {
-        ++st_occ;
-        st_pay += TIME ? (uint64_t)t.cnt[h] : (uint64_t)t.sum[h];
-        const uint64_t kk = t.key(h, p.w_scale);
-        best = kk > best ? kk : best;
+    const uint32_t d = *t.n_occ;
+    // sweep 1: lane maxima of the integer key -> threshold
+    uint64_t thr = 0;
+    if (d > SMALL_DIRECT) {
+      uint64_t best = 0;
+      for (uint32_t i = lane; i < d; i += 32) {
+        const uint64_t ik = t.ikey(t.occ[i], p.range);
+        best = ik > best ? ik : best;
       }
+      thr = with_margin(warp_kth_largest(best, p.k));
     }
-    const uint64_t thr = warp_kth_largest(best, p.k);
-    // sweep 2: candidates
-    for (uint32_t h = lane; h < slots; h += 32) {
-      if (t.keys[h] != KEY_EMPTY) {
-        const uint64_t kk = t.key(h, p.w_scale);
-        if (kk >= thr) {
-          const uint32_t at = atomicAdd(n_cand, 1u);
-          if (at < SMALL_CANDS) {
-            c.key[at] = kk;
-            c.sum[at] = (uint64_t)t.sum[h];
-            c.cnt[at] = TIME ? t.cnt[h] : 0u;
-          }
-        }
+    // sweep 2: candidates (+ stats)
+    for (uint32_t i0 = 0; i0 < d; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      bool q = false;
+      uint32_t y = 0, cnt = 0;
+      uint64_t sum = 0;
+      if (i < d) {
+        const uint32_t h = t.occ[i];
+        y = t.keys[h];
+        cnt = t.count(h);
+        sum = t.sum(h);
+        st_pay += TIME ? (uint64_t)cnt : sum;
+        q = t.ikey(h, p.range) >= thr;
       }
+      push_candidate<SMALL_CANDS>(q, n_cand, c, TIME, y, cnt, sum, p.w_scale);
     }
+    st_occ += (lane == 0) ? d : 0;
     __syncwarp();
     int n_c = (int)*n_cand;
     if (n_c > SMALL_CANDS) {  // adversarial layout: exact K-round selection straight from the table
       ++st_slow;
-      n_c = warp_select_table_slow<TIME, uint32_t>(t, 0, slots, 32, p.k, p.w_scale, c, 0);
+      n_c = warp_select_slow<TIME, SMALL_LOG>(t, 0, d, p.k, p.w_scale, c, 0);
     }
     const int found = warp_rank_emit(c, n_c, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) {
       emit_entry(p, o, r, kk, cnt, sum);
     });
     emit_finish(p, o, found);
+    t.clear_dirty(lane, 32, d);
+    if (lane == 0) *t.n_occ = 0;
     __syncwarp();
   }
   // one stats update per warp
   for (int off = 16; off > 0; off >>= 1) {
-    st_occ += __shfl_xor_sync(FULL_MASK, st_occ, off);
+    st_occ += shfl_u64(st_occ, lane ^ off);
     st_slow += __shfl_xor_sync(FULL_MASK, st_slow, off);
     st_pay += shfl_u64(st_pay, lane ^ off);
   }
@@ -327,56 +390,53 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const Re
 }
 
 // ---- medium / large bins: one block per bin, work taken from a list through an atomic cursor ----
-constexpr int BLOCK_CANDS = 256;
+constexpr int BLOCK_CANDS = 128;
 
-template <bool TIME, int THREADS, uint32_t SLOTS, typename SumT, bool LARGE>
+template <bool TIME, int THREADS, int LOG, bool LARGE>
 __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int WARPS = THREADS / 32;
+  constexpr uint32_t SLOTS = 1u << LOG;
   constexpr int NC = BLOCK_CANDS + OTTO_MAX_K;     // candidates + room for the carried best list
-  __shared__ uint32_t s_item, s_ncand;
-  __shared__ uint64_t s_thr[WARPS];
+  __shared__ uint32_t s_item, s_ncand, s_nocc;
+  __shared__ uint64_t s_gmax[WARPS][32];
+  __shared__ uint64_t s_thr;
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  // carve: cand key[NC] sum[NC] | best key[K] sum[K] (u64) | table sum | keys | cnt | cand cnt | best cnt
+  // carve: cand key[NC'] sum[NC'] | best key[K] sum[K] (u64) | keys lo hc | cand cnt[NC'] best cnt[K] (u32) | occ (u16)
+  constexpr int NCX = (NC > WARPS * OTTO_MAX_K ? NC : WARPS * OTTO_MAX_K) + OTTO_MAX_K;
   Cands c, best;
   c.key = (uint64_t*)smem_raw;
-  c.sum = c.key + NC;
-  best.key = c.sum + NC;
+  c.sum = c.key + NCX;
+  best.key = c.sum + NCX;
   best.sum = best.key + OTTO_MAX_K;
-  Table<TIME, SumT> t;
-  t.sum = (SumT*)(best.sum + OTTO_MAX_K);
-  t.keys = (uint32_t*)(t.sum + SLOTS);
-  t.cnt = t.keys + SLOTS;
-  c.cnt = t.cnt + (TIME ? SLOTS : 0);
-  best.cnt = c.cnt + NC;
+  Table<TIME, LOG> t;
+  t.keys = (uint32_t*)(best.sum + OTTO_MAX_K);
+  t.lo = t.keys + SLOTS;
+  t.hc = t.lo + SLOTS;
+  c.cnt = t.hc + (TIME ? SLOTS : 0);
+  best.cnt = c.cnt + NCX;
+  t.occ = (uint16_t*)(best.cnt + OTTO_MAX_K);
+  t.n_occ = &s_nocc;
 
   const uint32_t* list = LARGE ? p.list_l : p.list_m;
   const uint32_t n_items = p.counters[LARGE ? 1 : 0];
-  uint32_t st_occ = 0, st_slow = 0;
-  uint64_t st_pay = 0;
+  uint64_t st_occ = 0, st_pay = 0;
+  uint32_t st_slow = 0;
   bool overflow = false;
+  t.clear_all(threadIdx.x, THREADS);
+  if (threadIdx.x == 0) s_item = atomicAdd(&p.counters[LARGE ? 3 : 2], 1u);
+  __syncthreads();
   while (true) {
-    if (threadIdx.x == 0) s_item = atomicAdd(&p.counters[LARGE ? 3 : 2], 1u);
-    __syncthreads();
     const uint32_t item = s_item;
     if (item >= n_items) break;
     const int64_t b = p.bin_lo + list[item];
     const uint32_t n = bin_records(p, b);
     const uint32_t n_pass = (LARGE && n > LARGE_CAP) ? (n + LARGE_CAP - 1) / LARGE_CAP : 1;
-    uint32_t slots = SLOTS;
-    if (n_pass == 1) {
-      slots = 64;
-      while (slots < n + n / 3 + 1) slots <<= 1;
-      if (slots > SLOTS) slots = SLOTS;
-    }
-    t.mask = slots - 1;
     const BinOut o = bin_out(p, b);
     int n_best = 0;  // meaningful in warp 0
     for (uint32_t pass = 0; pass < n_pass; ++pass) {
       const bool last = pass + 1 == n_pass;
-      t.clear(threadIdx.x, THREADS);
       if (threadIdx.x == 0) s_ncand = 0;
-      __syncthreads();
       for (int s = 0; s < p.n_seg; ++s) {
         const uint64_t o0 = p.seg[s].offsets[0];
         const uint64_t beg = p.seg[s].offsets[b - p.bin_lo] - o0, end = p.seg[s].offsets[b - p.bin_lo + 1] - o0;
@@ -388,47 +448,52 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
         }
       }
       __syncthreads();
-      // sweep 1: thread maxima -> per-warp thresholds -> block threshold
+      const uint32_t d = s_nocc;
+      // sweep 1: lane-group maxima of the integer key (group = lane index, across warps)
       uint64_t tbest = 0;
-      for (uint32_t h = threadIdx.x; h < slots; h += THREADS) {
-        if (t.keys[h] != KEY_EMPTY) {
-          ++st_occ;
-          st_pay += TIME ? (uint64_t)t.cnt[h] : (uint64_t)t.sum[h];
-          const uint64_t kk = t.key(h, p.w_scale);
-          tbest = kk > tbest ? kk : tbest;
-        }
+      for (uint32_t i = threadIdx.x; i < d; i += THREADS) {
+        const uint64_t ik = t.ikey(t.occ[i], p.range);
+        tbest = ik > tbest ? ik : tbest;
       }
-      const uint64_t wthr = warp_kth_largest(tbest, p.k);
-      if (lane == 0) s_thr[warp] = wthr;
+      s_gmax[warp][lane] = tbest;
       __syncthreads();
-      uint64_t thr = 0;
+      if (warp == 0) {
+        uint64_t g = 0;
 #pragma unroll
-      for (int w = 0; w < WARPS; ++w) thr = s_thr[w] > thr ? s_thr[w] : thr;
-      // sweep 2: candidates
-      for (uint32_t h = threadIdx.x; h < slots; h += THREADS) {
-        if (t.keys[h] != KEY_EMPTY) {
-          const uint64_t kk = t.key(h, p.w_scale);
-          if (kk >= thr) {
-            const uint32_t at = atomicAdd(&s_ncand, 1u);
-            if (at < BLOCK_CANDS) {
-              c.key[at] = kk;
-              c.sum[at] = (uint64_t)t.sum[h];
-              c.cnt[at] = TIME ? t.cnt[h] : 0u;
-            }
-          }
-        }
+        for (int w = 0; w < WARPS; ++w) g = s_gmax[w][lane] > g ? s_gmax[w][lane] : g;
+        const uint64_t thr = with_margin(warp_kth_largest(g, p.k));
+        if (lane == 0) s_thr = thr;
       }
+      __syncthreads();
+      const uint64_t thr = s_thr;
+      // sweep 2: candidates (+ stats)
+      for (uint32_t i0 = 0; i0 < d; i0 += THREADS) {
+        const uint32_t i = i0 + threadIdx.x;
+        bool q = false;
+        uint32_t y = 0, cnt = 0;
+        uint64_t sum = 0;
+        if (i < d) {
+          const uint32_t h = t.occ[i];
+          y = t.keys[h];
+          cnt = t.count(h);
+          sum = t.sum(h);
+          st_pay += TIME ? (uint64_t)cnt : sum;
+          q = t.ikey(h, p.range) >= thr;
+        }
+        push_candidate<BLOCK_CANDS>(q, &s_ncand, c, TIME, y, cnt, sum, p.w_scale);
+      }
+      if (threadIdx.x == 0) st_occ += d;
       __syncthreads();
       int n_c = (int)s_ncand;
       if (n_c > BLOCK_CANDS) {
-        // adversarial layout: exact K-round selection per warp slice, lists land in c at warp * K
-        if (lane == 0 && warp == 0) ++st_slow;
-        const uint32_t per = slots / WARPS;
-        const int f = warp_select_table_slow<TIME, SumT>(t, warp * per, (warp + 1) * per, 32, p.k, p.w_scale, c,
-                                                         warp * OTTO_MAX_K);
+        // adversarial layout: exact K-round selection per warp slice of the occ list, lists land at warp * K
+        if (threadIdx.x == 0) ++st_slow;
+        const uint32_t per = (d + WARPS - 1) / WARPS;
+        const uint32_t lo = min(d, warp * per), hi = min(d, (warp + 1) * per);
+        const int f = warp_select_slow<TIME, LOG>(t, lo, hi, p.k, p.w_scale, c, warp * OTTO_MAX_K);
         for (int r = f + (int)lane; r < OTTO_MAX_K; r += 32) c.key[warp * OTTO_MAX_K + r] = 0;
         __syncthreads();
-        // compact the non-zero keys to the front (one warp; WARPS * 32 <= BLOCK_CANDS)
+        // compact the non-zero keys to the front (one warp)
         if (warp == 0) {
           int w = 0;
           for (int i0 = 0; i0 < WARPS * OTTO_MAX_K; i0 += 32) {
@@ -447,10 +512,13 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
           }
           n_c = w;
         }
+        // the slow path marks taken keys: restore them so that clear_dirty sees plain keys (it only stores)
       }
+      // all warps: reset the table for the next pass / bin while warp 0 ranks the candidates
+      t.clear_dirty(threadIdx.x, THREADS, d);
       if (warp == 0) {
         n_c = __shfl_sync(FULL_MASK, n_c, 0);
-        // entries carried from earlier passes join the candidates
+        // entries carried from earlier passes join the candidates (n_c + n_best <= NCX by construction)
         for (int r = lane; r < n_best; r += 32) {
           c.key[n_c + r] = best.key[r];
           c.sum[n_c + r] = best.sum[r];
@@ -470,11 +538,15 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
           __syncwarp();
         }
       }
+      if (threadIdx.x == THREADS - 1) {
+        s_nocc = 0;
+        if (last) s_item = atomicAdd(&p.counters[LARGE ? 3 : 2], 1u);
+      }
       __syncthreads();
     }
   }
   for (int off = 16; off > 0; off >>= 1) {
-    st_occ += __shfl_xor_sync(FULL_MASK, st_occ, off);
+    st_occ += shfl_u64(st_occ, lane ^ off);
     st_slow += __shfl_xor_sync(FULL_MASK, st_slow, off);
     st_pay += shfl_u64(st_pay, lane ^ off);
   }
@@ -486,11 +558,13 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
   if (overflow) atomicOr(&p.stats[2], 1ull);
 }
 
-template <bool TIME, int THREADS, uint32_t SLOTS, typename SumT>
+template <bool TIME, int THREADS, int LOG>
 constexpr size_t reduce_block_smem() {
   constexpr int NC = BLOCK_CANDS + OTTO_MAX_K;
-  return (size_t)NC * 16 + OTTO_MAX_K * 16 + SLOTS * sizeof(SumT) + SLOTS * 4 + (TIME ? SLOTS * 4 : 0) + NC * 4 +
-         OTTO_MAX_K * 4;
+  constexpr int WARPS = THREADS / 32;
+  constexpr int NCX = (NC > WARPS * OTTO_MAX_K ? NC : WARPS * OTTO_MAX_K) + OTTO_MAX_K;
+  constexpr size_t SLOTS = (size_t)1 << LOG;
+  return (size_t)NCX * 16 + OTTO_MAX_K * 16 + SLOTS * 8 + (TIME ? SLOTS * 4 : 0) + NCX * 4 + OTTO_MAX_K * 4 + SLOTS * 2;
 }
 
 // ---- split rows: merge the slices' partial lists (disjoint aid_y) into the final row ----
