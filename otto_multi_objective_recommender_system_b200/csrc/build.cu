@@ -85,7 +85,7 @@ struct Layout {
   int64_t tail_off, tail_aw, tail_ts, winmask, pair_ub, bin_base, bin_x, hist, bin_off, cursor, scan, stats, total;
 };
 
-static int32_t effective_split_ub(const OttoCovisitSpec* spec) { return spec->split_ub > 0 ? spec->split_ub : 32768; }
+static int32_t effective_split_ub(const OttoCovisitSpec* spec) { return spec->split_ub > 0 ? spec->split_ub : 8192; }
 
 static int check_spec(const OttoCovisitSpec* spec) {
   if (!spec) { otto_set_error("spec is NULL"); return OTTO_EINVAL; }

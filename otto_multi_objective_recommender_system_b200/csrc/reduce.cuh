@@ -103,20 +103,24 @@ struct Table {
       if (TIME) hc[h] = 0;
     }
   }
-  // returns false on overflow
+  // returns false on overflow.  The probe loop only finds / claims the slot; the payload atomics run after
+  // the warp has reconverged (profile r01_v3: with the payload inside the loop every probe iteration
+  // executed it for ~4 lanes at a time).
   __device__ __forceinline__ bool insert(uint32_t y, uint32_t v) {
     uint32_t h = (y * 0x9E3779B1u) >> (32 - LOG);
+    int state = 0;  // 1 = found, 2 = claimed a fresh slot
     for (uint32_t probe = 0; probe < SLOTS; ++probe) {
       const uint32_t prev = atomicCAS(&keys[h], KEY_EMPTY, y);
-      if (prev == KEY_EMPTY) occ[atomicAdd(n_occ, 1u)] = (uint16_t)h;
-      if (prev == KEY_EMPTY || prev == y) {
-        const uint32_t old = atomicAdd(&lo[h], v);
-        if (TIME) atomicAdd(&hc[h], 1u + ((old + v < old) ? (1u << 24) : 0u));
-        return true;
-      }
+      if (prev == KEY_EMPTY) { state = 2; break; }
+      if (prev == y) { state = 1; break; }
       h = (h + 1) & (SLOTS - 1);
     }
-    return false;
+    if (state == 2) occ[atomicAdd(n_occ, 1u)] = (uint16_t)h;
+    if (state != 0) {
+      const uint32_t old = atomicAdd(&lo[h], v);
+      if (TIME) atomicAdd(&hc[h], 1u + ((old + v < old) ? (1u << 24) : 0u));
+    }
+    return state != 0;
   }
   __device__ __forceinline__ uint32_t count(uint32_t h) const { return TIME ? (hc[h] & 0xffffffu) : 0u; }
   __device__ __forceinline__ uint64_t sum(uint32_t h) const {
