@@ -231,16 +231,18 @@ typedef struct {
   int32_t* len;    /* [n_targets][n_sessions] */
 } OttoCandidates;
 
-int64_t otto_candidates_scratch_bytes(const OttoSessions* sessions_shape_host, const OttoCandidateSpec* spec);
-int otto_candidates(const OttoSessions* sessions, const OttoCandidateSpec* spec, void* scratch, int64_t scratch_bytes,
-                    const OttoCandidates* out, void* stream);
+/* max_session_len = longest session of the frame (events); positions in a concatenation are 16-bit, so
+ * max_session_len * (largest sum of table_k over one target's sources) must stay below 65535. */
+int64_t otto_candidates_scratch_bytes(int64_t n_sessions, int32_t max_session_len, const OttoCandidateSpec* spec);
+int otto_candidates(const OttoSessions* sessions, int32_t max_session_len, const OttoCandidateSpec* spec, void* scratch,
+                    int64_t scratch_bytes, const OttoCandidates* out, void* stream);
 
-/* covisitation/inference.py:238-243: history + votes[:n - |H|] + popular[:n - len]; sessions whose
- * unique-aid count is >= n keep their first n history aids (the reference sends them to its recency
- * branch, :128-131; flagged in long_session so the caller can route them). */
+/* covisitation/inference.py:238-243: history + votes[:n - |H|] + popular[:n - len], -1 padded.  Sessions
+ * with >= n unique aids keep their n most recent unique aids and are flagged in long_session (the
+ * reference routes them to its recency branch, :128-131).  popular is [n_targets][n_popular]. */
 int otto_assemble_predictions(const OttoSessions* sessions, const OttoCandidates* cand, int32_t n_targets, int32_t top_n,
-                              const int32_t* popular /* [n_targets][n] */, int32_t n, int32_t* pred /* [n_targets][n_sessions][n] */,
-                              uint8_t* long_session /* [n_sessions] */, void* stream);
+                              const int32_t* popular, int32_t n_popular, int32_t n, int32_t* pred /* [n_targets][n_sessions][n] */,
+                              uint8_t* long_session /* [n_sessions] or NULL */, void* stream);
 
 #ifdef __cplusplus
 }

@@ -90,7 +90,9 @@ _SIGNATURES = {
     "otto_topk_row_offsets": (C.c_int, [P(OttoTopK), vp, P(i64), vp, i64, vp]),
     "otto_topk_to_rows": (C.c_int, [P(OttoTopK), vp, vp, vp, vp, vp]),
     "otto_rows_to_topk": (C.c_int, [vp, vp, vp, i64, P(OttoTopK), vp]),
-    # CANDIDATES-PLACEHOLDER
+    "otto_candidates_scratch_bytes": (i64, [i64, i32, P(OttoCandidateSpec)]),
+    "otto_candidates": (C.c_int, [P(OttoSessions), i32, P(OttoCandidateSpec), vp, i64, P(OttoCandidates), vp]),
+    "otto_assemble_predictions": (C.c_int, [P(OttoSessions), P(OttoCandidates), i32, i32, vp, i32, i32, vp, vp, vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

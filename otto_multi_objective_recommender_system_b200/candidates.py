@@ -1,0 +1,206 @@
+"""Covisitation candidate generation on one B200: host side of otto_candidates / otto_assemble_predictions.
+
+Mirrors the reference consumers of the top-K tables:
+  * src/ranker/covisitation_candidate_generation.py:108-157 / :248-288 - ranker form, most_common(100),
+    output frames (session, candidates uint64, candidate_scores float32[, candidate_labels uint8])
+    written to candidate/{click,cart,order}_covisitation_{validation,test}.pkl (:177-197, :290-307)
+  * src/covisitation/inference.py:204-247 / :396-441 - standalone form, most_common(20) + history +
+    popular fill (the fastText/Annoy neighbour term is out of scope: SURVEY.md §2)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .covisit import EventCSR, TopKTable, _require_cuda, _stream_ptr
+
+STEMS = ("time_weighted", "click_weighted", "cart_weighted", "order_weighted", "click_cart", "click_order", "cart_order")
+
+
+@dataclass(frozen=True)
+class CandidateSpec:
+    """sources: (table stem, history set); targets: per event type the ordered sources to concatenate."""
+    sources: tuple
+    targets: dict
+    top_n: int = 100
+    drop_history: bool = True
+
+
+def reference_spec(stems_available, top_n: int = 100) -> CandidateSpec:
+    """The reference's list recipe (ranker/covisitation_candidate_generation.py:119-138) restricted to the
+    tables that exist: clicks = time + click_w + cart_w + click_cart + cart_order, carts = orders =
+    time + cart_w + cart_order; time over the history in recency order, everything else over the sorted
+    unique aids with type <= 1 (note: cart_order too, :124).  Absent stems contribute nothing, like the
+    reference's `if aid in table` guards."""
+    have = set(stems_available)
+    recipe = {"time_weighted": N.HIST_RECENCY, "click_weighted": N.HIST_TYPE_LE1, "cart_weighted": N.HIST_TYPE_LE1,
+              "click_cart": N.HIST_TYPE_LE1, "cart_order": N.HIST_TYPE_LE1}
+    order = {"click": ["time_weighted", "click_weighted", "cart_weighted", "click_cart", "cart_order"],
+             "cart": ["time_weighted", "cart_weighted", "cart_order"],
+             "order": ["time_weighted", "cart_weighted", "cart_order"]}
+    sources = tuple((s, recipe[s]) for s in recipe if s in have)
+    index = {s: i for i, (s, _) in enumerate(sources)}
+    targets = {t: tuple(index[s] for s in lst if s in index) for t, lst in order.items()}
+    return CandidateSpec(sources, targets, top_n, True)
+
+
+@dataclass
+class Candidates:
+    """Fixed-stride candidate lists on the device: [target, session, rank]."""
+    targets: tuple
+    aid: torch.Tensor     # int32 [T, S, N], -1 padded
+    score: torch.Tensor   # int32 [T, S, N]
+    len: torch.Tensor     # int32 [T, S]
+    session_ids: torch.Tensor
+
+    def to_frames(self, labels: dict | None = None) -> dict:
+        """The exploded frames the ranker script pickles (:177-197): session, candidates uint64,
+        candidate_scores float32 (+ candidate_labels uint8 when labels = {target: {session: set}})."""
+        import pandas as pd
+        out = {}
+        n = self.aid.shape[2]
+        sid = self.session_ids.cpu().numpy()
+        for ti, t in enumerate(self.targets):
+            ln = self.len[ti].cpu().numpy()
+            mask = np.arange(n)[None, :] < ln[:, None]
+            f = pd.DataFrame({"session": np.repeat(sid, ln),
+                              "candidates": self.aid[ti].cpu().numpy()[mask].astype(np.uint64),
+                              "candidate_scores": self.score[ti].cpu().numpy()[mask].astype(np.float32)})
+            if labels is not None:
+                lab = labels.get(t, {})
+                f["candidate_labels"] = np.fromiter(
+                    (int(int(a) in lab.get(int(s), ())) for s, a in zip(f["session"], f["candidates"])),
+                    dtype=np.uint8, count=len(f))
+            out[t] = f
+        return out
+
+
+def _sessions_struct(csr: EventCSR) -> N.OttoSessions:
+    return N.OttoSessions(csr.n_sessions, csr.n_events, csr.offsets.data_ptr(), csr.aid.data_ptr(), csr.type.data_ptr())
+
+
+def max_session_len(csr: EventCSR) -> int:
+    if csr.n_sessions == 0:
+        return 1
+    return int((csr.offsets[1:] - csr.offsets[:-1]).max().item())
+
+
+class CandidateGenerator:
+    """Keeps the scratch and output buffers across calls."""
+
+    def __init__(self, tables: dict, spec: CandidateSpec, n_aids: int):
+        self.lib = N.lib()
+        self.tables, self.spec, self.n_aids = tables, spec, n_aids
+        stems = sorted({s for s, _ in spec.sources})
+        self.stems = stems
+        for s in stems:
+            _require_cuda(tables[s].aid_y, f"table {s}")
+        if len(stems) > N.MAX_TABLES or len(spec.sources) > N.MAX_SOURCES or len(spec.targets) > N.MAX_TARGETS:
+            raise ValueError("too many tables / sources / targets")
+        cs = N.OttoCandidateSpec()
+        cs.n_tables = len(stems)
+        for i, s in enumerate(stems):
+            cs.table_aid_y[i] = tables[s].aid_y.data_ptr()
+            cs.table_len[i] = tables[s].len.data_ptr()
+            cs.table_k[i] = tables[s].k
+        cs.n_aids = n_aids
+        cs.n_sources = len(spec.sources)
+        for i, (s, h) in enumerate(spec.sources):
+            cs.source_table[i] = stems.index(s)
+            cs.source_hist[i] = h
+        self.target_names = tuple(spec.targets)
+        cs.n_targets = len(self.target_names)
+        for ti, t in enumerate(self.target_names):
+            cs.target_n_sources[ti] = len(spec.targets[t])
+            for j, src in enumerate(spec.targets[t]):
+                cs.target_sources[ti][j] = src
+        cs.top_n = spec.top_n
+        cs.drop_history = 1 if spec.drop_history else 0
+        self.cspec = cs
+        self.scratch = None
+        self.out = None
+
+    def __call__(self, sessions: EventCSR, max_len: int | None = None) -> Candidates:
+        if sessions.order != "asc":
+            raise ValueError("candidate generation needs sessions in file order (ingest(..., order='asc'))")
+        _require_cuda(sessions.aid, "sessions")
+        dev = sessions.aid.device
+        S, T, n = sessions.n_sessions, len(self.target_names), self.spec.top_n
+        max_len = max_session_len(sessions) if max_len is None else max_len
+        need = int(self.lib.otto_candidates_scratch_bytes(S, max_len, C.byref(self.cspec)))
+        if need < 0:
+            N.check(N.OTTO_EINVAL)
+        if self.scratch is None or self.scratch.numel() < need:
+            self.scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+        if self.out is None or self.out[0].shape != (T, S, n):
+            self.out = (torch.empty((T, S, n), dtype=torch.int32, device=dev),
+                        torch.empty((T, S, n), dtype=torch.int32, device=dev),
+                        torch.empty((T, S), dtype=torch.int32, device=dev))
+        aid, score, ln = self.out
+        oc = N.OttoCandidates(aid.data_ptr(), score.data_ptr(), ln.data_ptr())
+        ss = _sessions_struct(sessions)
+        with torch.cuda.device(dev):
+            N.check(self.lib.otto_candidates(C.byref(ss), max_len, C.byref(self.cspec), self.scratch.data_ptr(),
+                                             self.scratch.numel(), C.byref(oc), _stream_ptr(dev)))
+        return Candidates(self.target_names, aid, score, ln, sessions.session_ids)
+
+
+def generate_candidates(sessions: EventCSR, tables: dict, spec: CandidateSpec | None = None) -> Candidates:
+    spec = reference_spec(tables.keys()) if spec is None else spec
+    return CandidateGenerator(tables, spec, sessions.n_aids)(sessions)
+
+
+def assemble_predictions(sessions: EventCSR, cand: Candidates, popular: dict, n: int = 20):
+    """covisitation/inference.py:238-243 -> (pred int32 [T, S, n] with -1 padding, long_session bool [S]).
+    popular = {target: most frequent aids} (data/aid_frequencies/*_20_most_frequent_*_aids.json, :76-83)."""
+    lib = N.lib()
+    dev = sessions.aid.device
+    T, S = len(cand.targets), sessions.n_sessions
+    n_pop = max(len(popular[t]) for t in cand.targets)
+    pop = torch.full((T, n_pop), -1, dtype=torch.int32)
+    for ti, t in enumerate(cand.targets):
+        pop[ti, :len(popular[t])] = torch.tensor(list(popular[t]), dtype=torch.int32)
+    pop = pop.to(dev)
+    pred = torch.empty((T, S, n), dtype=torch.int32, device=dev)
+    long_session = torch.zeros(S, dtype=torch.uint8, device=dev)
+    ss = _sessions_struct(sessions)
+    oc = N.OttoCandidates(cand.aid.data_ptr(), cand.score.data_ptr(), cand.len.data_ptr())
+    with torch.cuda.device(dev):
+        N.check(lib.otto_assemble_predictions(C.byref(ss), C.byref(oc), T, cand.aid.shape[2], pop.data_ptr(), n_pop, n,
+                                              pred.data_ptr(), long_session.data_ptr(), _stream_ptr(dev)))
+    return pred, long_session.bool()
+
+
+def recall_at_20(pred: torch.Tensor, labels: list) -> float:
+    """covisitation/inference.py:251-257 on device predictions: sum |pred ∩ label| / sum min(|label|, 20)."""
+    p = pred.cpu().numpy()
+    hits = sum(len(set(int(a) for a in row if a >= 0).intersection(l)) for row, l in zip(p, labels))
+    denom = sum(min(len(l), 20) for l in labels)
+    return hits / denom if denom else 0.0
+
+
+def smoke_check() -> None:
+    """Tiny candidate-generation run on cuda:0 against the CPU oracle (called by __graft_entry__.smoke)."""
+    from oracle import candidates_oracle as co_c
+    from oracle import covisit_oracle as co
+    from . import covisit, synth
+    train = synth.generate(synth.SynthSpec("train", 2000, 300, seed=3))
+    test = synth.generate(synth.SynthSpec("test", 500, 300, seed=4, first_session=2000))
+    csr = covisit.ingest(train, "desc", device="cuda:0")
+    tables, otables = {}, {}
+    for stem, spec in covisit.VARIANTS.items():
+        tables[stem], _ = covisit.build_topk(csr, spec)
+        otables[stem] = co_c.covisitation_df_to_dict(tables[stem].to_pandas())
+    sess = covisit.ingest(test, "asc", device="cuda:0")
+    cand = generate_candidates(sess, tables, reference_spec(tables.keys(), 20))
+    want = co_c.ranker_frame(test.to_pandas(), otables, 20)
+    got = cand.to_frames()
+    for t in ("click", "cart", "order"):
+        assert got[t]["session"].tolist() == want[t]["session"].tolist(), t
+        assert got[t]["candidates"].tolist() == want[t]["candidates"].tolist(), t
+        assert got[t]["candidate_scores"].tolist() == want[t]["candidate_scores"].tolist(), t
+    print(f"smoke candidates: {len(got['click'])} click rows ok")

@@ -1,0 +1,161 @@
+"""GPU parity tests of covisitation candidate generation: CUDA path vs the restated reference loops."""
+import json
+import pathlib
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from oracle import candidates_oracle as oc
+
+pytestmark = pytest.mark.gpu
+GOLDEN = pathlib.Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def mods(native_lib):
+    from otto_multi_objective_recommender_system_b200 import candidates, covisit, synth
+    return covisit, candidates, synth
+
+
+def random_table(cv, rng, n_aids, k, fill=0.8):
+    """A random ranked table (no build needed: candidate parity only needs identical tables on both sides)."""
+    rows = []
+    for x in range(n_aids):
+        if rng.random() < fill:
+            n = int(rng.integers(1, k + 1))
+            ys = rng.choice(n_aids, size=n, replace=False)
+            rows += [(x, int(y), float(n - i)) for i, y in enumerate(ys)]
+    df = pd.DataFrame(rows, columns=["aid_x", "aid_y", "wgt"])
+    t = cv.TopKTable.from_rows(torch.tensor(df["aid_x"].to_numpy(), device="cuda:0"),
+                               torch.tensor(df["aid_y"].to_numpy(), device="cuda:0"),
+                               torch.tensor(df["wgt"].to_numpy(), dtype=torch.float32, device="cuda:0"), n_aids, k)
+    return t, oc.covisitation_df_to_dict(df)
+
+
+def make_test_frame(synth, n_sessions, n_aids, seed, extra_lengths=()):
+    f = synth.generate(synth.SynthSpec("test", n_sessions, n_aids, seed=seed, first_session=1000))
+    df = f.to_pandas()
+    rng = np.random.default_rng(seed)
+    sid = int(df["session"].max()) + 1
+    rows = []
+    for L in extra_lengths:
+        ts = np.sort(rng.integers(1661724000, 1662328791, size=L))
+        # few distinct aids in some long sessions, many in others
+        pool = n_aids if L % 2 else max(3, n_aids // 10)
+        rows += [(sid, int(a), int(t), int(y)) for a, t, y in
+                 zip(rng.integers(0, pool, size=L), ts, rng.choice([0, 1, 2], size=L, p=[0.7, 0.2, 0.1]))]
+        sid += 1
+    if rows:
+        df = pd.concat([df, pd.DataFrame(rows, columns=df.columns)], ignore_index=True)
+    return synth.EventFrame.from_pandas(df, n_aids), df
+
+
+def compare(cand_mod, cv, frame, df, tables, otables, stems, top_n):
+    sess = cv.ingest(frame, "asc", device="cuda:0")
+    spec = cand_mod.reference_spec(stems, top_n)
+    got = cand_mod.generate_candidates(sess, tables, spec).to_frames()
+    want = oc.ranker_frame(df, otables, top_n)
+    for t in ("click", "cart", "order"):
+        g, w = got[t], want[t]
+        assert len(g) == len(w), f"{t}: {len(g)} rows vs {len(w)}"
+        assert g["session"].tolist() == w["session"].tolist(), t
+        assert g["candidates"].tolist() == w["candidates"].tolist(), t
+        assert g["candidate_scores"].tolist() == w["candidate_scores"].tolist(), t
+        assert g["candidates"].dtype == np.uint64 and g["candidate_scores"].dtype == np.float32
+
+
+@pytest.mark.parametrize("top_n", [100, 20, 3])
+def test_three_table_recipe_matches_reference_loop(mods, top_n):
+    cv, cand_mod, synth = mods
+    rng = np.random.default_rng(1)
+    n_aids = 400
+    tables, otables = {}, {}
+    for stem, k in (("time_weighted", 20), ("cart_weighted", 15), ("cart_order", 15)):
+        tables[stem], otables[stem] = random_table(cv, rng, n_aids, k)
+    frame, df = make_test_frame(synth, 1500, n_aids, seed=2)
+    compare(cand_mod, cv, frame, df, tables, otables, tables.keys(), top_n)
+
+
+def test_seven_table_recipe_and_all_tiers(mods):
+    """All seven reference stems; sessions of 70 / 150 / 458 events reach the block and global tiers."""
+    cv, cand_mod, synth = mods
+    rng = np.random.default_rng(5)
+    n_aids = 600
+    tables, otables = {}, {}
+    for stem in oc.STEMS:
+        tables[stem], otables[stem] = random_table(cv, rng, n_aids, 15, fill=0.9)
+    frame, df = make_test_frame(synth, 800, n_aids, seed=6, extra_lengths=(70, 71, 150, 151, 300, 458, 11, 12, 64, 65))
+    compare(cand_mod, cv, frame, df, tables, otables, oc.STEMS, 100)
+
+
+def test_built_tables_end_to_end(mods):
+    """Build the three graded matrices on the GPU, then candidates from them vs the oracle fed the same tables."""
+    cv, cand_mod, synth = mods
+    train = synth.generate(synth.SynthSpec("train", 6000, 500, seed=8))
+    csr = cv.ingest(train, "desc", device="cuda:0")
+    tables, otables = {}, {}
+    for stem, spec in cv.VARIANTS.items():
+        tables[stem], _ = cv.build_topk(csr, spec)
+        otables[stem] = oc.covisitation_df_to_dict(tables[stem].to_pandas())
+    frame, df = make_test_frame(synth, 2000, 500, seed=9, extra_lengths=(90, 200))
+    compare(cand_mod, cv, frame, df, tables, otables, tables.keys(), 100)
+
+
+def test_standalone_predictions_and_recall(mods):
+    """covisitation/inference.py:227-243: history + votes + popular fill, and recall@20 on held-out tails."""
+    cv, cand_mod, synth = mods
+    rng = np.random.default_rng(3)
+    n_aids = 300
+    tables, otables = {}, {}
+    for stem, k in (("time_weighted", 20), ("cart_weighted", 15), ("cart_order", 15)):
+        tables[stem], otables[stem] = random_table(cv, rng, n_aids, k)
+    frame, df = make_test_frame(synth, 1200, n_aids, seed=4, extra_lengths=(40, 120))
+    popular = json.load(open(GOLDEN / "popular.json"))
+    popular = {t: [a % n_aids for a in popular[t]] for t in ("click", "cart", "order")}
+    # split every session at a cutoff: history -> predictions, tail -> labels (validation.py:73-83 semantics)
+    lists = oc.session_lists(df)
+    hist_rows, labels = [], {"click": [], "cart": [], "order": []}
+    for t in lists.itertuples():
+        cut = 0 if len(t.aid) <= 2 else int(rng.integers(0, len(t.aid) - 1))
+        (ha, ht), (c, k, o) = oc.split_for_recall(t.aid, t.type, cut)
+        hist_rows += [(t.session, a, i, y) for i, (a, y) in enumerate(zip(ha, ht))]
+        labels["click"].append(set(c)); labels["cart"].append(set(k)); labels["order"].append(set(o))
+    hdf = pd.DataFrame(hist_rows, columns=["session", "aid", "ts", "type"])
+    sess = cv.ingest(synth.EventFrame.from_pandas(hdf, n_aids), "asc", device="cuda:0")
+    cand = cand_mod.generate_candidates(sess, tables, cand_mod.reference_spec(tables.keys(), 20))
+    pred, long_session = cand_mod.assemble_predictions(sess, cand, popular, 20)
+    pred = pred.cpu().numpy()
+    long_session = long_session.cpu().numpy()
+    hl = oc.session_lists(hdf)
+    want_all = {"click": [], "cart": [], "order": []}
+    for i, t in enumerate(hl.itertuples()):
+        uniq = len(set(t.aid))
+        assert bool(long_session[i]) == (uniq >= 20)
+        want = oc.standalone_predictions(t.aid, t.type, otables, [popular["click"], popular["cart"], popular["order"]], 20)
+        for ti, name in enumerate(("click", "cart", "order")):
+            want_all[name].append(want[ti])
+            if uniq < 20:
+                got = [int(a) for a in pred[ti, i] if a >= 0]
+                assert got == want[ti], (name, t.session)
+    # recall@20 identical on the sessions the covisitation branch serves
+    keep = [i for i in range(len(hl)) if not long_session[i]]
+    for ti, name in enumerate(("click", "cart", "order")):
+        got_r = cand_mod.recall_at_20(torch.tensor(pred[ti][keep]), [labels[name][i] for i in keep])
+        want_r = oc.recall_at_20([want_all[name][i] for i in keep], [labels[name][i] for i in keep])
+        assert got_r == want_r
+
+
+def test_candidate_edge_cases(mods):
+    cv, cand_mod, synth = mods
+    n_aids = 50
+    # an aid with an empty table row, an aid outside every table, a session of one event, duplicated events
+    tdf = pd.DataFrame({"aid_x": [1, 1, 1, 2, 2, 7], "aid_y": [2, 3, 4, 1, 3, 1], "wgt": np.float32([3, 2, 1, 2, 1, 1])})
+    t = cv.TopKTable.from_rows(*(torch.tensor(tdf[c].to_numpy(), device="cuda:0") for c in ("aid_x", "aid_y", "wgt")), n_aids, 4)
+    tables = {"time_weighted": t}
+    otables = {"time_weighted": oc.covisitation_df_to_dict(tdf)}
+    df = pd.DataFrame({"session": [5, 6, 6, 6, 7, 7, 8], "aid": [1, 2, 1, 2, 9, 9, 7], "ts": range(7), "type": [0, 0, 1, 2, 0, 0, 2]})
+    frame = synth.EventFrame.from_pandas(df, n_aids)
+    compare(cand_mod, cv, frame, df, tables, otables, tables.keys(), 100)
+    compare(cand_mod, cv, frame, df, tables, otables, tables.keys(), 1)
