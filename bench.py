@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=float, default=0.01, help="fraction of full scale for the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-candidates", action="store_true")
     ap.add_argument("--split-ub", type=int, default=0)
     return ap.parse_args()
 
@@ -168,7 +169,7 @@ def run_reference(args):
               f"{len(df)} events per step")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(args), "cpu_sample": args.cpu_sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -183,7 +184,7 @@ def run_b200(args):
     import __graft_entry__ as g
     g.build()
     from otto_multi_objective_recommender_system_b200 import _native as N
-    from otto_multi_objective_recommender_system_b200 import covisit, synth
+    from otto_multi_objective_recommender_system_b200 import candidates, covisit, distributed, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,22 +199,52 @@ def run_b200(args):
         from dataclasses import replace
         spec = replace(spec, split_ub=args.split_ub)
 
-    # ---- synthetic frame on the device (weak scaling: every rank holds `scale` of full OTTO) ----
-    sspec = synth.SynthSpec.scaled("train", args.scale, seed=42 + rank)
+    # ---- synthetic frame on the device; N > 1: strong scaling, the same frame sharded by session chunk ----
+    sspec = synth.SynthSpec.scaled("train", args.scale, seed=42)
     frame = synth.generate(sspec, device=dev)
+    if world > 1:
+        full = covisit.ingest(frame, "asc", device=dev)
+        S_all = full.n_sessions
+        lo_s, hi_s = rank * S_all // world, (rank + 1) * S_all // world
+        e0, e1 = int(full.offsets[lo_s].item()), int(full.offsets[hi_s].item())
+        frame = synth.EventFrame(frame.session[e0:e1].clone(), frame.aid[e0:e1].clone(), frame.ts[e0:e1].clone(),
+                                 frame.type[e0:e1].clone(), frame.n_aids)
+        del full
+        torch.cuda.empty_cache()
     csr = covisit.ingest(frame, "desc", device=dev)
     E, S, A = csr.n_events, csr.n_sessions, csr.n_aids
-    builder = covisit.CovisitBuilder(csr, spec)
+    backend = distributed.GpuRankBackend(csr, spec)
+    builder = backend.b
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def allsum(x: int) -> int:
+        if world == 1:
+            return int(x)
+        t = torch.tensor([int(x)], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        return int(t.item())
+
+    def allmax(x: float) -> float:
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     ev = lambda: torch.cuda.Event(enable_timing=True)
     phases = ["count_begin", "count_finish", "scatter", "reduce"]
+    last = {}
 
     def step(marks=None):
+        if world > 1:
+            # sessions sharded by chunk; all-reduce of bounds / counts; all-to-all of pair slabs; owner reduce
+            _, _, st, _ = distributed.build_topk_distributed(backend)
+            last.update(st)
+            return
         m = [ev() for _ in range(5)] if marks is not None else None
         if m: m[0].record()
         builder.count_begin()
@@ -235,7 +266,7 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     launches0 = lib.otto_launch_count()
-    marks = []
+    marks = [] if world == 1 else None
     t_start, t_end = ev(), ev()
     barrier()
     t_start.record()
@@ -245,21 +276,11 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = (lib.otto_launch_count() - launches0) // max(1, args.steps)
-    ms_total = t_start.elapsed_time(t_end)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-        ev_total = torch.tensor([E], device=dev, dtype=torch.int64)
-        dist.all_reduce(ev_total)
-        events_all = int(ev_total.item())
-    else:
-        events_all = E
-    ms_step = ms_total / args.steps
+    ms_step = allmax(t_start.elapsed_time(t_end)) / args.steps
+    events_all = allsum(E)
     value = events_all / (ms_step * 1e-3)
-    phase_ms = {p: statistics.mean(m[i].elapsed_time(m[i + 1]) for m in marks) for i, p in enumerate(phases)}
 
-    # ---- roofline of the dominant phase (algorithmic bytes: DESIGN.md §Kernels) ----
+    # ---- roofline (algorithmic bytes: DESIGN.md, "Kernels") ----
     E30, P, B, D = stats["tail_events"], stats["pairs"], stats["bins"], stats["distinct"]
     K = spec.k
     alg = {
@@ -277,15 +298,24 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    dom = max(phase_ms, key=phase_ms.get)
-    achieved = alg[dom] / (phase_ms[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": kernel_of[dom], "phase": dom, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes": alg[dom], "phase_ms": phase_ms,
-                "phase_gbs": {p: alg[p] / (phase_ms[p] * 1e-3) / 1e9 for p in phases},
-                "whole_build": {"algorithmic_bytes": sum(alg.values()),
-                                "achieved": sum(alg.values()) / (ms_step * 1e-3) / 1e9,
-                                "frac": sum(alg.values()) / (ms_step * 1e-3) / 1e9 / peak}}
+    bytes_all = allsum(sum(alg.values()))
+    whole = {"algorithmic_bytes": bytes_all, "achieved_per_gpu": bytes_all / world / (ms_step * 1e-3) / 1e9,
+             "frac": bytes_all / world / (ms_step * 1e-3) / 1e9 / peak}
+    if world == 1:
+        phase_ms = {p: statistics.mean(m[i].elapsed_time(m[i + 1]) for m in marks) for i, p in enumerate(phases)}
+        dom = max(phase_ms, key=phase_ms.get)
+        achieved = alg[dom] / (phase_ms[dom] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": kernel_of[dom], "phase": dom, "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes": alg[dom], "phase_ms": phase_ms,
+                    "phase_gbs": {p: alg[p] / (phase_ms[p] * 1e-3) / 1e9 for p in phases}, "whole_build": whole}
+    else:
+        sent = allsum(P * 8)
+        roofline = {"bound": "hbm", "kernel": "whole build (phases interleave with collectives)", "achieved":
+                    whole["achieved_per_gpu"], "peak": peak, "unit": "GB/s", "frac": whole["frac"], "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes": bytes_all,
+                    "exchange": {"all_to_all_bytes_total": sent, "per_gpu_per_step": sent / world,
+                                 "note": "upper bound: includes the slab a rank keeps for itself"}}
 
     # ---- end to end from pinned host columns ----
     e2e = None
@@ -294,20 +324,23 @@ def run_b200(args):
                                 n_aids=A)
         h2d = sum(t.numel() * t.element_size() for t in (host.session, host.aid, host.ts, host.type))
         del frame
-        d2h = 0
+        d2h = [0]
 
         def e2e_step():
-            nonlocal d2h
             f = synth.EventFrame(host.session.to(dev, non_blocking=True), host.aid.to(dev, non_blocking=True),
                                  host.ts.to(dev, non_blocking=True), host.type.to(dev, non_blocking=True), A)
             c = covisit.ingest(f, "desc", device=dev)
-            b = covisit.CovisitBuilder(c, spec)
+            be = distributed.GpuRankBackend(c, spec)
+            b = be.b
             b.workspace = builder.workspace          # reuse device buffers, as a long-running service would
             b.records, b.scratch, b.table = builder.records, builder.scratch, builder.table
-            t = b.build()
-            ax, ay, w = t.to_rows()
-            out = [x.cpu() for x in (ax, ay, w)]
-            d2h = sum(x.numel() * x.element_size() for x in out)
+            if world > 1:
+                t, (lo, hi), _, _ = distributed.build_topk_distributed(be)
+                out = [x[lo:hi].cpu() for x in (t.aid_y, t.wgt, t.len)]      # the rows this rank owns
+            else:
+                t = b.build()
+                out = [x.cpu() for x in t.to_rows()]
+            d2h[0] = sum(x.numel() * x.element_size() for x in out)
             return out
 
         e2e_step()
@@ -316,13 +349,34 @@ def run_b200(args):
         for _ in range(args.e2e_steps):
             e2e_step()
         barrier()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        if world > 1:
-            t = torch.tensor([dt], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": events_all / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": dt * 1e3, "steps": args.e2e_steps}
+        dt = allmax((time.perf_counter() - t0) / args.e2e_steps)
+        e2e = {"value": events_all / dt, "unit": UNIT, "h2d_bytes_per_step": allsum(h2d),
+               "d2h_bytes_per_step": allsum(d2h[0]), "ms_per_step": dt * 1e3, "steps": args.e2e_steps}
+
+    # ---- candidate generation from the three graded matrices (second metric of BASELINE.json) ----
+    cand_info = None
+    if world == 1 and not args.no_candidates:
+        tables = {}
+        for stem, vspec in covisit.VARIANTS.items():
+            tables[stem], _ = covisit.build_topk(csr, vspec)
+        test = synth.generate(synth.SynthSpec.scaled("test", args.scale), device=dev)
+        sess = covisit.ingest(test, "asc", device=dev)
+        gen = candidates.CandidateGenerator(tables, candidates.reference_spec(tables.keys(), 20), A)
+        mlen = candidates.max_session_len(sess)
+        for _ in range(2):
+            gen(sess, mlen)
+        torch.cuda.synchronize(dev)
+        c0, c1 = ev(), ev()
+        c0.record()
+        reps = 3
+        for _ in range(reps):
+            gen(sess, mlen)
+        c1.record()
+        torch.cuda.synchronize(dev)
+        cms = c0.elapsed_time(c1) / reps
+        cand_info = {"metric": "candidate_gen_sessions_per_s", "value": sess.n_sessions / (cms * 1e-3),
+                     "unit": "sessions/s", "ms": cms, "sessions": sess.n_sessions, "events": sess.n_events,
+                     "tables": list(tables), "top_n": 20, "targets": 3}
 
     if rank == 0:
         cpu = None
@@ -330,13 +384,15 @@ def run_b200(args):
             cpu = cpu_baseline(args, 1)
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32/u64 accumulate, f32 weights", "data": "synthetic",
-            "config": {"workload": workload_name(args), "sessions": S, "events": E, "aids": A, "tail_events": E30,
-                       "pairs": P, "distinct_pairs": D, "bins": B, "split_rows": stats["split_rows"], "k": K,
-                       "l2": "inputs larger than L2 (event CSR and pair records are GBs)",
-                       "events_all_ranks": events_all},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}))
+            "config": {"workload": workload_name(args), "sessions_rank0": S, "events_rank0": E, "aids": A,
+                       "tail_events_rank0": E30, "pairs_rank0": P, "distinct_pairs_rank0": D, "bins": B,
+                       "split_rows": stats["split_rows"], "k": K, "events_all_ranks": events_all,
+                       "parallelism": "1 GPU" if world == 1 else f"sessions sharded over {world} GPUs, aid_x-owner all-to-all",
+                       "l2": "inputs larger than L2 (event CSR and pair records are GBs)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "candidates": cand_info,
+            "gpu_launches": int(launches), "clocks": clocks}))
     if world > 1:
         dist.destroy_process_group()
 

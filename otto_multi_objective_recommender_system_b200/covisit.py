@@ -248,7 +248,7 @@ class CovisitBuilder:
     def scatter(self) -> torch.Tensor:
         P = int(self.stats.pairs)
         if self.records is None or self.records.numel() < max(P, 1):
-            self.records = torch.empty((max(P, 1), 2), dtype=torch.int32, device=self.device)
+            self.records = torch.empty(max(P, 1), dtype=torch.int64, device=self.device)   # 8-byte {aid_y, v}
         with torch.cuda.device(self.device):
             N.check(self.lib.otto_covisit_scatter(C.byref(self.ev), C.byref(self.cspec), self.workspace.data_ptr(),
                                                   self.workspace.numel(), self.records.data_ptr(), P, self._st()))

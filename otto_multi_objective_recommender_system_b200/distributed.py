@@ -1,0 +1,141 @@
+"""Multi-GPU covisitation build: one process per GPU, sessions sharded by contiguous chunk, pair records
+exchanged by one all-to-all keyed on aid_x ownership.
+
+    rank r                                   collective (torch.distributed, NCCL over NVLink)
+    ------                                   -----------------------------------------------
+    count_begin  (tails, local upper bounds)
+                                             all-reduce  pair_ub [A] uint32   -> identical bins everywhere
+    count_finish (winner masks, local per-bin pair counts)
+                                             all-reduce  bin counts [B] int64 -> balanced aid_x ranges
+    scatter      (records grouped by bin; an owner's bins are one contiguous slab)
+                                             all-to-all  record slabs + their bin offsets
+    reduce       (accumulate + top-k over the G received segments of my aid range)
+                                             broadcast   each owner's rows (gather_table) for candidate-gen
+
+Every rank forms the same bins (the upper bounds are all-reduced before bins exist) and the accumulators are
+integers, so the G-GPU table equals the 1-GPU table byte for byte.  The reference has no distributed code
+(SURVEY.md §2.1); its only partitioning is the aid_x-range "part" files, which is what ownership mirrors.
+
+The rank-local work sits behind a small backend interface so that the exchange logic runs in CPU tests
+(world_size 2, gloo) with a numpy stand-in; the product backend is covisit.CovisitBuilder.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+from .covisit import CovisitBuilder, CovisitSpec, EventCSR, TopKTable
+
+
+class GpuRankBackend:
+    """Rank-local phases on one B200 (the product backend)."""
+
+    def __init__(self, csr: EventCSR, spec: CovisitSpec, exact: bool = False):
+        self.b = CovisitBuilder(csr, spec, exact=exact)
+        self.n_aids, self.k, self.device = csr.n_aids, spec.k, csr.aid.device
+
+    def count_begin(self) -> torch.Tensor:
+        self.b.count_begin()
+        self.b.stats.bins = 0
+        return self.b.views()["pair_ub"]            # int32 view of the uint32 bounds, reduced in place
+
+    def count_finish(self):
+        stats = self.b.count_finish()
+        v = self.b.views()
+        return stats, v["bin_offsets"], v["bin_base"]
+
+    def scatter(self) -> torch.Tensor:
+        return self.b.scatter()
+
+    def reduce(self, segments, bin_lo, bin_hi, aid_lo, aid_hi) -> TopKTable:
+        return self.b.reduce(segments, bin_lo, bin_hi, aid_lo, aid_hi)
+
+    def stats(self) -> dict:
+        return self.b.stats.as_dict()
+
+
+@dataclass
+class OwnerPlan:
+    aid_cuts: list      # [G + 1] aid_x range of every owner
+    bin_cuts: list      # [G + 1] the same cuts in bin ids
+
+
+def plan_owners(bin_counts: torch.Tensor, bin_base: torch.Tensor, world: int) -> OwnerPlan:
+    """Contiguous aid_x ranges with (nearly) equal pair counts: Zipf skew makes equal-width ranges useless.
+    bin_counts: global records per bin [B]; bin_base: first bin of every aid [A + 1]."""
+    A = bin_base.numel() - 1
+    cum = torch.zeros(bin_counts.numel() + 1, dtype=torch.int64, device=bin_counts.device)
+    torch.cumsum(bin_counts.to(torch.int64), 0, out=cum[1:])
+    before_aid = cum[bin_base.to(torch.int64)]                   # records in rows < x, for x = 0..A
+    total = int(cum[-1].item())
+    targets = torch.tensor([total * g // world for g in range(1, world)], dtype=torch.int64, device=cum.device)
+    inner = torch.searchsorted(before_aid, targets, right=False).clamp_(0, A).tolist() if world > 1 else []
+    aid_cuts = [0] + [int(x) for x in inner] + [A]
+    for i in range(1, len(aid_cuts)):                              # keep the cuts monotone
+        aid_cuts[i] = max(aid_cuts[i], aid_cuts[i - 1])
+    bb = bin_base.to(torch.int64)
+    bin_cuts = [int(bb[x].item()) for x in aid_cuts]
+    return OwnerPlan(aid_cuts, bin_cuts)
+
+
+def build_topk_distributed(backend, group=None):
+    """All ranks call this with their own session shard.  Returns (table, (aid_lo, aid_hi), stats, plan): rows
+    [aid_lo, aid_hi) of `table` are final on this rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    ub = backend.count_begin()
+    if world > 1:
+        dist.all_reduce(ub, group=group)
+    stats, bin_off, bin_base = backend.count_finish()
+    B = int(stats["bins"])
+    counts = (bin_off[1:B + 1] - bin_off[:B]).clone()
+    if world > 1:
+        dist.all_reduce(counts, group=group)
+    plan = plan_owners(counts, bin_base, world)
+    records = backend.scatter()
+    lo, hi = plan.bin_cuts[rank], plan.bin_cuts[rank + 1]
+    if world == 1:
+        segments = [(records, bin_off)]
+    else:
+        # slab of owner o = records[bin_off[cut_o] : bin_off[cut_o + 1]]; offsets travel with their slab
+        cut_off = bin_off[torch.tensor(plan.bin_cuts, device=bin_off.device)]
+        send_counts = (cut_off[1:] - cut_off[:-1])
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+        send_list, recv_list = send_counts.tolist(), recv_counts.tolist()
+        first = int(cut_off[0].item())
+        recv_records = torch.empty(max(1, sum(recv_list)), dtype=records.dtype, device=records.device)
+        dist.all_to_all_single(recv_records[:sum(recv_list)], records[first:first + sum(send_list)], recv_list,
+                               send_list, group=group)
+        n_mine = hi - lo + 1
+        send_off = torch.cat([bin_off[plan.bin_cuts[o]:plan.bin_cuts[o + 1] + 1] for o in range(world)])
+        off_send_sizes = [plan.bin_cuts[o + 1] - plan.bin_cuts[o] + 1 for o in range(world)]
+        recv_off = torch.empty(world * n_mine, dtype=torch.int64, device=records.device)
+        dist.all_to_all_single(recv_off, send_off, [n_mine] * world, off_send_sizes, group=group)
+        segments, at = [], 0
+        for g in range(world):
+            segments.append((recv_records[at:at + max(1, recv_list[g])] if recv_list[g] else recv_records[:1],
+                             recv_off[g * n_mine:(g + 1) * n_mine]))
+            at += recv_list[g]
+        backend._keepalive = (recv_records, recv_off)
+    table = backend.reduce(segments, lo, hi, plan.aid_cuts[rank], plan.aid_cuts[rank + 1])
+    out_stats = dict(backend.stats())
+    out_stats["owned_aids"] = plan.aid_cuts[rank + 1] - plan.aid_cuts[rank]
+    out_stats["sent_records"] = int(stats["pairs"])
+    return table, (plan.aid_cuts[rank], plan.aid_cuts[rank + 1]), out_stats, plan
+
+
+def gather_table(table: TopKTable, plan: OwnerPlan, group=None) -> TopKTable:
+    """Every rank ends up with all rows (one broadcast per owner range); needed before candidate generation."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return table
+    world = dist.get_world_size(group)
+    for o in range(world):
+        lo, hi = plan.aid_cuts[o], plan.aid_cuts[o + 1]
+        if hi > lo:
+            src = dist.get_global_rank(group, o) if group is not None else o
+            for t in (table.aid_y, table.wgt, table.len):
+                dist.broadcast(t[lo:hi], src=src, group=group)
+    return table

@@ -1,0 +1,127 @@
+"""World-size-2 gloo tests of the multi-GPU exchange logic (owner planning, slab all-to-all, segment
+assembly) with a numpy stand-in for the rank-local CUDA phases.  The stand-in follows the same interface as
+distributed.GpuRankBackend and forms the same bins (upper bounds, split_ub, aid_y-hash slices)."""
+import os
+import socket
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import covisit_oracle as co
+
+
+def _hash32(x):
+    x = x.astype(np.uint64)
+    m = np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16); x = (x * np.uint64(0x7feb352d)) & m
+    x ^= x >> np.uint64(15); x = (x * np.uint64(0x846ca68b)) & m
+    x ^= x >> np.uint64(16)
+    return x
+
+
+def _sub_bin(y, nb):
+    return (_hash32(y) * nb.astype(np.uint64)) >> np.uint64(32)
+
+
+class NumpyRankBackend:
+    """Same phases as the CUDA backend, computed with pandas/numpy from the oracle's deduplicated pairs."""
+
+    def __init__(self, df, spec, n_aids, split_ub):
+        self.df, self.spec, self.n_aids, self.split_ub = df, spec, n_aids, split_ub
+
+    def count_begin(self):
+        d = self.df.sort_values(["session", "ts"], ascending=[True, False], kind="stable")
+        d = d.loc[d.groupby("session").cumcount() < self.spec.tail_n]
+        n = d.groupby("session")["aid"].transform("size").to_numpy()
+        self.ub = torch.from_numpy(np.bincount(d["aid"].to_numpy(), weights=n - 1, minlength=self.n_aids).astype(np.int32))
+        return self.ub
+
+    def count_finish(self):
+        ub = self.ub.numpy().astype(np.int64)
+        nb = np.maximum(1, -(-ub // self.split_ub))
+        self.bin_base = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
+        pairs = co.dedup_pairs(self.df, self.spec)
+        x, y = pairs["aid_x"].to_numpy().astype(np.int64), pairs["aid_y"].to_numpy().astype(np.int64)
+        nbx = nb[x]
+        b = self.bin_base[x] + np.where(nbx > 1, _sub_bin(y, nbx).astype(np.int64), 0)
+        order = np.argsort(b, kind="stable")
+        self.rec = (y[order] | (np.ones_like(y) << 32)).astype(np.int64)       # v = 1 (unit weights)
+        B = int(self.bin_base[-1])
+        self.bin_off = np.concatenate([[0], np.cumsum(np.bincount(b, minlength=B))]).astype(np.int64)
+        self.bin_x = np.repeat(np.arange(self.n_aids), nb)
+        stats = {"bins": B, "pairs": len(self.rec)}
+        return stats, torch.from_numpy(self.bin_off), torch.from_numpy(self.bin_base.astype(np.int32))
+
+    def scatter(self):
+        return torch.from_numpy(self.rec)
+
+    def reduce(self, segments, bin_lo, bin_hi, aid_lo, aid_hi):
+        rows = []
+        for rec, off in segments:
+            rec, off = rec.numpy(), off.numpy()
+            off = off - off[0]
+            for i, b in enumerate(range(bin_lo, bin_hi)):
+                r = rec[off[i]:off[i + 1]]
+                rows.append(pd.DataFrame({"aid_x": self.bin_x[b], "aid_y": r & 0xFFFFFFFF, "wgt": (r >> 32).astype(np.float32)}))
+        acc = pd.concat(rows).groupby(["aid_x", "aid_y"])["wgt"].sum().reset_index() if rows else pd.DataFrame(columns=["aid_x", "aid_y", "wgt"])
+        return co.topk(acc, self.spec.k)
+
+    def stats(self):
+        return {}
+
+
+def _worker(rank, world, port, split_ub, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from otto_multi_objective_recommender_system_b200 import distributed, synth
+    frame = synth.generate(synth.SynthSpec("train", 600, 80, seed=17))
+    df = frame.to_pandas()
+    sessions = np.sort(df["session"].unique())
+    mine = sessions[rank * len(sessions) // world:(rank + 1) * len(sessions) // world]     # contiguous session chunk
+    spec = co.OracleSpec(co.WEIGHT_UNIT, k=7)
+    backend = NumpyRankBackend(df.loc[df["session"].isin(mine)], spec, 80, split_ub)
+    table, (lo, hi), stats, plan = distributed.build_topk_distributed(backend)
+    assert table["aid_x"].between(lo, hi - 1).all()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (table, plan.aid_cuts))
+    if rank == 0:
+        got = pd.concat([g[0] for g in gathered], ignore_index=True)
+        want = co.build(df, spec)
+        out.put((got.astype({"aid_x": np.int32, "aid_y": np.int32}).to_dict("list"), want.to_dict("list"),
+                 [g[1] for g in gathered]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("split_ub", [1 << 30, 40])
+def test_two_rank_exchange_equals_single_process(split_ub):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, split_ub, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, want, cuts = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert cuts[0] == cuts[1], "every rank must derive the same ownership plan"
+    assert got["aid_x"] == want["aid_x"] and got["aid_y"] == want["aid_y"] and got["wgt"] == want["wgt"]
+
+
+def test_plan_owners_balances_skewed_rows():
+    from otto_multi_objective_recommender_system_b200 import distributed
+    counts = torch.tensor([1000, 1, 1, 1, 500, 500, 1, 1], dtype=torch.int64)      # one hot row split in 3 bins
+    bin_base = torch.tensor([0, 3, 4, 5, 6, 7, 8], dtype=torch.int32)              # aid 0 owns bins 0..2
+    plan = distributed.plan_owners(counts, bin_base, 2)
+    assert plan.aid_cuts[0] == 0 and plan.aid_cuts[-1] == 6 and plan.aid_cuts == sorted(plan.aid_cuts)
+    # cuts fall on aid boundaries, never inside a split row
+    assert plan.bin_cuts == [int(bin_base[a]) for a in plan.aid_cuts]
+    assert distributed.plan_owners(counts, bin_base, 1).aid_cuts == [0, 6]
+    p8 = distributed.plan_owners(counts, bin_base, 8)
+    assert len(p8.aid_cuts) == 9 and p8.aid_cuts == sorted(p8.aid_cuts)

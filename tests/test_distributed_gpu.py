@@ -1,0 +1,46 @@
+"""Multi-GPU build == single-GPU build, byte for byte (needs >= 2 GPUs: run with `gpurun --gpus 2`)."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, variant, split_ub, n_sessions, n_aids):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from dataclasses import replace
+    from otto_multi_objective_recommender_system_b200 import covisit, distributed, synth
+    spec = replace(getattr(covisit, variant), split_ub=split_ub)
+    frame = synth.generate(synth.SynthSpec("train", n_sessions, n_aids, seed=31), device=dev)
+    csr = covisit.ingest(frame, "desc", device=dev)
+    S = csr.n_sessions
+    shard = csr.slice_sessions(rank * S // world, (rank + 1) * S // world)
+    backend = distributed.GpuRankBackend(shard, spec, exact=True)
+    table, (lo, hi), stats, plan = distributed.build_topk_distributed(backend)
+    distributed.gather_table(table, plan)
+    single, sstats = covisit.build_topk(csr, spec, exact=True)
+    for name in ("aid_y", "wgt", "len"):
+        assert torch.equal(getattr(table, name), getattr(single, name)), (rank, name)
+    # exact integer side outputs on the rows this rank owns
+    assert torch.equal(table.cnt[lo:hi], single.cnt[lo:hi]) and torch.equal(table.tsum[lo:hi], single.tsum[lo:hi])
+    total = torch.tensor([stats["pair_checksum"], stats["distinct"]], device=dev)
+    dist.all_reduce(total)
+    assert int(total[0]) == sstats["pair_checksum"] and int(total[1]) == sstats["distinct"]
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("variant,split_ub", [("CLICKS", 0), ("CARTS_ORDERS", 64), ("BUY2BUY", 0)])
+def test_multi_gpu_equals_single_gpu(native_lib, variant, split_ub):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    torch.multiprocessing.spawn(_worker, args=(world, port, variant, split_ub, 20000, 2500), nprocs=world, join=True)
