@@ -1,0 +1,128 @@
+"""CLI twin of src/covisitation/inference.py for the covisitation branch, on one B200.
+
+    python -m otto_multi_objective_recommender_system_b200.inference {validation|submission} --data DIR [--build]
+
+Mirrors the reference script's file contract (covisitation/inference.py:44-52,76-131,251-267,437-447):
+  validation  reads  DIR/splits/val.parquet (+ val_labels.parquet), DIR/aid_frequencies/train_20_most_frequent_*,
+                     DIR/covisitation/validation/top_15_<stem>_<part>.pqt
+              logs   recall@20 per type and the 0.1 / 0.3 / 0.6 weighted recall
+  submission  reads  DIR/test.pkl (or splits/test.parquet), DIR/aid_frequencies/all_20_most_frequent_*,
+                     DIR/covisitation/submission/top_15_<stem>_<part>.pqt
+              writes DIR/submissions/covisitation_submission.csv.gz
+  any other mode raises ValueError('Invalid mode'), like the reference.
+--build first builds the three graded matrices (the builder the reference ships without) from
+train ∪ val (validation) or train ∪ test (submission) and writes the part files.
+Differences, stated: the fastText/Annoy neighbour term (:223-224) is not on this path; sessions with >= 20
+unique aids keep their 20 most recent unique aids (the reference routes them to its recency branch, :128-131).
+"""
+from __future__ import annotations
+
+import argparse
+import logging
+import pathlib
+
+import numpy as np
+import torch
+
+from . import candidates, covisit, io
+
+
+def _first_existing(*paths):
+    for p in paths:
+        if pathlib.Path(p).exists():
+            return p
+    raise FileNotFoundError(" | ".join(str(p) for p in paths))
+
+
+def build_matrices(data: pathlib.Path, mode: str, n_aids: int | None, device) -> dict:
+    if mode == "validation":
+        frame = io.read_event_frame(data / "splits" / "train.parquet", data / "splits" / "val.parquet", n_aids=n_aids)
+    else:
+        frame = io.read_event_frame(_first_existing(data / "train.pkl", data / "splits" / "train.parquet"),
+                                    _first_existing(data / "test.pkl", data / "splits" / "test.parquet"), n_aids=n_aids)
+    csr = covisit.ingest(frame, "desc", device=device)
+    tables = {}
+    for stem, spec in covisit.VARIANTS.items():
+        tables[stem], stats = covisit.build_topk(csr, spec)
+        io.write_topk_parts(tables[stem], data / "covisitation" / mode, stem, io.n_parts_for(stem, mode), 15, k=15)
+        logging.info(f"built {stem}: {stats}")
+    return tables
+
+
+def load_matrices(data: pathlib.Path, mode: str, n_aids: int, device) -> dict:
+    tables = {}
+    for stem in candidates.STEMS:
+        try:
+            tables[stem] = io.read_topk_parts(data / "covisitation" / mode, stem, n_aids, 15,
+                                              io.n_parts_for(stem, mode), 15, device)
+        except FileNotFoundError:
+            continue
+    if not tables:
+        raise FileNotFoundError(f"no top_15_<stem>_<part>.pqt under {data / 'covisitation' / mode}; run with --build")
+    logging.info(f"Loaded top covisitation statistics: {sorted(tables)}")
+    return tables
+
+
+def validation_labels(data: pathlib.Path, session_ids: np.ndarray) -> dict | None:
+    """splits/val_labels.parquet: session, type in {clicks, carts, orders}, ground_truth list (covisitation/inference.py:116-122)."""
+    import pandas as pd
+    path = data / "splits" / "val_labels.parquet"
+    if not path.exists():
+        return None
+    df = pd.read_parquet(path)
+    out = {}
+    for name, event in (("clicks", "click"), ("carts", "cart"), ("orders", "order")):
+        d = df.loc[df["type"] == name].set_index("session")["ground_truth"].to_dict()
+        out[event] = [set(int(a) for a in np.atleast_1d(d[s])) if s in d else set() for s in session_ids]
+    return out
+
+
+def main(argv=None) -> dict:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("mode", type=str)
+    ap.add_argument("--data", type=pathlib.Path, required=True)
+    ap.add_argument("--build", action="store_true")
+    ap.add_argument("--n-aids", type=int, default=None)
+    ap.add_argument("--device", default="cuda:0")
+    args = ap.parse_args(argv)
+    if args.mode not in ("validation", "submission"):
+        raise ValueError("Invalid mode")
+    logging.basicConfig(level=logging.INFO, format="%(asctime)s %(message)s")
+    data, mode, dev = args.data, args.mode, torch.device(args.device)
+
+    if mode == "validation":
+        test_frame = io.read_event_frame(data / "splits" / "val.parquet", n_aids=args.n_aids)
+        popular = io.read_popular(data / "aid_frequencies", "train")
+    else:
+        test_frame = io.read_event_frame(_first_existing(data / "test.pkl", data / "splits" / "test.parquet"), n_aids=args.n_aids)
+        popular = io.read_popular(data / "aid_frequencies", "all")
+    tables = build_matrices(data, mode, args.n_aids, dev) if args.build else None
+    n_aids = max([test_frame.n_aids] + ([t.n_aids for t in tables.values()] if tables else [])) if args.n_aids is None else args.n_aids
+    if tables is None:
+        tables = load_matrices(data, mode, n_aids, dev)
+    n_aids = next(iter(tables.values())).n_aids
+    test_frame.n_aids = n_aids
+    sess = covisit.ingest(test_frame, "asc", device=dev)
+    cand = candidates.generate_candidates(sess, tables, candidates.reference_spec(tables.keys(), 20))
+    pred, long_session = candidates.assemble_predictions(sess, cand, popular, 20)
+    logging.info(f"{int((~long_session).sum())} sessions are predicted with covisitation")
+    result = {"sessions": sess.n_sessions, "long_sessions": int(long_session.sum()), "session_ids": sess.session_ids,
+              "pred": pred, "long_session": long_session}
+    if mode == "validation":
+        labels = validation_labels(data, sess.session_ids.cpu().numpy())
+        if labels is not None:
+            rec = {t: candidates.recall_at_20(pred[i], labels[t]) for i, t in enumerate(cand.targets)}
+            rec["weighted"] = 0.1 * rec["click"] + 0.3 * rec["cart"] + 0.6 * rec["order"]
+            logging.info("Covisitation model validation scores " +
+                         " ".join(f"{k} recall@20: {v:.6f}" for k, v in rec.items()))
+            result["recall"] = rec
+    else:
+        out = data / "submissions"
+        out.mkdir(parents=True, exist_ok=True)
+        io.write_submission(sess.session_ids, pred, out / "covisitation_submission.csv.gz")
+        result["submission"] = str(out / "covisitation_submission.csv.gz")
+    return result
+
+
+if __name__ == "__main__":
+    main()

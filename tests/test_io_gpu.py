@@ -1,0 +1,123 @@
+"""File boundary through the device path: part files round-trip, and the CLI twin of covisitation/inference.py
+end to end on a tiny synthetic data directory, checked against the oracle loops."""
+import json
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from oracle import candidates_oracle as oc
+from oracle import covisit_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods(native_lib):
+    from otto_multi_objective_recommender_system_b200 import candidates, covisit, inference, io, synth
+    return covisit, candidates, inference, io, synth
+
+
+def test_topk_part_files_round_trip_and_reference_reader(mods, tmp_path):
+    cv, _, _, io, synth = mods
+    frame = synth.generate(synth.SynthSpec("train", 3000, 400, seed=11))
+    csr = cv.ingest(frame, "desc", device="cuda:0")
+    table, _ = cv.build_topk(csr, cv.CARTS_ORDERS)
+    paths = io.write_topk_parts(table, tmp_path, "cart_weighted", 4, 15)
+    assert [p.name for p in paths] == [f"top_15_cart_weighted_{i}.pqt" for i in range(4)]
+    want = co.build(frame.to_pandas(), co.CARTS_ORDERS)
+    parts = [pd.read_parquet(p) for p in paths]
+    assert all(p.dtypes.astype(str).to_dict() == {"aid_x": "int32", "aid_y": "int32", "wgt": "float32"} for p in parts)
+    assert all(a["aid_x"].max() < b["aid_x"].min() for a, b in zip(parts, parts[1:]) if len(a) and len(b))
+    got = pd.concat(parts, ignore_index=True)
+    assert got.equals(want)
+    # the reference's reader (covisitation/inference.py:87-90): dict per part, merged with update()
+    d = {}
+    for p in parts:
+        d.update(oc.covisitation_df_to_dict(p))
+    assert d == oc.covisitation_df_to_dict(want)
+    back = io.read_topk_parts(tmp_path, "cart_weighted", 400, 15, 4, 15, "cuda:0")
+    assert torch.equal(back.aid_y, table.aid_y) and torch.equal(back.len, table.len) and torch.equal(back.wgt, table.wgt)
+
+
+def _make_data_dir(tmp_path, synth, io, n_aids=300):
+    train = synth.generate(synth.SynthSpec("train", 2500, n_aids, seed=21))
+    val_full = synth.generate(synth.SynthSpec("test", 600, n_aids, seed=22, first_session=2500)).to_pandas()
+    rng = np.random.default_rng(5)
+    hist, labels = [], []
+    for s, g in val_full.groupby("session"):
+        a, t = g["aid"].tolist(), g["type"].tolist()
+        cut = 0 if len(a) <= 2 else int(rng.integers(0, len(a) - 1))
+        (ha, ht), (c, k, o) = oc.split_for_recall(a, t, cut)
+        hist.append(g.iloc[:cut + 1])
+        for name, l in (("clicks", c), ("carts", k), ("orders", o)):
+            if l:
+                labels.append({"session": s, "type": name, "ground_truth": l})
+    (tmp_path / "splits").mkdir()
+    (tmp_path / "aid_frequencies").mkdir()
+    io.write_event_frame(train, tmp_path / "splits" / "train.parquet")
+    val = pd.concat(hist, ignore_index=True)
+    io.write_event_frame(synth.EventFrame.from_pandas(val, n_aids), tmp_path / "splits" / "val.parquet")
+    pd.DataFrame(labels).to_parquet(tmp_path / "splits" / "val_labels.parquet")
+    popular = {}
+    for e, ty in (("click", 0), ("cart", 1), ("order", 2)):
+        top = train.to_pandas().query("type == @ty")["aid"].value_counts().head(20)
+        popular[e] = [int(a) for a in top.index]
+        for prefix in ("train", "all"):
+            json.dump({str(a): int(c) for a, c in top.items()}, open(tmp_path / "aid_frequencies" / f"{prefix}_20_most_frequent_{e}_aids.json", "w"))
+    return train, val, pd.DataFrame(labels), popular
+
+
+def test_cli_validation_end_to_end_matches_oracle(mods, tmp_path):
+    cv, _, inference, io, synth = mods
+    train, val, labels, popular = _make_data_dir(tmp_path, synth, io)
+    res = inference.main(["validation", "--data", str(tmp_path), "--build", "--n-aids", "300"])
+    # part files exist with the reference's names and counts
+    for stem in ("time_weighted", "cart_weighted"):
+        assert all((tmp_path / "covisitation" / "validation" / f"top_15_{stem}_{i}.pqt").exists() for i in range(4))
+    assert (tmp_path / "covisitation" / "validation" / "top_15_cart_order_0.pqt").exists()
+    # oracle: matrices from train ∪ val, cut to 15 rows, then the reference's per-session loop
+    both = pd.concat([train.to_pandas(), val], ignore_index=True)
+    otables = {}
+    for stem, spec in (("time_weighted", co.CLICKS), ("cart_weighted", co.CARTS_ORDERS), ("cart_order", co.BUY2BUY)):
+        t = pd.concat([pd.read_parquet(p) for p in sorted((tmp_path / "covisitation" / "validation").glob(f"top_15_{stem}_*.pqt"))])
+        want = co.build(both, spec)
+        want = want.loc[want.groupby("aid_x").cumcount() < 15]
+        if spec.weight_mode != co.WEIGHT_TIME:
+            assert t.reset_index(drop=True).equals(want.reset_index(drop=True)), stem
+        otables[stem] = oc.covisitation_df_to_dict(t)
+    pred = res["pred"].cpu().numpy()
+    long_session = res["long_session"].cpu().numpy()
+    lists = oc.session_lists(val)
+    assert res["session_ids"].cpu().tolist() == lists["session"].tolist()
+    want_pred = {"click": [], "cart": [], "order": []}
+    for i, t in enumerate(lists.itertuples()):
+        want = oc.standalone_predictions(t.aid, t.type, otables, [popular["click"], popular["cart"], popular["order"]], 20)
+        for ti, name in enumerate(("click", "cart", "order")):
+            got = [int(a) for a in pred[ti, i] if a >= 0]
+            if not long_session[i]:
+                assert got == want[ti], (name, t.session)
+            want_pred[name].append(got)
+    # recall exactly as covisitation/inference.py:251-257 on the same predictions
+    lab = {n: labels.loc[labels["type"] == n].set_index("session")["ground_truth"].to_dict() for n in ("clicks", "carts", "orders")}
+    for name, plural in (("click", "clicks"), ("cart", "carts"), ("order", "orders")):
+        ll = [list(lab[plural].get(s, [])) for s in lists["session"]]
+        assert res["recall"][name] == oc.recall_at_20(want_pred[name], ll)
+    assert res["recall"]["weighted"] == pytest.approx(0.1 * res["recall"]["click"] + 0.3 * res["recall"]["cart"] + 0.6 * res["recall"]["order"])
+
+
+def test_cli_submission_and_invalid_mode(mods, tmp_path):
+    cv, _, inference, io, synth = mods
+    train, val, _, _ = _make_data_dir(tmp_path, synth, io)
+    (tmp_path / "splits" / "val.parquet").rename(tmp_path / "splits" / "test.parquet")
+    res = inference.main(["submission", "--data", str(tmp_path), "--build", "--n-aids", "300"])
+    sub = pd.read_csv(res["submission"])
+    assert list(sub.columns) == ["session_type", "labels"]
+    assert len(sub) == 3 * res["sessions"]
+    assert sub["session_type"].iloc[:3].tolist() == [f"{int(res['session_ids'][0])}_{t}s" for t in ("click", "cart", "order")]
+    assert (sub["labels"].str.split().str.len() <= 20).all()
+    assert len(list((tmp_path / "covisitation" / "submission").glob("top_15_cart_order_*.pqt"))) == 2
+    assert len(list((tmp_path / "covisitation" / "submission").glob("top_15_time_weighted_*.pqt"))) == 6
+    with pytest.raises(ValueError, match="Invalid mode"):
+        inference.main(["train", "--data", str(tmp_path)])
