@@ -198,6 +198,45 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Unfiltered variants (every event type enters the tail): the tail of a session is simply its first
+// min(len, tail_n) events, so a warp takes 32 consecutive sessions and one lane per OUTPUT event; the owning
+// session of an output position is found by a 5-step binary descent over the 32 tail offsets held in
+// registers.  Loads and stores are coalesced across session boundaries (tail_copy_kernel spends a whole
+// warp per session, which leaves two thirds of the lanes idle at the median session length of 6).
+__global__ void __launch_bounds__(256)
+    tail_copy_all_kernel(const int32_t* __restrict__ off, const int32_t* __restrict__ aid, const int32_t* __restrict__ ts,
+                         const uint8_t* __restrict__ type, int64_t S, const uint32_t* __restrict__ tail_off,
+                         uint32_t* __restrict__ tail_aw, int32_t* __restrict__ tail_ts, uint32_t* __restrict__ pair_ub) {
+  const int64_t s0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
+  if (s0 >= S) return;
+  const int lane = (int)lane_id();
+  const int ns = (int)min((int64_t)32, S - s0);
+  const int32_t src0 = off[s0 + min(lane, ns - 1)];
+  const uint32_t to = tail_off[s0 + min(lane, ns)];
+  const uint32_t to_next = tail_off[s0 + min(lane + 1, ns)];
+  const uint32_t T0 = __shfl_sync(FULL_MASK, to, 0);
+  const uint32_t total = __shfl_sync(FULL_MASK, to_next, ns - 1) - T0;
+  for (uint32_t q0 = 0; q0 < total; q0 += 32) {
+    const uint32_t q = q0 + lane;
+    int u = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      const int c = u + step;
+      const uint32_t tc = __shfl_sync(FULL_MASK, to, min(c, 31));
+      if (c < ns && tc - T0 <= q) u = c;
+    }
+    const uint32_t tu = __shfl_sync(FULL_MASK, to, u);
+    const uint32_t n = __shfl_sync(FULL_MASK, to_next, u) - tu;
+    const int32_t src = __shfl_sync(FULL_MASK, src0, u) + (int32_t)(q - (tu - T0));
+    if (q < total) {
+      const int32_t a = aid[src];
+      tail_aw[T0 + q] = (uint32_t)a | ((uint32_t)type[src] << 30);
+      tail_ts[T0 + q] = ts[src];
+      if (n > 1) atomicAdd(&pair_ub[a], n - 1);
+    }
+  }
+}
+
 // sub-bins per aid_x row: ceil(ub / split_ub), at least 1
 __global__ void bins_count_kernel(const uint32_t* __restrict__ pair_ub, int64_t A, uint32_t split_ub,
                                   uint32_t* __restrict__ nb, unsigned long long* stats) {
@@ -215,11 +254,12 @@ __global__ void bins_fill_kernel(const uint32_t* __restrict__ bin_base, int64_t 
   for (uint32_t b = bin_base[x]; b < bin_base[x + 1]; ++b) bin_x[b] = (uint32_t)x;
 }
 
+// record positions fit 32 bits (otto_covisit_scatter rejects P >= 2^32)
 __global__ void init_cursor_kernel(const unsigned long long* __restrict__ bin_off, const uint32_t* __restrict__ bin_base,
-                                   int64_t A, unsigned long long* __restrict__ cursor) {
+                                   int64_t A, uint32_t* __restrict__ cursor) {
   const int64_t B = bin_base[A];
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x)
-    cursor[b] = bin_off[b];
+    cursor[b] = (uint32_t)bin_off[b];
 }
 
 // stats[0] tail events, [1] pairs, [2] bins ([3] split rows is counted by bins_count_kernel)
@@ -265,7 +305,12 @@ extern "C" int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitS
   }
   if ((rc = exclusive_scan<uint32_t, uint32_t>(WS(uint32_t, tail_off), S, WS(uint32_t, tail_off), WS(uint32_t, scan), st)))
     return rc;
-  if (S > 0) {
+  if (S > 0 && (spec->event_type_mask & 7u) == 7u) {
+    tail_copy_all_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(ev->session_offsets, ev->aid, ev->ts, ev->type, S,
+                                                                     WS(uint32_t, tail_off), WS(uint32_t, tail_aw),
+                                                                     WS(int32_t, tail_ts), WS(uint32_t, pair_ub));
+    LAUNCH_CHECK();
+  } else if (S > 0) {
     tail_copy_kernel<<<(unsigned)ceil_div(S, 8), 256, 0, st>>>(ev->session_offsets, ev->aid, ev->ts, ev->type, S,
                                                                spec->event_type_mask, WS(uint32_t, tail_off),
                                                                WS(uint32_t, tail_aw), WS(int32_t, tail_ts),
@@ -283,7 +328,7 @@ static PairGenParams make_pairgen(const Layout& L, const OttoCovisitSpec* spec, 
   p.winmask = WS(uint32_t, winmask);
   p.bin_base = WS(uint32_t, bin_base);
   p.hist = WS(uint32_t, hist);
-  p.cursor = WS(unsigned long long, cursor);
+  p.cursor = WS(uint32_t, cursor);
   p.records = nullptr;
   p.n_sessions = L.S;
   p.window = (uint32_t)spec->window_s;
@@ -367,9 +412,10 @@ extern "C" int otto_covisit_scatter(const OttoEvents* ev, const OttoCovisitSpec*
   const Layout L = make_layout(ev->n_sessions, ev->n_events, spec);
   if ((rc = check_ws(L, workspace, workspace_bytes))) return rc;
   if (!records && records_capacity > 0) { otto_set_error("records is NULL"); return OTTO_EINVAL; }
+  if (records_capacity >= (1ll << 32)) { otto_set_error("a rank is limited to 2^32 - 1 pair records (32 GiB); shard the sessions"); return OTTO_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
   init_cursor_kernel<<<592, 256, 0, st>>>(WS(unsigned long long, bin_off), WS(uint32_t, bin_base), L.A,
-                                          WS(unsigned long long, cursor));
+                                          WS(uint32_t, cursor));
   LAUNCH_CHECK();
   if (L.S > 0) {
     PairGenParams p = make_pairgen(L, spec, workspace);

@@ -7,22 +7,27 @@
 // (ts desc, row asc) order as two 4-byte columns: aw = aid | type << 30 and ts.  Because the tails of
 // consecutive sessions are contiguous, a warp takes 32 consecutive sessions, then repeatedly packs as
 // many whole sessions as fit into its 32 lanes (one event per lane).  One coalesced load brings the
-// batch in; every later step is register / shuffle work:
-//   row loop i = 0..max_n-1: each session group broadcasts its i-th event (aid_x, ts_x, type_x) and every
-//   lane j of the group decides "pair (i, j) valid" (window, aid_x != aid_y, type masks).  The dedupe
-//   winner of pandas' drop_duplicates(['session','aid_x','aid_y']) (first row in i-major, j-minor
-//   order) is found with three 32-bit masks per lane:
-//     same   lanes of my session holding my aid          (one __match_any_sync per batch)
-//     v      ballot of valid lanes of this row
-//     cov    rows (by owner lane) in which my aid was valid as aid_y
-//   lane j wins row i  <=>  valid  &&  no earlier lane of the row has my aid (v & same & lt == 0)
-//                           &&  no earlier row with the same aid_x covered my aid (cov & samelt_x == 0).
-//   The winner mask of row i is kept by the lane that owns event i ("row owner").
-// Pass 1 (count) stores the group-relative winner masks (4 B per tail event) and adds the per-row pair
-// counts into the bin histogram: one RED per (session, row) for ordinary rows, one per pair for rows that
-// are split into aid_y-hash sub-bins (hot aid_x).  Pass 2 (scatter) re-reads events + masks, reserves the
-// row's slots with one atomic per (session, row) and writes 8-byte records {aid_y, v}; aid_x is implicit
-// in the bin.  v = ts_x - ts_min (time), type_weight[type_y] (type) or 1 (unit).
+// batch in; every later step is register / shuffle work.
+//
+// Pass 1 (count) finds, for every lane j (an event in its role as aid_y), the 32-bit COLUMN mask of the
+// rows i (events of the same session in their role as aid_x) for which (i, j) is the row pandas keeps in
+//   merge(on='session') -> |ts_x - ts_y| < W, aid_x != aid_y -> drop_duplicates(['session','aid_x','aid_y'])
+// (first row in i-major, j-minor order).  Because a session is sorted by ts, the window of an event is a
+// contiguous lane range [lo, hi] (found by a 5-step binary descent, skipped when the whole session spans
+// less than W), which makes the dedupe O(1) per lane instead of a loop over rows (v1-v3 of this kernel):
+//   V_j   = range(lo_j, hi_j) & ~same_j                      rows in window with another aid
+//   y side  a row keeps the first in-window occurrence of aid_y: rows i <= hi_prev(j) already saw the
+//           previous occurrence of my aid, so  V_j &= ~lowmask(hi_prev + 1)
+//   x side  of several rows with the same aid_x only the first that sees ANY occurrence of aid_y keeps
+//           the pair: U_j = union of V over the occurrences of my aid; row i is dropped when an earlier
+//           row with the same aid is in U_j.  Only lanes that repeat an aid can be dropped, so this is a
+//           loop over the (few) repeat lanes of the batch, not over rows.
+// A 5-step butterfly transposes the column masks into ROW masks (bit j of row i), which are stored
+// (4 B per tail event) and whose popcounts feed the bin histogram: one RED per (session, row) for ordinary
+// rows, one per pair for rows that are split into aid_y-hash sub-bins (hot aid_x).
+// Pass 2 (scatter) re-reads events + row masks, reserves the row's slots with one atomic per
+// (session, row) and writes 8-byte records {aid_y, v}; aid_x is implicit in the bin.
+// v = ts_x - ts_min (time), type_weight[type_y] (type) or 1 (unit).
 #pragma once
 #include "common.cuh"
 
@@ -33,7 +38,7 @@ struct PairGenParams {
   uint32_t* winmask;          // [E30]
   const uint32_t* bin_base;   // [A + 1]
   uint32_t* hist;             // [B]      pass 1
-  unsigned long long* cursor; // [B]      pass 2 (starts as the exclusive scan of hist)
+  uint32_t* cursor;           // [B]      pass 2 (starts as the exclusive scan of hist; P < 2^32)
   uint2* records;             //          pass 2
   int64_t n_sessions;
   uint32_t window;
@@ -43,11 +48,21 @@ struct PairGenParams {
   uint32_t type_weight[3];
 };
 
-__device__ __forceinline__ uint32_t abs_diff_i32(int32_t a, int32_t b) {
-  return a > b ? (uint32_t)a - (uint32_t)b : (uint32_t)b - (uint32_t)a;
-}
-
 constexpr int PAIRGEN_WARPS = 8;
+
+__device__ __forceinline__ uint32_t lowmask(int k) { return k >= 32 ? FULL_MASK : ((1u << k) - 1u); }
+
+// 32 x 32 bit-matrix transpose across the lanes of a warp: on return lane i holds bit i of every lane's x
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x) {
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const uint32_t m = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t o = __shfl_xor_sync(FULL_MASK, x, s);
+    x = (lane & s) ? ((x & ~m) | ((o >> s) & m)) : ((x & m) | ((o << s) & ~m));
+  }
+  return x;
+}
 
 template <bool SCATTER>
 __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairGenParams p) {
@@ -57,6 +72,7 @@ __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairG
   const int64_t s0 = warp * 32;
   if (s0 >= p.n_sessions) return;
   const int ns = (int)min((int64_t)32, p.n_sessions - s0);
+  const bool masks_on = ((p.x_type_mask & p.y_type_mask & 7u) != 7u);
 
   // lane l: tail offsets of session s0 + l (clamped so every lane holds a valid pair)
   const uint32_t o = p.tail_off[s0 + min((int)lane, ns)];
@@ -74,13 +90,12 @@ __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairG
     a = b;
 
     const bool active = lane < total;
-    // my session's lanes: [base, base + n)
+    // my session's lanes: [base, gend)
     const uint32_t le = heads & (FULL_MASK >> (31 - lane));
     const uint32_t gt = heads & ~(FULL_MASK >> (31 - lane));
     const int base = active ? 31 - __clz(le) : (int)lane;
     const int gend = active ? (gt ? __ffs(gt) - 1 : (int)total) : (int)lane + 1;
     const int n = gend - base;
-    const uint32_t grpmask = active ? ((n >= 32 ? FULL_MASK : ((1u << n) - 1u)) << base) : 0u;
     const int maxn = __reduce_max_sync(FULL_MASK, active ? n : 0);
 
     const uint32_t aw = active ? p.tail_aw[e0 + lane] : (0x80000000u | lane);
@@ -95,64 +110,123 @@ __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairG
       nbx = p.bin_base[aid + 1] - bb0;
     }
 
-    uint32_t mywm = 0;  // winner lanes of the row I own (absolute lane bits)
     if (!SCATTER) {
+      const uint32_t grpmask = active ? (lowmask(n) << base) : 0u;
       const uint32_t same = __match_any_sync(FULL_MASK, active ? aid : (0x80000000u | lane)) & grpmask;
-      const uint32_t samelt = same & lt;
-      const bool y_ok = active && ((p.y_type_mask >> ty) & 1u);
-      uint32_t cov = 0;
-      for (int i = 0; i < maxn; ++i) {
-        const bool rowact = active && i < n;
-        const int src = rowact ? base + i : (int)lane;
-        const uint32_t axw = __shfl_sync(FULL_MASK, aw, src);
-        const int32_t tx = __shfl_sync(FULL_MASK, t, src);
-        const uint32_t sx = __shfl_sync(FULL_MASK, samelt, src);
-        const bool valid = rowact && y_ok && ((axw & AID_MASK) != aid) && (abs_diff_i32(tx, t) < p.window) &&
-                           ((p.x_type_mask >> (axw >> 30)) & 1u);
-        const uint32_t v = __ballot_sync(FULL_MASK, valid) & grpmask;
-        const bool win = valid && !(v & samelt) && !(cov & sx);
-        const uint32_t wmi = __ballot_sync(FULL_MASK, win) & grpmask;
-        if (rowact && (int)lane == src) mywm = wmi;
-        if (v & same) cov |= 1u << src;
+      bool y_ok = active, x_ok = active;
+      uint32_t xrows = FULL_MASK, yok_m = FULL_MASK;
+      if (masks_on) {
+        y_ok = active && ((p.y_type_mask >> ty) & 1u);
+        x_ok = active && ((p.x_type_mask >> ty) & 1u);
+        xrows = __ballot_sync(FULL_MASK, x_ok);
+        yok_m = __ballot_sync(FULL_MASK, y_ok);
       }
-      if (active) p.winmask[e0 + lane] = mywm >> base;
-      const uint32_t cnt = __popc(mywm);
-      if (active && cnt && nbx == 1) atomicAdd(&p.hist[bb0], cnt);
-      // split rows: one RED per pair into the aid_y-hash sub-bin
-      if (__ballot_sync(FULL_MASK, active && cnt && nbx > 1)) {
-        for (int i = 0; i < maxn; ++i) {
-          const bool rowact = active && i < n;
-          const int src = rowact ? base + i : (int)lane;
-          const uint32_t wmi = __shfl_sync(FULL_MASK, mywm, src);
-          const uint32_t nbi = __shfl_sync(FULL_MASK, nbx, src);
-          const uint32_t bbi = __shfl_sync(FULL_MASK, bb0, src);
-          if (rowact && nbi > 1 && ((wmi >> lane) & 1u)) atomicAdd(&p.hist[bbi + sub_bin(aid, nbi)], 1u);
+      // window [lo, hi] of my event (lane indices); a session is sorted by ts descending
+      int lo = base, hi = gend - 1;
+      const int32_t t_first = __shfl_sync(FULL_MASK, t, base);
+      const int32_t t_last = __shfl_sync(FULL_MASK, t, gend - 1);
+      if (__any_sync(FULL_MASK, active && (uint32_t)(t_first - t_last) >= p.window)) {
+        lo = hi = (int)lane;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+          const int cl = lo - step, ch = hi + step;
+          const bool okl = active && cl >= base, okh = active && ch < gend;
+          const int32_t tl = __shfl_sync(FULL_MASK, t, okl ? cl : (int)lane);
+          const int32_t th = __shfl_sync(FULL_MASK, t, okh ? ch : (int)lane);
+          if (okl && (uint32_t)(tl - t) < p.window) lo = cl;
+          if (okh && (uint32_t)(t - th) < p.window) hi = ch;
         }
       }
-    } else {
-      mywm = active ? (p.winmask[e0 + lane] << base) : 0u;
-      const uint32_t cnt = __popc(mywm);
-      unsigned long long slot = 0;
-      if (active && cnt && nbx == 1) slot = atomicAdd(&p.cursor[bb0], (unsigned long long)cnt);
-      uint32_t v = 1;
-      if (p.weight_mode == OTTO_WEIGHT_TYPE) v = ty == 0 ? p.type_weight[0] : (ty == 1 ? p.type_weight[1] : p.type_weight[2]);
-      if (__ballot_sync(FULL_MASK, cnt != 0)) {
-        for (int i = 0; i < maxn; ++i) {
-          const bool rowact = active && i < n;
-          const int src = rowact ? base + i : (int)lane;
-          const uint32_t wmi = __shfl_sync(FULL_MASK, mywm, src);
-          const unsigned long long sloti = shfl_u64(slot, src);
-          const uint32_t nbi = __shfl_sync(FULL_MASK, nbx, src);
-          const uint32_t bbi = __shfl_sync(FULL_MASK, bb0, src);
-          const int32_t tx = __shfl_sync(FULL_MASK, t, src);
-          if (rowact && ((wmi >> lane) & 1u)) {
-            unsigned long long pos;
-            if (nbi == 1) pos = sloti + __popc(wmi & lt);
-            else pos = atomicAdd(&p.cursor[bbi + sub_bin(aid, nbi)], 1ull);
-            const uint32_t val = p.weight_mode == OTTO_WEIGHT_TIME ? (uint32_t)(tx - p.ts_min) : v;
-            st_stream_u2(p.records + pos, make_uint2(aid, val));
+      uint32_t V = y_ok ? ((lowmask(hi - lo + 1) << lo) & ~same & xrows) : 0u;
+      // y side: rows up to hi(previous occurrence of my aid that may act as aid_y) keep that occurrence
+      const uint32_t prevs = same & lt & yok_m;
+      const int prev = prevs ? 31 - __clz(prevs) : (int)lane;
+      const int hi_prev = __shfl_sync(FULL_MASK, hi, prev);
+      if (prevs) V &= ~lowmask(hi_prev + 1);
+      // x side: only lanes that repeat an aid can lose a pair to an earlier row with the same aid
+      const uint32_t rep = __ballot_sync(FULL_MASK, active && (same & lt) != 0);
+      if (rep) {
+        const int first = same ? __ffs(same) - 1 : (int)lane;
+        uint32_t U = V | __shfl_sync(FULL_MASK, V, first);
+        for (uint32_t m = rep; m; m &= m - 1) {
+          const int d = __ffs(m) - 1;
+          const uint32_t vd = __shfl_sync(FULL_MASK, V, d);
+          if ((same >> d) & 1u) U |= vd;
+        }
+        const uint32_t earlier_x = same & lt & xrows;     // earlier rows with my aid that may act as aid_x
+        for (uint32_t m = rep; m; m &= m - 1) {
+          const int i = __ffs(m) - 1;
+          const uint32_t ei = __shfl_sync(FULL_MASK, earlier_x, i);
+          if (((V >> i) & 1u) && (ei & U)) V &= ~(1u << i);
+        }
+      }
+      // split rows: one RED per pair into the aid_y-hash sub-bin of the row
+      const uint32_t spl = __ballot_sync(FULL_MASK, active && nbx > 1);
+      if (spl) {
+        uint32_t rem = V & spl;
+        const uint32_t hy = hash32(aid);
+        while (__any_sync(FULL_MASK, rem != 0)) {
+          const int i = rem ? __ffs(rem) - 1 : (int)lane;
+          const uint32_t nbi = __shfl_sync(FULL_MASK, nbx, i);
+          const uint32_t bbi = __shfl_sync(FULL_MASK, bb0, i);
+          if (rem) {
+            atomicAdd(&p.hist[bbi + __umulhi(hy, nbi)], 1u);
+            rem &= rem - 1;
           }
         }
+      }
+      // column masks -> row masks; lane i now owns the winners of row i
+      const uint32_t R = warp_transpose32(V);
+      if (active) p.winmask[e0 + lane] = R >> base;
+      const uint32_t cnt = __popc(R);
+      if (active && cnt && nbx == 1) atomicAdd(&p.hist[bb0], cnt);
+    } else {
+      const uint32_t mywm = active ? (p.winmask[e0 + lane] << base) : 0u;
+      const uint32_t cnt = __popc(mywm);
+      const bool split_row = active && nbx > 1;
+      uint32_t slot = 0;
+      if (active && cnt && nbx == 1) slot = atomicAdd(&p.cursor[bb0], cnt);
+      uint32_t v = 1;
+      if (p.weight_mode == OTTO_WEIGHT_TYPE) v = ty == 0 ? p.type_weight[0] : (ty == 1 ? p.type_weight[1] : p.type_weight[2]);
+      const bool time_mode = p.weight_mode == OTTO_WEIGHT_TIME;
+      const int32_t tv = t - p.ts_min;
+      // Split rows: every pair takes its own slot in the aid_y-hash sub-bin of the row.  Done from the
+      // column view (lane j walks the split rows it won) with the atomics of a chunk issued back to back
+      // and the stores behind them, so that one round trip covers SPLIT_CHUNK pairs (a row loop with the
+      // atomic inside serialised one round trip per row: profiles/r01_pairgen_v4).
+      const uint32_t spl = __ballot_sync(FULL_MASK, split_row && cnt);
+      if (spl) {
+        constexpr int SPLIT_CHUNK = 8;
+        uint32_t rem = warp_transpose32(mywm) & spl;
+        const uint32_t hy = hash32(aid);
+        while (__any_sync(FULL_MASK, rem != 0)) {
+          uint32_t pos[SPLIT_CHUNK], val[SPLIT_CHUNK], todo = 0;
+#pragma unroll
+          for (int k = 0; k < SPLIT_CHUNK; ++k) {
+            const int i = rem ? __ffs(rem) - 1 : (int)lane;
+            const uint32_t nbi = __shfl_sync(FULL_MASK, nbx, i);
+            const uint32_t bbi = __shfl_sync(FULL_MASK, bb0, i);
+            val[k] = time_mode ? (uint32_t)__shfl_sync(FULL_MASK, tv, i) : v;
+            pos[k] = 0;
+            if (rem) {
+              pos[k] = atomicAdd(&p.cursor[bbi + __umulhi(hy, nbi)], 1u);
+              todo |= 1u << k;
+              rem &= rem - 1;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < SPLIT_CHUNK; ++k)
+            if ((todo >> k) & 1u) st_stream_u2(p.records + pos[k], make_uint2(aid, val[k]));
+        }
+      }
+      // ordinary rows: row i's winners write one contiguous run
+      const uint32_t wm_run = split_row ? 0u : mywm;
+      for (int i = 0; i < maxn; ++i) {
+        const int src = (active && i < n) ? base + i : (int)lane;   // own row mask never holds the own lane
+        const uint32_t wmi = __shfl_sync(FULL_MASK, wm_run, src);
+        const uint32_t sloti = __shfl_sync(FULL_MASK, slot, src);
+        const uint32_t val = time_mode ? (uint32_t)__shfl_sync(FULL_MASK, tv, src) : v;
+        if ((wmi >> lane) & 1u) st_stream_u2(p.records + (sloti + __popc(wmi & lt)), make_uint2(aid, val));
       }
     }
   }
