@@ -430,7 +430,7 @@ extern "C" int otto_covisit_scatter(const OttoEvents* ev, const OttoCovisitSpec*
 // ------------------------------------------------------------------ reduce
 
 struct ScratchLayout {
-  int64_t p_key, p_sum, p_cnt, p_len, list_m, list_l, counters, stats, total;
+  int64_t p_key, p_sum, p_cnt, p_len, list_m, list_l, list_x, counters, stats, total;
 };
 
 static ScratchLayout make_scratch(int k, int64_t n_bins, int64_t n_aids_range) {
@@ -446,6 +446,7 @@ static ScratchLayout make_scratch(int k, int64_t n_bins, int64_t n_aids_range) {
   s.p_len = take(slots * 4);
   s.list_m = take((n_bins + 1) * 4);
   s.list_l = take((n_bins + 1) * 4);
+  s.list_x = take((n_bins + 1) * 4);
   s.counters = take(64);
   s.stats = take(64);
   s.total = o;
@@ -474,17 +475,24 @@ static int launch_reduce(const ReduceParams& p, int n_sm, cudaStream_t st) {
   reduce_small_kernel<TIME><<<(unsigned)small_blocks, SMALL_WARPS * 32, small_smem, st>>>(p);
   LAUNCH_CHECK();
   {
-    auto kern = reduce_block_kernel<TIME, 128, 11, false>;
-    constexpr size_t smem = reduce_block_smem<TIME, 128, 11>();
+    auto kern = reduce_block_kernel<TIME, 128, 11, 0>;
+    constexpr size_t smem = reduce_block_smem<TIME, 128, 11, 0>();
     if ((rc = set_smem(kern, smem))) return rc;
     kern<<<n_sm * 7, 128, smem, st>>>(p);
     LAUNCH_CHECK();
   }
   {
-    auto kern = reduce_block_kernel<TIME, 256, 12, true>;
-    constexpr size_t smem = reduce_block_smem<TIME, 256, 12>();
+    auto kern = reduce_block_kernel<TIME, 256, 12, 1>;
+    constexpr size_t smem = reduce_block_smem<TIME, 256, 12, 1>();
     if ((rc = set_smem(kern, smem))) return rc;
     kern<<<n_sm * 3, 256, smem, st>>>(p);
+    LAUNCH_CHECK();
+  }
+  {
+    auto kern = reduce_block_kernel<TIME, 512, 13, 2>;
+    constexpr size_t smem = reduce_block_smem<TIME, 512, 13, 2>();
+    if ((rc = set_smem(kern, smem))) return rc;
+    kern<<<n_sm, 512, smem, st>>>(p);
     LAUNCH_CHECK();
   }
   merge_split_rows_kernel<<<n_sm * 4, 256, 0, st>>>(p);
@@ -534,6 +542,7 @@ extern "C" int otto_covisit_reduce(const OttoCovisitSpec* spec, const uint32_t* 
   p.p_len = (int32_t*)(sc + SL.p_len);
   p.list_m = (uint32_t*)(sc + SL.list_m);
   p.list_l = (uint32_t*)(sc + SL.list_l);
+  p.list_x = (uint32_t*)(sc + SL.list_x);
   p.counters = (uint32_t*)(sc + SL.counters);
   p.stats = (unsigned long long*)(sc + SL.stats);
   CUDA_TRY(cudaMemsetAsync(p.counters, 0, 64, st));

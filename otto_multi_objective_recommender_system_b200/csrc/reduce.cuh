@@ -55,14 +55,16 @@ struct ReduceParams {
   // work lists for the block kernels
   uint32_t* list_m;
   uint32_t* list_l;
-  uint32_t* counters;        // [0] n_m  [1] n_l  [2] next_m  [3] next_l
+  uint32_t* list_x;
+  uint32_t* counters;        // [0] n_m  [1] n_l  [2] next_m  [3] next_l  [4] n_x  [5] next_x
   unsigned long long* stats; // [0] distinct  [1] checksum  [2] overflow  [3] slow-path selections
 };
 
+constexpr uint32_t TINY_MAX = 32;      // records: one step of one warp, no table at all
 constexpr uint32_t SMALL_MAX = 256;    // records: warp kernel, 512-slot table
 constexpr uint32_t MEDIUM_MAX = 1024;  // records: 128-thread kernel, 2048-slot table
-constexpr uint32_t LARGE_SLOTS = 4096; // 256-thread kernel; more than LARGE_CAP records -> multi-pass
-constexpr uint32_t LARGE_CAP = 3072;
+constexpr uint32_t LARGE_MAX = 3072;   // records: 256-thread kernel, 4096-slot table
+// beyond: 512-thread kernel, 8192-slot table; single pass up to 3/4 of the slots, else aid_y-hash passes
 
 __device__ __forceinline__ int64_t partial_slot(const ReduceParams& p, uint32_t x, uint32_t j) {
   const int64_t extra = ((int64_t)p.bin_base[x] - x) - (p.bin_lo - p.aid_lo);
@@ -73,6 +75,17 @@ __device__ __forceinline__ uint32_t bin_records(const ReduceParams& p, int64_t b
   uint32_t n = 0;
   for (int s = 0; s < p.n_seg; ++s) n += (uint32_t)(p.seg[s].offsets[b - p.bin_lo + 1] - p.seg[s].offsets[b - p.bin_lo]);
   return n;
+}
+
+// record i of bin b in the concatenation of the segments' runs (i < bin_records)
+__device__ __forceinline__ uint2 bin_record(const ReduceParams& p, int64_t b, uint32_t i) {
+  for (int s = 0; s < p.n_seg; ++s) {
+    const uint64_t beg = p.seg[s].offsets[b - p.bin_lo], end = p.seg[s].offsets[b - p.bin_lo + 1];
+    const uint32_t len = (uint32_t)(end - beg);
+    if (i < len) return ld_stream_u2((const uint2*)p.seg[s].records + (beg - p.seg[s].offsets[0]) + i);
+    i -= len;
+  }
+  return make_uint2(KEY_EMPTY, 0);
 }
 
 // Open-addressing table over SLOTS = 2^LOG slots.  TIME: hc = count | carries << 24, lo = low 32 bits of
@@ -103,24 +116,36 @@ struct Table {
       if (TIME) hc[h] = 0;
     }
   }
-  // returns false on overflow.  The probe loop only finds / claims the slot; the payload atomics run after
-  // the warp has reconverged (profile r01_v3: with the payload inside the loop every probe iteration
-  // executed it for ~4 lanes at a time).
-  __device__ __forceinline__ bool insert(uint32_t y, uint32_t v) {
+  // One record per lane (has = this lane holds one); EVERY lane of the warp must call.  Returns false on
+  // overflow.  The probe loop only finds / claims the slot.  Lanes leave it after different numbers of
+  // probes, and without the __syncwarp() below the compiler keeps them diverged: profile r01_reduce_v3b
+  // shows the payload atomics and the occupied-list append executing with 6.7 of 32 lanes per issue
+  // (45 % of all instructions of the kernel).  After reconvergence the append is one atomic per warp.
+  __device__ __forceinline__ bool insert(bool has, uint32_t y, uint32_t v) {
     uint32_t h = (y * 0x9E3779B1u) >> (32 - LOG);
     int state = 0;  // 1 = found, 2 = claimed a fresh slot
-    for (uint32_t probe = 0; probe < SLOTS; ++probe) {
-      const uint32_t prev = atomicCAS(&keys[h], KEY_EMPTY, y);
-      if (prev == KEY_EMPTY) { state = 2; break; }
-      if (prev == y) { state = 1; break; }
-      h = (h + 1) & (SLOTS - 1);
+    if (has) {
+      for (uint32_t probe = 0; probe < SLOTS; ++probe) {
+        const uint32_t prev = atomicCAS(&keys[h], KEY_EMPTY, y);
+        if (prev == KEY_EMPTY) { state = 2; break; }
+        if (prev == y) { state = 1; break; }
+        h = (h + 1) & (SLOTS - 1);
+      }
     }
-    if (state == 2) occ[atomicAdd(n_occ, 1u)] = (uint16_t)h;
+    __syncwarp();
+    const uint32_t fresh = __ballot_sync(FULL_MASK, state == 2);
+    if (fresh) {
+      const int leader = __ffs(fresh) - 1;
+      uint32_t base = 0;
+      if ((int)lane_id() == leader) base = atomicAdd(n_occ, (uint32_t)__popc(fresh));
+      base = __shfl_sync(FULL_MASK, base, leader);
+      if (state == 2) occ[base + __popc(fresh & lanemask_lt())] = (uint16_t)h;
+    }
     if (state != 0) {
       const uint32_t old = atomicAdd(&lo[h], v);
       if (TIME) atomicAdd(&hc[h], 1u + ((old + v < old) ? (1u << 24) : 0u));
     }
-    return state != 0;
+    return state != 0 || !has;
   }
   __device__ __forceinline__ uint32_t count(uint32_t h) const { return TIME ? (hc[h] & 0xffffffu) : 0u; }
   __device__ __forceinline__ uint64_t sum(uint32_t h) const {
@@ -284,7 +309,7 @@ __device__ __forceinline__ void push_candidate(bool q, uint32_t* n_cand, const C
 constexpr int SMALL_WARPS = 4;
 constexpr int SMALL_LOG = 9;           // 512 slots
 constexpr int SMALL_CANDS = 64;
-constexpr int SMALL_DIRECT = 40;       // up to this many distinct entries: skip the threshold
+constexpr int SMALL_DIRECT = 32;       // up to this many distinct entries: skip the threshold
 // per warp: cand key[64] sum[64] (u64) | keys[512] lo[512] hc[512] cand cnt[64] counters[4] (u32) | occ[256] (u16)
 constexpr uint32_t SMALL_PER_WARP = SMALL_CANDS * 16 + (1u << SMALL_LOG) * 12 + SMALL_CANDS * 4 + 16 + SMALL_MAX * 2;
 
@@ -317,7 +342,8 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const Re
     if (n > SMALL_MAX) {  // hand over to a block kernel
       if (lane == 0) {
         if (n <= MEDIUM_MAX) p.list_m[atomicAdd(&p.counters[0], 1u)] = (uint32_t)(b - p.bin_lo);
-        else p.list_l[atomicAdd(&p.counters[1], 1u)] = (uint32_t)(b - p.bin_lo);
+        else if (n <= LARGE_MAX) p.list_l[atomicAdd(&p.counters[1], 1u)] = (uint32_t)(b - p.bin_lo);
+        else p.list_x[atomicAdd(&p.counters[4], 1u)] = (uint32_t)(b - p.bin_lo);
       }
       continue;
     }
@@ -326,14 +352,46 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const Re
       emit_finish(p, o, 0);
       continue;
     }
+    if (n <= TINY_MAX) {
+      // the whole bin is one step: fold duplicates with match_any, rank the group leaders, done
+      const bool has = lane < n;
+      uint2 r = make_uint2(0x80000000u | lane, 0);
+      if (has) r = bin_record(p, b, lane);
+      const uint32_t lt = lanemask_lt();
+      const uint32_t peers = __match_any_sync(FULL_MASK, r.x);
+      const bool lead = has && (peers & lt) == 0;
+      const uint32_t cnt = TIME ? (uint32_t)__popc(peers) : 0u;
+      uint64_t sum = r.y;
+      uint32_t rest = lead ? (peers & (peers - 1)) : 0u;
+      while (__any_sync(FULL_MASK, rest != 0)) {
+        const int src = rest ? __ffs(rest) - 1 : (int)lane;
+        const uint32_t vv = __shfl_sync(FULL_MASK, r.y, src);
+        if (rest) {
+          sum += vv;
+          rest &= rest - 1;
+        }
+      }
+      const uint64_t key = lead ? float_key(TIME, r.x, cnt, sum, p.w_scale) : 0ull;
+      const uint32_t lm = __ballot_sync(FULL_MASK, lead);
+      int rank = 0;
+      for (uint32_t m = lm; m; m &= m - 1) rank += shfl_u64(key, __ffs(m) - 1) > key;
+      if (lead && rank < p.k) emit_entry(p, o, rank, key, cnt, sum);
+      const int nl = __popc(lm);
+      emit_finish(p, o, nl < p.k ? nl : p.k);
+      if (lane == 0) st_occ += nl;
+      if (lead) st_pay += TIME ? (uint64_t)cnt : sum;
+      continue;
+    }
     if (lane == 0) *n_cand = 0;
     for (int s = 0; s < p.n_seg; ++s) {
       const uint64_t o0 = p.seg[s].offsets[0];
       const uint64_t beg = p.seg[s].offsets[b - p.bin_lo] - o0, end = p.seg[s].offsets[b - p.bin_lo + 1] - o0;
       const uint2* rec = (const uint2*)p.seg[s].records;
-      for (uint64_t i = beg + lane; i < end; i += 32) {
-        const uint2 r = ld_stream_u2(rec + i);
-        if (!t.insert(r.x, r.y)) overflow = true;
+      for (uint64_t i0 = beg; i0 < end; i0 += 32) {
+        const bool has = i0 + lane < end;
+        uint2 r = make_uint2(0, 0);
+        if (has) r = ld_stream_u2(rec + i0 + lane);
+        if (!t.insert(has, r.x, r.y)) overflow = true;
       }
     }
     __syncwarp();
@@ -396,7 +454,9 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const Re
 // ---- medium / large bins: one block per bin, work taken from a list through an atomic cursor ----
 constexpr int BLOCK_CANDS = 128;
 
-template <bool TIME, int THREADS, int LOG, bool LARGE>
+// TIER 0: medium list, 1: large list, 2: extra-large list (single pass up to 3/4 of the slots, otherwise
+// aid_y-hash passes whose records are first compacted per warp so that every insert step runs 32 wide)
+template <bool TIME, int THREADS, int LOG, int TIER>
 __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int WARPS = THREADS / 32;
@@ -421,35 +481,67 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
   best.cnt = c.cnt + NCX;
   t.occ = (uint16_t*)(best.cnt + OTTO_MAX_K);
   t.n_occ = &s_nocc;
+  uint2* stage = (uint2*)(t.occ + SLOTS) + warp * 64;    // TIER 2 only (see reduce_block_smem)
+  constexpr int CUR = TIER == 0 ? 2 : TIER == 1 ? 3 : 5;
+  constexpr uint32_t SINGLE_CAP = TIER == 2 ? SLOTS / 4 * 3 : 0xffffffffu;
+  const uint32_t lt = lanemask_lt();
 
-  const uint32_t* list = LARGE ? p.list_l : p.list_m;
-  const uint32_t n_items = p.counters[LARGE ? 1 : 0];
+  const uint32_t* list = TIER == 0 ? p.list_m : TIER == 1 ? p.list_l : p.list_x;
+  const uint32_t n_items = p.counters[TIER == 0 ? 0 : TIER == 1 ? 1 : 4];
   uint64_t st_occ = 0, st_pay = 0;
   uint32_t st_slow = 0;
   bool overflow = false;
   t.clear_all(threadIdx.x, THREADS);
-  if (threadIdx.x == 0) s_item = atomicAdd(&p.counters[LARGE ? 3 : 2], 1u);
+  if (threadIdx.x == 0) s_item = atomicAdd(&p.counters[CUR], 1u);
   __syncthreads();
   while (true) {
     const uint32_t item = s_item;
     if (item >= n_items) break;
     const int64_t b = p.bin_lo + list[item];
     const uint32_t n = bin_records(p, b);
-    const uint32_t n_pass = (LARGE && n > LARGE_CAP) ? (n + LARGE_CAP - 1) / LARGE_CAP : 1;
+    const uint32_t n_pass = n > SINGLE_CAP ? (n + SLOTS / 2 - 1) / (SLOTS / 2) : 1;
     const BinOut o = bin_out(p, b);
     int n_best = 0;  // meaningful in warp 0
     for (uint32_t pass = 0; pass < n_pass; ++pass) {
       const bool last = pass + 1 == n_pass;
       if (threadIdx.x == 0) s_ncand = 0;
+      uint32_t n_st = 0;   // records staged by this warp (multi-pass only)
       for (int s = 0; s < p.n_seg; ++s) {
         const uint64_t o0 = p.seg[s].offsets[0];
         const uint64_t beg = p.seg[s].offsets[b - p.bin_lo] - o0, end = p.seg[s].offsets[b - p.bin_lo + 1] - o0;
         const uint2* rec = (const uint2*)p.seg[s].records;
-        for (uint64_t i = beg + threadIdx.x; i < end; i += THREADS) {
-          const uint2 r = ld_stream_u2(rec + i);
-          if (n_pass > 1 && __umulhi(hash32b(r.x), n_pass) != pass) continue;
-          if (!t.insert(r.x, r.y)) overflow = true;
+        // software pipeline: the next record is in flight while the current one is inserted
+        bool has_n = beg + threadIdx.x < end;
+        uint2 r_n = make_uint2(0, 0);
+        if (has_n) r_n = ld_stream_u2(rec + beg + threadIdx.x);
+        for (uint64_t i0 = beg; i0 < end; i0 += THREADS) {
+          bool has = has_n;
+          const uint2 r = r_n;
+          has_n = i0 + THREADS + threadIdx.x < end;
+          if (has_n) r_n = ld_stream_u2(rec + i0 + THREADS + threadIdx.x);
+          if (n_pass == 1) {
+            if (!t.insert(has, r.x, r.y)) overflow = true;
+          } else {
+            has = has && __umulhi(hash32b(r.x), n_pass) == pass;
+            const uint32_t m = __ballot_sync(FULL_MASK, has);
+            if (has) stage[n_st + __popc(m & lt)] = r;
+            n_st += __popc(m);
+            __syncwarp();
+            if (n_st >= 32) {
+              n_st -= 32;
+              const uint2 q = stage[n_st + lane];
+              __syncwarp();
+              if (!t.insert(true, q.x, q.y)) overflow = true;
+            }
+          }
         }
+      }
+      if (n_pass > 1 && n_st) {
+        uint2 q = make_uint2(0, 0);
+        if (lane < n_st) q = stage[lane];
+        __syncwarp();
+        if (!t.insert(lane < n_st, q.x, q.y)) overflow = true;
+        n_st = 0;
       }
       __syncthreads();
       const uint32_t d = s_nocc;
@@ -544,7 +636,7 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
       }
       if (threadIdx.x == THREADS - 1) {
         s_nocc = 0;
-        if (last) s_item = atomicAdd(&p.counters[LARGE ? 3 : 2], 1u);
+        if (last) s_item = atomicAdd(&p.counters[CUR], 1u);
       }
       __syncthreads();
     }
@@ -562,13 +654,14 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
   if (overflow) atomicOr(&p.stats[2], 1ull);
 }
 
-template <bool TIME, int THREADS, int LOG>
+template <bool TIME, int THREADS, int LOG, int TIER>
 constexpr size_t reduce_block_smem() {
   constexpr int NC = BLOCK_CANDS + OTTO_MAX_K;
   constexpr int WARPS = THREADS / 32;
   constexpr int NCX = (NC > WARPS * OTTO_MAX_K ? NC : WARPS * OTTO_MAX_K) + OTTO_MAX_K;
   constexpr size_t SLOTS = (size_t)1 << LOG;
-  return (size_t)NCX * 16 + OTTO_MAX_K * 16 + SLOTS * 8 + (TIME ? SLOTS * 4 : 0) + NCX * 4 + OTTO_MAX_K * 4 + SLOTS * 2;
+  return (size_t)NCX * 16 + OTTO_MAX_K * 16 + SLOTS * 8 + (TIME ? SLOTS * 4 : 0) + NCX * 4 + OTTO_MAX_K * 4 + SLOTS * 2 +
+         (TIER == 2 ? (size_t)WARPS * 64 * 8 : 0);
 }
 
 // ---- split rows: merge the slices' partial lists (disjoint aid_y) into the final row ----
