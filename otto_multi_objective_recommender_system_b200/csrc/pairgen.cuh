@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairG
       // atomic inside serialised one round trip per row: profiles/r01_pairgen_v4).
       const uint32_t spl = __ballot_sync(FULL_MASK, split_row && cnt);
       if (spl) {
-        constexpr int SPLIT_CHUNK = 8;
+        constexpr int SPLIT_CHUNK = 4;
         uint32_t rem = warp_transpose32(mywm) & spl;
         const uint32_t hy = hash32(aid);
         while (__any_sync(FULL_MASK, rem != 0)) {
