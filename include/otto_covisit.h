@@ -173,6 +173,16 @@ int otto_covisit_reduce(const OttoCovisitSpec* spec, const uint32_t* bin_base, c
                         int32_t n_segments, void* scratch, int64_t scratch_bytes, const OttoTopK* out,
                         OttoBuildStats* stats_host, void* stream);
 
+/* Multi-GPU owner side: gathers the G received segments of bins [0, n_bins) into ONE bin-contiguous record
+ * array (merged_records, capacity >= sum of all segment lengths) with offsets merged_offsets [n_bins + 1],
+ * so that the reduce kernels stream each bin as a single run (with G runs per bin every small bin costs G
+ * partial warp steps).  scratch: otto_covisit_merge_scratch_bytes(n_bins).  *n_records_host (optional)
+ * receives the total and synchronises. */
+int64_t otto_covisit_merge_scratch_bytes(int64_t n_bins);
+int otto_covisit_merge_segments(const OttoPairSegment* segments_host, int32_t n_segments, int64_t n_bins,
+                                void* merged_records, int64_t merged_capacity, uint64_t* merged_offsets, void* scratch,
+                                int64_t scratch_bytes, int64_t* n_records_host, void* stream);
+
 /* One-shot single-GPU build; the pair records and the reduce scratch are carved from the workspace after
  * the fixed part.  Returns OTTO_ENOSPC (stats_host->pairs / bins set) when the workspace cannot hold
  * them; otto_covisit_build_bytes gives the size to retry with. */

@@ -85,6 +85,8 @@ _SIGNATURES = {
     "otto_covisit_reduce_scratch_bytes": (i64, [P(OttoCovisitSpec), i64, i64]),
     "otto_covisit_reduce": (C.c_int, [P(OttoCovisitSpec), vp, vp, i64, i64, i32, i32, P(OttoPairSegment), i32, vp,
                                       i64, P(OttoTopK), P(OttoBuildStats), vp]),
+    "otto_covisit_merge_scratch_bytes": (i64, [i64]),
+    "otto_covisit_merge_segments": (C.c_int, [P(OttoPairSegment), i32, i64, vp, i64, vp, vp, i64, P(i64), vp]),
     "otto_covisit_build": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(OttoTopK), P(OttoBuildStats), vp]),
     "otto_covisit_build_bytes": (i64, [i64, i64, P(OttoCovisitSpec), i64, i64]),
     "otto_topk_row_offsets": (C.c_int, [P(OttoTopK), vp, P(i64), vp, i64, vp]),

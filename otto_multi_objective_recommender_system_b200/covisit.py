@@ -170,6 +170,20 @@ class TopKTable:
             N.check(lib.otto_topk_to_rows(C.byref(tc), row_off.data_ptr(), ax.data_ptr(), ay.data_ptr(), w.data_ptr(), st))
         return ax, ay, w
 
+    def to_host_rows(self, buffers: list | None = None):
+        """to_rows() copied into pinned host memory (a pageable .cpu() runs at ~2 GB/s, pinned at PCIe speed).
+        `buffers`: pinned tensors from an earlier call, reused when large enough.  Returns (ax, ay, w, buffers)."""
+        rows = self.to_rows()
+        n = rows[0].numel()
+        if buffers is None or buffers[0].numel() < n:
+            buffers = [torch.empty(max(n, 1), dtype=r.dtype, pin_memory=True) for r in rows]
+        out = []
+        for r, b in zip(rows, buffers):
+            b[:n].copy_(r, non_blocking=True)
+            out.append(b[:n])
+        torch.cuda.current_stream(self.aid_y.device).synchronize()
+        return out[0], out[1], out[2], buffers
+
     def to_pandas(self):
         import pandas as pd
         ax, ay, w = self.to_rows()
@@ -278,6 +292,21 @@ class CovisitBuilder:
                                                  self.scratch.data_ptr(), self.scratch.numel(), C.byref(tc),
                                                  C.byref(self.stats) if sync else None, self._st()))
         return table
+
+    def merge_segments(self, segments, n_bins: int):
+        """Multi-GPU owner side: the G received (records, offsets) segments of my bins -> one bin-contiguous
+        segment, so that the reduce kernels see a single run per bin."""
+        total_cap = sum(int(r.numel()) for r, _ in segments)
+        merged = torch.empty(max(total_cap, 1), dtype=torch.int64, device=self.device)
+        offsets = torch.empty(n_bins + 1, dtype=torch.int64, device=self.device)
+        need = int(self.lib.otto_covisit_merge_scratch_bytes(n_bins))
+        scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        segs = (N.OttoPairSegment * len(segments))(*[N.OttoPairSegment(r.data_ptr(), o.data_ptr()) for r, o in segments])
+        n = C.c_int64(0)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.otto_covisit_merge_segments(segs, len(segments), n_bins, merged.data_ptr(), merged.numel(),
+                                                         offsets.data_ptr(), scratch.data_ptr(), need, C.byref(n), self._st()))
+        return merged, offsets
 
     # -- whole build --------------------------------------------------------------------------
     def build(self, sync: bool = True) -> TopKTable:

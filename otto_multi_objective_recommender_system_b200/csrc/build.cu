@@ -569,6 +569,74 @@ extern "C" int otto_covisit_reduce(const OttoCovisitSpec* spec, const uint32_t* 
   return OTTO_OK;
 }
 
+// ------------------------------------------------------------------ multi-GPU: merge the received segments
+
+struct MergeParams {
+  OttoPairSegment seg[OTTO_MAX_SEGMENTS];
+  int32_t n_seg;
+  int64_t n_bins;
+};
+
+__global__ void merge_count_kernel(const MergeParams p, unsigned long long* __restrict__ total) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.n_bins) return;
+  unsigned long long n = 0;
+  for (int s = 0; s < p.n_seg; ++s) n += p.seg[s].offsets[b + 1] - p.seg[s].offsets[b];
+  total[b] = n;
+}
+
+// one warp per bin: the runs of the segments, in segment order, back to back
+__global__ void __launch_bounds__(256)
+    merge_copy_kernel(const MergeParams p, const unsigned long long* __restrict__ merged_off, uint2* __restrict__ dst) {
+  const uint32_t lane = lane_id();
+  const int64_t n_warps = (int64_t)gridDim.x * 8;
+  for (int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); b < p.n_bins; b += n_warps) {
+    unsigned long long at = merged_off[b];
+    for (int s = 0; s < p.n_seg; ++s) {
+      const uint64_t beg = p.seg[s].offsets[b] - p.seg[s].offsets[0], end = p.seg[s].offsets[b + 1] - p.seg[s].offsets[0];
+      const uint2* src = (const uint2*)p.seg[s].records;
+      for (uint64_t i = beg + lane; i < end; i += 32) st_stream_u2(dst + at + (i - beg), ld_stream_u2(src + i));
+      at += end - beg;
+    }
+  }
+}
+
+extern "C" int64_t otto_covisit_merge_scratch_bytes(int64_t n_bins) { return scan_scratch_elems(n_bins + 1) * 8 + 256; }
+
+extern "C" int otto_covisit_merge_segments(const OttoPairSegment* segments_host, int32_t n_segments, int64_t n_bins,
+                                           void* merged_records, int64_t merged_capacity, uint64_t* merged_offsets,
+                                           void* scratch, int64_t scratch_bytes, int64_t* n_records_host, void* stream) {
+  if (n_segments < 1 || n_segments > OTTO_MAX_SEGMENTS) { otto_set_error("n_segments must be in [1, 8]"); return OTTO_EINVAL; }
+  if (n_bins < 0 || !merged_offsets) { otto_set_error("bad argument"); return OTTO_EINVAL; }
+  if (scratch_bytes < otto_covisit_merge_scratch_bytes(n_bins)) { otto_set_error("merge scratch too small"); return OTTO_ENOSPC; }
+  cudaStream_t st = (cudaStream_t)stream;
+  MergeParams p;
+  memset(&p, 0, sizeof(p));
+  for (int s = 0; s < n_segments; ++s) p.seg[s] = segments_host[s];
+  p.n_seg = n_segments;
+  p.n_bins = n_bins;
+  unsigned long long* off = (unsigned long long*)merged_offsets;
+  if (n_bins > 0) {
+    merge_count_kernel<<<(unsigned)ceil_div(n_bins, 256), 256, 0, st>>>(p, off);
+    LAUNCH_CHECK();
+  }
+  int rc = exclusive_scan<unsigned long long, unsigned long long>(off, n_bins, off, (unsigned long long*)scratch, st);
+  if (rc) return rc;
+  int64_t total = 0;
+  CUDA_TRY(cudaMemcpyAsync(&total, off + n_bins, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (total > merged_capacity) { otto_set_error("merged_records too small: need %lld records", (long long)total); return OTTO_ENOSPC; }
+  if (n_bins > 0 && total > 0) {
+    int dev = 0, n_sm = 148;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    merge_copy_kernel<<<n_sm * 8, 256, 0, st>>>(p, off, (uint2*)merged_records);
+    LAUNCH_CHECK();
+  }
+  if (n_records_host) *n_records_host = total;
+  return OTTO_OK;
+}
+
 // ------------------------------------------------------------------ one-shot build
 
 extern "C" int otto_covisit_build(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,

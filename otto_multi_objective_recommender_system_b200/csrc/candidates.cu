@@ -33,6 +33,8 @@ struct CandParams {
   int64_t slab_words;     // u64 words per block
   int32_t max_k_sum;      // max over targets of the sum of table_k over its sources
   int32_t max_len;        // longest session (events)
+  int32_t n_run;          // targets with distinct source lists (the others are copies: carts == orders in the reference)
+  int32_t run_target[OTTO_MAX_TARGETS];
 };
 
 constexpr int W_LCAP = 64, W_MCAP = 512;        // warp tier
@@ -133,7 +135,8 @@ __device__ void process_session(const CandParams& p, int64_t s, int tid, const W
   }
   gsync<T>();
 
-  for (int tg = 0; tg < sp.n_targets; ++tg) {
+  for (int ri = 0; ri < p.n_run; ++ri) {
+    const int tg = p.run_target[ri];
     // 4. gather: concatenate the table rows of every source in order
     int base = 0;
     for (int si = 0; si < sp.target_n_sources[tg]; ++si) {
@@ -411,6 +414,19 @@ extern "C" int otto_candidates(const OttoSessions* sessions, int32_t max_session
   p.max_k_sum = spec_max_k_sum(spec);
   p.max_len = max_session_len;
   p.slab_words = global_slab_words(max_session_len, p.max_k_sum);
+  // targets with the same ordered source list give the same lists (ranker/covisitation_candidate_generation.py
+  // :133,:138: carts and orders are the same concatenation): compute once, copy the slab
+  int dup_of[OTTO_MAX_TARGETS];
+  p.n_run = 0;
+  for (int tg = 0; tg < spec->n_targets; ++tg) {
+    dup_of[tg] = -1;
+    for (int u = 0; u < tg && dup_of[tg] < 0; ++u) {
+      bool same = spec->target_n_sources[u] == spec->target_n_sources[tg];
+      for (int i = 0; same && i < spec->target_n_sources[tg]; ++i) same = spec->target_sources[u][i] == spec->target_sources[tg][i];
+      if (same) dup_of[tg] = dup_of[u] >= 0 ? dup_of[u] : u;
+    }
+    if (dup_of[tg] < 0) p.run_target[p.n_run++] = tg;
+  }
   CUDA_TRY(cudaMemsetAsync(p.counters, 0, 64, st));
   int dev = 0, n_sm = 148;
   CUDA_TRY(cudaGetDevice(&dev));
@@ -431,6 +447,13 @@ extern "C" int otto_candidates(const OttoSessions* sessions, int32_t max_session
   }
   candidates_block_kernel<true><<<GLOBAL_BLOCKS, 256, 64, st>>>(p);
   LAUNCH_CHECK();
+  for (int tg = 0; tg < spec->n_targets; ++tg) {
+    if (dup_of[tg] < 0) continue;
+    const int64_t slab = S * spec->top_n;
+    CUDA_TRY(cudaMemcpyAsync(out->aid + tg * slab, out->aid + dup_of[tg] * slab, slab * 4, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(out->score + tg * slab, out->score + dup_of[tg] * slab, slab * 4, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(out->len + tg * S, out->len + dup_of[tg] * S, S * 4, cudaMemcpyDeviceToDevice, st));
+  }
   return OTTO_OK;
 }
 

@@ -50,6 +50,8 @@ class GpuRankBackend:
         return self.b.scatter()
 
     def reduce(self, segments, bin_lo, bin_hi, aid_lo, aid_hi) -> TopKTable:
+        if len(segments) > 1:    # one run per bin for the reduce kernels
+            segments = [self.b.merge_segments(segments, bin_hi - bin_lo)]
         return self.b.reduce(segments, bin_lo, bin_hi, aid_lo, aid_hi)
 
     def stats(self) -> dict:

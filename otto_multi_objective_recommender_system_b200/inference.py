@@ -96,10 +96,11 @@ def main(argv=None) -> dict:
     else:
         test_frame = io.read_event_frame(_first_existing(data / "test.pkl", data / "splits" / "test.parquet"), n_aids=args.n_aids)
         popular = io.read_popular(data / "aid_frequencies", "all")
-    tables = build_matrices(data, mode, args.n_aids, dev) if args.build else None
-    n_aids = max([test_frame.n_aids] + ([t.n_aids for t in tables.values()] if tables else [])) if args.n_aids is None else args.n_aids
-    if tables is None:
-        tables = load_matrices(data, mode, n_aids, dev)
+    built = build_matrices(data, mode, args.n_aids, dev) if args.build else None
+    n_aids = max([test_frame.n_aids] + ([t.n_aids for t in built.values()] if built else [])) if args.n_aids is None else args.n_aids
+    del built
+    # always consume the part files (15 rows per aid), exactly what the reference script reads
+    tables = load_matrices(data, mode, n_aids, dev)
     n_aids = next(iter(tables.values())).n_aids
     test_frame.n_aids = n_aids
     sess = covisit.ingest(test_frame, "asc", device=dev)
