@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-candidates", action="store_true")
     ap.add_argument("--split-ub", type=int, default=0)
+    ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: exchange records with an NCCL all-to-all instead of NVLink peer reads")
+    ap.add_argument("--dist-timing", action="store_true", help="N > 1: synchronise between phases and print their times (stderr)")
     return ap.parse_args()
 
 
@@ -213,7 +215,8 @@ def run_b200(args):
         torch.cuda.empty_cache()
     csr = covisit.ingest(frame, "desc", device=dev)
     E, S, A = csr.n_events, csr.n_sessions, csr.n_aids
-    backend = distributed.GpuRankBackend(csr, spec)
+    peer = distributed.PeerRecords(dev) if world > 1 and not args.nccl_exchange else None
+    backend = distributed.GpuRankBackend(csr, spec, peer=peer)
     builder = backend.b
 
     def barrier():
@@ -238,11 +241,12 @@ def run_b200(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     phases = ["count_begin", "count_finish", "scatter", "reduce"]
     last = {}
+    dist_timing = {}
 
     def step(marks=None):
         if world > 1:
             # sessions sharded by chunk; all-reduce of bounds / counts; all-to-all of pair slabs; owner reduce
-            _, _, st, _ = distributed.build_topk_distributed(backend)
+            _, _, st, _ = distributed.build_topk_distributed(backend, timing=dist_timing if args.dist_timing else None)
             last.update(st)
             return
         m = [ev() for _ in range(5)] if marks is not None else None
@@ -261,6 +265,7 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step()
     stats = builder.stats.as_dict()
+    dist_timing.clear()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -342,7 +347,7 @@ def run_b200(args):
             f = synth.EventFrame(host.session.to(dev, non_blocking=True), host.aid.to(dev, non_blocking=True),
                                  host.ts.to(dev, non_blocking=True), host.type.to(dev, non_blocking=True), A)
             c = covisit.ingest(f, "desc", device=dev)
-            be = distributed.GpuRankBackend(c, spec)
+            be = distributed.GpuRankBackend(c, spec, peer=peer)
             b = be.b
             b.workspace = builder.workspace          # reuse device buffers, as a long-running service would
             b.records, b.scratch, b.table = builder.records, builder.scratch, builder.table
@@ -390,6 +395,9 @@ def run_b200(args):
                      "unit": "sessions/s", "ms": cms, "sessions": sess.n_sessions, "events": sess.n_events,
                      "tables": list(tables), "top_n": 20, "targets": 3}
 
+    if args.dist_timing and world > 1:
+        n_calls = args.steps
+        print(f"rank {rank} phase ms/step: " + json.dumps({k: round(v / n_calls, 3) for k, v in dist_timing.items()}), file=sys.stderr)
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -406,6 +414,8 @@ def run_b200(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "candidates": cand_info,
             "gpu_launches": int(launches), "clocks": clocks}))
     if world > 1:
+        if peer is not None:
+            peer.close()
         dist.destroy_process_group()
 
 

@@ -183,6 +183,17 @@ int otto_covisit_merge_segments(const OttoPairSegment* segments_host, int32_t n_
                                 void* merged_records, int64_t merged_capacity, uint64_t* merged_offsets, void* scratch,
                                 int64_t scratch_bytes, int64_t* n_records_host, void* stream);
 
+/* Peer memory over NVLink (one process per GPU of one box).  The pair records of a rank live in a buffer
+ * that every other rank maps (CUDA IPC); the owner's merge kernel then READS the senders' slabs straight
+ * from their HBM over NVLink / NVSwitch - the all-to-all of SURVEY.md §8e is fused into the merge, no
+ * staging copy and no NCCL bulk transfer.  Handles are 64 opaque bytes, exchanged by the host (all_gather). */
+#define OTTO_PEER_HANDLE_BYTES 64
+int otto_peer_alloc(int64_t bytes, void** ptr_host);
+int otto_peer_free(void* ptr);
+int otto_peer_get_handle(void* ptr, uint8_t* handle_host /* [64] */);
+int otto_peer_open(const uint8_t* handle_host /* [64] */, void** ptr_host);
+int otto_peer_close(void* ptr);
+
 /* One-shot single-GPU build; the pair records and the reduce scratch are carved from the workspace after
  * the fixed part.  Returns OTTO_ENOSPC (stats_host->pairs / bins set) when the workspace cannot hold
  * them; otto_covisit_build_bytes gives the size to retry with. */

@@ -87,6 +87,11 @@ _SIGNATURES = {
                                       i64, P(OttoTopK), P(OttoBuildStats), vp]),
     "otto_covisit_merge_scratch_bytes": (i64, [i64]),
     "otto_covisit_merge_segments": (C.c_int, [P(OttoPairSegment), i32, i64, vp, i64, vp, vp, i64, P(i64), vp]),
+    "otto_peer_alloc": (C.c_int, [i64, P(vp)]),
+    "otto_peer_free": (C.c_int, [vp]),
+    "otto_peer_get_handle": (C.c_int, [vp, C.c_char_p]),
+    "otto_peer_open": (C.c_int, [C.c_char_p, P(vp)]),
+    "otto_peer_close": (C.c_int, [vp]),
     "otto_covisit_build": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(OttoTopK), P(OttoBuildStats), vp]),
     "otto_covisit_build_bytes": (i64, [i64, i64, P(OttoCovisitSpec), i64, i64]),
     "otto_topk_row_offsets": (C.c_int, [P(OttoTopK), vp, P(i64), vp, i64, vp]),

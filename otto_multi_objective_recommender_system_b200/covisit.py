@@ -226,6 +226,7 @@ class CovisitBuilder:
         self.sizes = sizes
         self.workspace = torch.empty(sizes.workspace_bytes, dtype=torch.uint8, device=self.device)
         self.records = None
+        self.merged = None
         self.scratch = None
         self.stats = N.OttoBuildStats()
         self.table = None
@@ -296,12 +297,17 @@ class CovisitBuilder:
     def merge_segments(self, segments, n_bins: int):
         """Multi-GPU owner side: the G received (records, offsets) segments of my bins -> one bin-contiguous
         segment, so that the reduce kernels see a single run per bin."""
-        total_cap = sum(int(r.numel()) for r, _ in segments)
-        merged = torch.empty(max(total_cap, 1), dtype=torch.int64, device=self.device)
+        # a segment's records are a tensor, or (device pointer, n_records) for a peer's slab mapped over NVLink
+        ptr = lambda r: r[0] if isinstance(r, tuple) else r.data_ptr()
+        cnt = lambda r: int(r[1]) if isinstance(r, tuple) else int(r.numel())
+        total_cap = sum(cnt(r) for r, _ in segments)
+        if self.merged is None or self.merged.numel() < max(total_cap, 1):
+            self.merged = torch.empty(max(total_cap, 1), dtype=torch.int64, device=self.device)
+        merged = self.merged
         offsets = torch.empty(n_bins + 1, dtype=torch.int64, device=self.device)
         need = int(self.lib.otto_covisit_merge_scratch_bytes(n_bins))
         scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
-        segs = (N.OttoPairSegment * len(segments))(*[N.OttoPairSegment(r.data_ptr(), o.data_ptr()) for r, o in segments])
+        segs = (N.OttoPairSegment * len(segments))(*[N.OttoPairSegment(ptr(r), o.data_ptr()) for r, o in segments])
         n = C.c_int64(0)
         with torch.cuda.device(self.device):
             N.check(self.lib.otto_covisit_merge_segments(segs, len(segments), n_bins, merged.data_ptr(), merged.numel(),

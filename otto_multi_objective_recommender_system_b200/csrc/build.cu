@@ -637,6 +637,35 @@ extern "C" int otto_covisit_merge_segments(const OttoPairSegment* segments_host,
   return OTTO_OK;
 }
 
+// ------------------------------------------------------------------ peer memory (CUDA IPC over NVLink)
+
+extern "C" int otto_peer_alloc(int64_t bytes, void** ptr_host) {
+  if (bytes <= 0 || !ptr_host) { otto_set_error("bad argument"); return OTTO_EINVAL; }
+  CUDA_TRY(cudaMalloc(ptr_host, (size_t)bytes));
+  return OTTO_OK;
+}
+extern "C" int otto_peer_free(void* ptr) {
+  CUDA_TRY(cudaFree(ptr));
+  return OTTO_OK;
+}
+extern "C" int otto_peer_get_handle(void* ptr, uint8_t* handle_host) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == OTTO_PEER_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle_host, &h, sizeof(h));
+  return OTTO_OK;
+}
+extern "C" int otto_peer_open(const uint8_t* handle_host, void** ptr_host) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_host, sizeof(h));
+  CUDA_TRY(cudaIpcOpenMemHandle(ptr_host, h, cudaIpcMemLazyEnablePeerAccess));
+  return OTTO_OK;
+}
+extern "C" int otto_peer_close(void* ptr) {
+  CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return OTTO_OK;
+}
+
 // ------------------------------------------------------------------ one-shot build
 
 extern "C" int otto_covisit_build(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,

@@ -26,15 +26,81 @@ from dataclasses import dataclass
 import torch
 import torch.distributed as dist
 
+import ctypes as C
+
+from . import _native as N
 from .covisit import CovisitBuilder, CovisitSpec, EventCSR, TopKTable
+
+
+class _RawCuda:
+    """__cuda_array_interface__ view of a raw device allocation (int64 elements)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+class PeerRecords:
+    """The rank's pair-record buffer, mapped by every other rank of the box (CUDA IPC over NVLink).
+
+    The owner of an aid_x range never receives a copy of the senders' slabs: its merge kernel reads them in
+    place from the senders' HBM, so the exchange of SURVEY.md §8e is fused into the merge
+    (otto_covisit_merge_segments with peer pointers) and NCCL only carries the small control arrays."""
+
+    def __init__(self, device, group=None):
+        self.lib, self.device, self.group = N.lib(), device, group
+        self.capacity, self.ptr, self.local, self.peers = 0, None, None, []
+
+    def ensure(self, n_records: int) -> torch.Tensor:
+        """Collective.  Grows every rank's buffer to the largest need and re-exchanges the handles."""
+        need = torch.tensor([max(int(n_records), 1)], dtype=torch.int64, device=self.device)
+        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
+        need = int(need.item())
+        if need <= self.capacity:
+            return self.local
+        self.close()
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.capacity = need + need // 8
+        with torch.cuda.device(self.device):
+            p = C.c_void_p()
+            N.check(self.lib.otto_peer_alloc(self.capacity * 8, C.byref(p)))
+            self.ptr = p.value
+            handle = C.create_string_buffer(64)
+            N.check(self.lib.otto_peer_get_handle(self.ptr, handle))
+            mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=self.device)
+            every = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine, group=self.group)
+            self.peers = []
+            for g in range(world):
+                if g == rank:
+                    self.peers.append(self.ptr)
+                    continue
+                q = C.c_void_p()
+                N.check(self.lib.otto_peer_open(bytes(every[g].cpu().tolist()), C.byref(q)))
+                self.peers.append(q.value)
+        self.local = torch.as_tensor(_RawCuda(self.ptr, self.capacity), device=self.device)
+        return self.local
+
+    def close(self) -> None:
+        if self.ptr is None:
+            return
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            dist.barrier(group=self.group)      # nobody may still be reading my buffer
+        with torch.cuda.device(self.device):
+            for q in self.peers:
+                if q != self.ptr:
+                    self.lib.otto_peer_close(q)
+            self.lib.otto_peer_free(self.ptr)
+        self.capacity, self.ptr, self.local, self.peers = 0, None, None, []
 
 
 class GpuRankBackend:
     """Rank-local phases on one B200 (the product backend)."""
 
-    def __init__(self, csr: EventCSR, spec: CovisitSpec, exact: bool = False):
+    def __init__(self, csr: EventCSR, spec: CovisitSpec, exact: bool = False, peer: PeerRecords | None = None):
         self.b = CovisitBuilder(csr, spec, exact=exact)
         self.n_aids, self.k, self.device = csr.n_aids, spec.k, csr.aid.device
+        self.peer = peer          # set: records are exchanged through peer memory instead of NCCL
 
     def count_begin(self) -> torch.Tensor:
         self.b.count_begin()
@@ -47,6 +113,8 @@ class GpuRankBackend:
         return stats, v["bin_offsets"], v["bin_base"]
 
     def scatter(self) -> torch.Tensor:
+        if self.peer is not None:
+            self.b.records = self.peer.ensure(int(self.b.stats.pairs))     # collective
         return self.b.scatter()
 
     def reduce(self, segments, bin_lo, bin_hi, aid_lo, aid_hi) -> TopKTable:
@@ -82,24 +150,56 @@ def plan_owners(bin_counts: torch.Tensor, bin_base: torch.Tensor, world: int) ->
     return OwnerPlan(aid_cuts, bin_cuts)
 
 
-def build_topk_distributed(backend, group=None):
+def build_topk_distributed(backend, group=None, timing: dict | None = None):
     """All ranks call this with their own session shard.  Returns (table, (aid_lo, aid_hi), stats, plan): rows
     [aid_lo, aid_hi) of `table` are final on this rank."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    import time
+    t_last = [time.perf_counter()]
+
+    def mark(name):     # phase timing for profiling runs only (synchronises)
+        if timing is not None:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            timing[name] = timing.get(name, 0.0) + (now - t_last[0]) * 1e3
+            t_last[0] = now
+    mark("start")
     ub = backend.count_begin()
+    mark("count_begin")
     if world > 1:
         dist.all_reduce(ub, group=group)
+    mark("allreduce_ub")
     stats, bin_off, bin_base = backend.count_finish()
+    mark("count_finish")
     B = int(stats["bins"])
     counts = (bin_off[1:B + 1] - bin_off[:B]).clone()
     if world > 1:
         dist.all_reduce(counts, group=group)
     plan = plan_owners(counts, bin_base, world)
+    mark("allreduce_counts+plan")
     records = backend.scatter()
+    mark("scatter")
     lo, hi = plan.bin_cuts[rank], plan.bin_cuts[rank + 1]
+    peer = getattr(backend, "peer", None)
     if world == 1:
         segments = [(records, bin_off)]
+    elif peer is not None:
+        # slab (sender g -> owner o) = records_g[cuts[g][o] : cuts[g][o + 1]], read in place over NVLink
+        cut_off = bin_off[torch.tensor(plan.bin_cuts, device=bin_off.device)]
+        every = [torch.empty_like(cut_off) for _ in range(world)]
+        dist.all_gather(every, cut_off, group=group)
+        cuts = torch.stack(every).tolist()
+        n_mine = hi - lo + 1
+        send_off = torch.cat([bin_off[plan.bin_cuts[o]:plan.bin_cuts[o + 1] + 1] for o in range(world)])
+        off_send_sizes = [plan.bin_cuts[o + 1] - plan.bin_cuts[o] + 1 for o in range(world)]
+        recv_off = torch.empty(world * n_mine, dtype=torch.int64, device=records.device)
+        # also the barrier "every sender's scatter is complete": a rank's part of this collective is ordered
+        # behind its scatter kernel on its stream
+        dist.all_to_all_single(recv_off, send_off, [n_mine] * world, off_send_sizes, group=group)
+        segments = [((peer.peers[g] + 8 * cuts[g][rank], cuts[g][rank + 1] - cuts[g][rank]), recv_off[g * n_mine:(g + 1) * n_mine])
+                    for g in range(world)]
+        backend._keepalive = (recv_off,)
     else:
         # slab of owner o = records[bin_off[cut_o] : bin_off[cut_o + 1]]; offsets travel with their slab
         cut_off = bin_off[torch.tensor(plan.bin_cuts, device=bin_off.device)]
@@ -122,7 +222,9 @@ def build_topk_distributed(backend, group=None):
                              recv_off[g * n_mine:(g + 1) * n_mine]))
             at += recv_list[g]
         backend._keepalive = (recv_records, recv_off)
+    mark("all_to_all")
     table = backend.reduce(segments, lo, hi, plan.aid_cuts[rank], plan.aid_cuts[rank + 1])
+    mark("merge+reduce")
     out_stats = dict(backend.stats())
     out_stats["owned_aids"] = plan.aid_cuts[rank + 1] - plan.aid_cuts[rank]
     out_stats["sent_records"] = int(stats["pairs"])

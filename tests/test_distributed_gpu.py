@@ -8,7 +8,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, variant, split_ub, n_sessions, n_aids):
+def _worker(rank, world, port, variant, split_ub, n_sessions, n_aids, use_peer):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
@@ -21,7 +21,8 @@ def _worker(rank, world, port, variant, split_ub, n_sessions, n_aids):
     csr = covisit.ingest(frame, "desc", device=dev)
     S = csr.n_sessions
     shard = csr.slice_sessions(rank * S // world, (rank + 1) * S // world)
-    backend = distributed.GpuRankBackend(shard, spec, exact=True)
+    peer = distributed.PeerRecords(dev) if use_peer else None     # NVLink peer memory vs NCCL all-to-all
+    backend = distributed.GpuRankBackend(shard, spec, exact=True, peer=peer)
     table, (lo, hi), stats, plan = distributed.build_topk_distributed(backend)
     distributed.gather_table(table, plan)
     single, sstats = covisit.build_topk(csr, spec, exact=True)
@@ -32,15 +33,18 @@ def _worker(rank, world, port, variant, split_ub, n_sessions, n_aids):
     total = torch.tensor([stats["pair_checksum"], stats["distinct"]], device=dev)
     dist.all_reduce(total)
     assert int(total[0]) == sstats["pair_checksum"] and int(total[1]) == sstats["distinct"]
+    if peer is not None:
+        peer.close()
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("use_peer", [True, False])
 @pytest.mark.parametrize("variant,split_ub", [("CLICKS", 0), ("CARTS_ORDERS", 64), ("BUY2BUY", 0)])
-def test_multi_gpu_equals_single_gpu(native_lib, variant, split_ub):
+def test_multi_gpu_equals_single_gpu(native_lib, variant, split_ub, use_peer):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    torch.multiprocessing.spawn(_worker, args=(world, port, variant, split_ub, 20000, 2500), nprocs=world, join=True)
+    torch.multiprocessing.spawn(_worker, args=(world, port, variant, split_ub, 20000, 2500, use_peer), nprocs=world, join=True)
