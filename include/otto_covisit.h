@@ -72,6 +72,8 @@ typedef struct {
   int32_t ts_min;            /* OTTO_WEIGHT_TIME constants: 1659304800, 1662328791 */
   int32_t ts_max;
   int32_t split_ub;          /* rows whose pair upper bound exceeds this are split into y-hash sub-bins; 0 = default */
+  int64_t global_events;     /* multi-GPU: events of ALL ranks (bins are formed from the all-reduced bounds, so the
+                                bin arrays must be sized for the global frame); 0 = this rank's frame is the whole frame */
 } OttoCovisitSpec;
 
 /* Sizes the caller needs to allocate the build workspace for a given input shape. */

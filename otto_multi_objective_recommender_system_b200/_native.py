@@ -30,7 +30,7 @@ class OttoEvents(C.Structure):
 class OttoCovisitSpec(C.Structure):
     _fields_ = [("n_aids", i32), ("weight_mode", i32), ("type_weight", i32 * 3), ("event_type_mask", u32),
                 ("x_type_mask", u32), ("y_type_mask", u32), ("window_s", i32), ("tail_n", i32), ("k", i32),
-                ("ts_min", i32), ("ts_max", i32), ("split_ub", i32)]
+                ("ts_min", i32), ("ts_max", i32), ("split_ub", i32), ("global_events", i64)]
 
 
 class OttoBuildSizes(C.Structure):

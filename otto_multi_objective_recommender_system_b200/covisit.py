@@ -34,12 +34,13 @@ class CovisitSpec:
     ts_min: int = TS_MIN
     ts_max: int = TS_MAX
     split_ub: int = 0                  # 0 = library default
+    global_events: int = 0             # multi-GPU: events of all ranks (sizes the bin arrays); 0 = single frame
 
     def to_c(self, n_aids: int) -> N.OttoCovisitSpec:
         mask = lambda ts: sum(1 << int(t) for t in set(ts))
         return N.OttoCovisitSpec(n_aids, self.weight_mode, (C.c_int32 * 3)(*[int(w) for w in self.type_weight]),
                                  mask(self.event_types), mask(self.x_types), mask(self.y_types), self.window_s,
-                                 self.tail_n, self.k, self.ts_min, self.ts_max, self.split_ub)
+                                 self.tail_n, self.k, self.ts_min, self.ts_max, self.split_ub, self.global_events)
 
 
 CLICKS = CovisitSpec(N.WEIGHT_TIME, k=20)                                  # stem "time_weighted"

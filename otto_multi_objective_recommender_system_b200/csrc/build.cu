@@ -114,7 +114,10 @@ static Layout make_layout(int64_t S, int64_t E, const OttoCovisitSpec* spec) {
   L.A = spec->n_aids;
   L.Ecap = E < S * spec->tail_n ? E : S * spec->tail_n;
   if (L.Ecap < 1) L.Ecap = 1;
-  L.Bmax = L.A + (L.Ecap * (spec->tail_n - 1)) / effective_split_ub(spec) + 1;
+  // extra bins = sum over rows of (ceil(ub / split_ub) - 1) <= (sum of ub) / split_ub <= events * (tail_n - 1) / split_ub,
+  // with the events of every rank when the bounds are all-reduced (multi-GPU)
+  const int64_t Eg = spec->global_events > E ? spec->global_events : L.Ecap;
+  L.Bmax = L.A + (Eg * (spec->tail_n - 1)) / effective_split_ub(spec) + 1;
   int64_t o = 0;
   auto take = [&](int64_t bytes) { int64_t at = o; o = align_up(o + bytes, 256); return at; };
   L.tail_off = take((S + 2) * 4);
@@ -356,6 +359,17 @@ extern "C" int otto_covisit_count_finish(const OttoEvents* ev, const OttoCovisit
   LAUNCH_CHECK();
   if ((rc = exclusive_scan<uint32_t, uint32_t>(WS(uint32_t, bin_base), A, WS(uint32_t, bin_base), WS(uint32_t, scan), st)))
     return rc;
+  {
+    // the bin arrays were sized from the event count: refuse before anything is written past them
+    uint32_t n_bins = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n_bins, WS(uint32_t, bin_base) + A, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if ((int64_t)n_bins > L.Bmax) {
+      otto_set_error("%u bins exceed the %lld the workspace was sized for: set spec.global_events to the event count of all ranks",
+                     n_bins, (long long)L.Bmax);
+      return OTTO_ENOSPC;
+    }
+  }
   bins_fill_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(WS(uint32_t, bin_base), A, WS(uint32_t, bin_x));
   LAUNCH_CHECK();
   // pass 1: winner masks + per-bin pair counts
@@ -641,7 +655,16 @@ extern "C" int otto_covisit_merge_segments(const OttoPairSegment* segments_host,
 
 extern "C" int otto_peer_alloc(int64_t bytes, void** ptr_host) {
   if (bytes <= 0 || !ptr_host) { otto_set_error("bad argument"); return OTTO_EINVAL; }
-  CUDA_TRY(cudaMalloc(ptr_host, (size_t)bytes));
+  const cudaError_t e = cudaMalloc(ptr_host, (size_t)bytes);
+  if (e != cudaSuccess) {
+    size_t free_b = 0, total_b = 0;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    cudaMemGetInfo(&free_b, &total_b);
+    otto_set_error("otto_peer_alloc: cudaMalloc of %lld bytes on device %d failed (%s); %zu of %zu bytes free", (long long)bytes,
+                   dev, cudaGetErrorString(e), free_b, total_b);
+    return OTTO_ECUDA;
+  }
   return OTTO_OK;
 }
 extern "C" int otto_peer_free(void* ptr) {
