@@ -7,12 +7,17 @@
 //   np.unique(aids[types <= 1]) etc.                                              -> ascending subsets
 //   itertools.chain(*[table[aid] for aid in <set> if aid in table])               -> gather, in set order
 //   Counter(concat).most_common(N) ... if aid not in session_unique_aids          -> vote + cut + filter
-// Counter.most_common sorts by (count desc, first insertion asc); both fall out of two sorts:
-//   items  = (aid_y << 32 | position in the concatenation), ascending  -> runs per aid, head = first seen
-//   entry  = (count << 48 | (0xffff - first position) << 32 | aid_y), descending -> the most_common order.
+// Counter.most_common sorts by (count desc, first insertion asc).  v2 counts the votes in an open-addressing
+// table (shared memory; key = aid_y, payload = count and the smallest position in the concatenation) instead of
+// sorting all gathered items (v1: two bitonic sorts per target were 60 % of the instructions,
+// profiles/r01_cand_v1), then ranks only the entries that can reach the top N:
+//   entry  = count << 48 | (0xffff - first position) << 32 | aid_y          (descending = most_common order)
+//   N <= 32: the N-th largest of the 32 lane-group maxima is a lower bound of the N-th largest entry; the
+//            entries at or above it (about N .. 2N) are sorted in registers by one warp
+//   N  > 32: all entries are sorted (bitonic, shared memory)
 // One cooperative routine serves three tiers that differ only in group size and where the arrays live:
-// a warp with shared-memory arrays (sessions whose bound is <= 512 items), a 256-thread block with
-// shared-memory arrays (<= 4096 items) and a 256-thread block over a global scratch slab (anything else;
+// a warp with shared-memory arrays (sessions whose bound is <= 256 items), a 256-thread block with
+// shared-memory arrays (<= 2048 items) and a 256-thread block over a global scratch slab (anything else;
 // OTTO's longest test session has 458 events).
 #include "common.cuh"
 
@@ -37,8 +42,8 @@ struct CandParams {
   int32_t run_target[OTTO_MAX_TARGETS];
 };
 
-constexpr int W_LCAP = 64, W_MCAP = 512;        // warp tier
-constexpr int B_LCAP = 512, B_MCAP = 4096;      // block-smem tier
+constexpr int W_LCAP = 32, W_MCAP = 256;        // warp tier: events, gathered items
+constexpr int B_LCAP = 256, B_MCAP = 2048;      // block-smem tier
 constexpr int CAND_WARPS = 4;
 
 template <int T>
@@ -64,6 +69,21 @@ __device__ __forceinline__ void bitonic_sort(uint64_t* a, int n, int tid) {
   }
 }
 
+// bitonic sort of one u64 per lane, descending (lane 0 ends with the largest)
+__device__ __forceinline__ uint64_t cand_warp_sort_desc(uint64_t v) {
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t o = shfl_u64(v, lane ^ j);
+      const bool keep_max = ((lane & j) == 0) == ((lane & k) == 0);
+      v = keep_max ? (o > v ? o : v) : (o < v ? o : v);
+    }
+  }
+  return v;
+}
+
 __device__ __forceinline__ int pow2_at_least(int n) {
   int p = 1;
   while (p < n) p <<= 1;
@@ -80,21 +100,47 @@ struct Work {
   int32_t* elen;     // [Lcap] per element of the current source: table row length
   int32_t* estart;   // [Lcap] exclusive prefix of elen
   uint64_t* ord;     // [pow2(Lcap)] subset sort buffer
-  uint64_t* items;   // [Mcap]
-  uint64_t* ent;     // [Mcap]
-  int32_t* scal;     // [8] scalars: 0 U, 1 n_ord, 2 n_ent, 3 kept
+  uint32_t* keys;    // [HS] vote table: aid_y (KEY_EMPTY = free)
+  uint32_t* cnt;     // [HS] votes
+  uint32_t* first;   // [HS] smallest position in the concatenation
+  uint32_t* occ;     // [HS / 2] claimed slots
+  uint64_t* ent;     // [Mcap] inverted entries of the survivors, best first
+  int32_t* scal;     // [8] scalars: 0 U, 1 n_ord, 2 n_occ, 3 kept, 4 n_cand;  [6..7] threshold (u64)
+  uint32_t hmask;    // HS - 1
+  int hshift;        // 32 - log2(HS)
 };
 
 __device__ __forceinline__ uint32_t hist_mask(int sel) {
   return sel == OTTO_HIST_TYPE_LE1 ? 3u : sel == OTTO_HIST_TYPE_GE1 ? 6u : sel == OTTO_HIST_TYPE_EQ0 ? 1u : 7u;
 }
 
+// one vote for aid y at position pos of the concatenation (the table never fills: items <= HS / 2)
+__device__ __forceinline__ void vote(const Work& w, uint32_t y, uint32_t pos) {
+  uint32_t h = (y * 0x9E3779B1u) >> w.hshift;
+  while (true) {
+    const uint32_t prev = atomicCAS(&w.keys[h], KEY_EMPTY, y);
+    if (prev == KEY_EMPTY) {
+      w.occ[atomicAdd(&w.scal[2], 1)] = h;
+      break;
+    }
+    if (prev == y) break;
+    h = (h + 1) & w.hmask;
+  }
+  atomicAdd(&w.cnt[h], 1u);
+  atomicMin(&w.first[h], pos);
+}
+
+__device__ __forceinline__ uint64_t entry_key(const Work& w, uint32_t h) {
+  return ((uint64_t)w.cnt[h] << 48) | ((uint64_t)(0xffffu - w.first[h]) << 32) | w.keys[h];
+}
+
 template <int T>
-__device__ void process_session(const CandParams& p, int64_t s, int tid, const Work& w) {
+__device__ void process_session(const CandParams& p, int64_t s, int tid, const Work& w, uint64_t* s_gmax) {
   const OttoCandidateSpec& sp = p.spec;
   const int32_t beg = p.off[s], end = p.off[s + 1];
   const int L = end - beg;
   const int N = sp.top_n;
+  const uint32_t lane = tid & 31, lt = lanemask_lt();
   // 1. events, most recent first
   for (int i = tid; i < L; i += T) {
     w.ev_aid[i] = p.aid[end - 1 - i];
@@ -137,7 +183,7 @@ __device__ void process_session(const CandParams& p, int64_t s, int tid, const W
 
   for (int ri = 0; ri < p.n_run; ++ri) {
     const int tg = p.run_target[ri];
-    // 4. gather: concatenate the table rows of every source in order
+    // 4. gather + vote: walk the table rows of every source in concatenation order
     int base = 0;
     for (int si = 0; si < sp.target_n_sources[tg]; ++si) {
       const int src = sp.target_sources[tg][si];
@@ -165,7 +211,6 @@ __device__ void process_session(const CandParams& p, int64_t s, int tid, const W
         }
         gsync<T>();
         ne = w.scal[1];
-        // reuse estart as the int32 view of the sorted subset
         for (int u = tid; u < ne; u += T) w.uidx[u] = (int32_t)w.ord[u];
         gsync<T>();
         E = w.uidx;
@@ -184,70 +229,123 @@ __device__ void process_session(const CandParams& p, int64_t s, int tid, const W
       const int total = ne > 0 ? w.estart[ne - 1] + w.elen[ne - 1] : 0;
       for (int idx = tid; idx < ne * K; idx += T) {
         const int e = idx / K, r = idx - e * K;
-        if (r < w.elen[e]) {
-          const int pos = base + w.estart[e] + r;
-          w.items[pos] = ((uint64_t)(uint32_t)ty[(int64_t)E[e] * K + r] << 32) | (uint32_t)pos;
-        }
+        if (r < w.elen[e]) vote(w, (uint32_t)ty[(int64_t)E[e] * K + r], (uint32_t)(base + w.estart[e] + r));
       }
       gsync<T>();
       base += total;
     }
-    const int m = base;
-    // 5. sort by (aid, position); 6. one entry per run
-    const int np = pow2_at_least(m > 1 ? m : 1);
-    for (int i = m + tid; i < np; i += T) w.items[i] = ~0ull;
-    if (tid == 0) w.scal[2] = 0;
-    gsync<T>();
-    bitonic_sort<T>(w.items, np, tid);
-    for (int i = tid; i < m; i += T) {
-      const uint32_t a = (uint32_t)(w.items[i] >> 32);
-      if (i == 0 || (uint32_t)(w.items[i - 1] >> 32) != a) {
-        int j = i + 1;
-        while (j < m && (uint32_t)(w.items[j] >> 32) == a) ++j;
-        const uint64_t cnt = (uint64_t)(j - i);
-        const uint64_t first = (uint32_t)w.items[i];
-        const int at = atomicAdd(&w.scal[2], 1);
-        // stored inverted so that the ascending sort yields (count desc, first-seen asc)
-        w.ent[at] = ~((cnt << 48) | ((0xffffull - first) << 32) | a);
+    const int d = w.scal[2];
+    const int n_top = d < N ? d : N;
+    // 5. the n_top best entries, inverted (~key), best first, into w.ent
+    if (d <= 32) {
+      if (tid < 32) {
+        const uint64_t v = (int)lane < d ? entry_key(w, w.occ[lane]) : 0ull;
+        const uint64_t sorted = cand_warp_sort_desc(v);
+        if ((int)lane < d) w.ent[lane] = ~sorted;
       }
+    } else if (N <= 32) {
+      uint64_t best = 0;
+      for (int i = tid; i < d; i += T) {
+        const uint64_t k = entry_key(w, w.occ[i]);
+        best = k > best ? k : best;
+      }
+      if (T > 32) {
+        s_gmax[tid] = best;
+        __syncthreads();
+      }
+      if (tid < 32) {
+        uint64_t g = best;
+        if (T > 32)
+          for (int wv = 1; wv < T / 32; ++wv) g = s_gmax[wv * 32 + lane] > g ? s_gmax[wv * 32 + lane] : g;
+        const uint64_t kth = shfl_u64(cand_warp_sort_desc(g), N - 1);   // d > 32: every lane holds an entry
+        if (lane == 0) {
+          *(uint64_t*)(w.scal + 6) = kth;
+          w.scal[4] = 0;
+        }
+      }
+      gsync<T>();
+      const uint64_t thr = *(const uint64_t*)(w.scal + 6);
+      for (int i = tid; i < d; i += T) {
+        const uint64_t k = entry_key(w, w.occ[i]);
+        if (k >= thr) w.ent[atomicAdd(&w.scal[4], 1)] = ~k;
+      }
+      gsync<T>();
+      const int n_c = w.scal[4];
+      if (n_c <= 32) {
+        if (tid < 32) {
+          const uint64_t v = (int)lane < n_c ? ~w.ent[lane] : 0ull;
+          const uint64_t sorted = cand_warp_sort_desc(v);
+          if ((int)lane < n_c) w.ent[lane] = ~sorted;
+        }
+      } else {
+        const int np = pow2_at_least(n_c);
+        for (int i = n_c + tid; i < np; i += T) w.ent[i] = ~0ull;
+        gsync<T>();
+        bitonic_sort<T>(w.ent, np, tid);
+      }
+    } else {
+      for (int i = tid; i < d; i += T) w.ent[i] = ~entry_key(w, w.occ[i]);
+      const int np = pow2_at_least(d);
+      for (int i = d + tid; i < np; i += T) w.ent[i] = ~0ull;
+      gsync<T>();
+      bitonic_sort<T>(w.ent, np, tid);
     }
     gsync<T>();
-    const int d = w.scal[2];
-    const int dp = pow2_at_least(d > 1 ? d : 1);
-    for (int i = d + tid; i < dp; i += T) w.ent[i] = ~0ull;
-    gsync<T>();
-    bitonic_sort<T>(w.ent, dp, tid);
-    // 7. most_common(N), then drop history aids; order is preserved
-    const int top = d < N ? d : N;
-    for (int r = tid; r < top; r += T) {
+    // reset the claimed slots for the next target / session
+    for (int i = tid; i < d; i += T) {
+      const uint32_t h = w.occ[i];
+      w.keys[h] = KEY_EMPTY;
+      w.cnt[h] = 0;
+      w.first[h] = 0xffffffffu;
+    }
+    // 6. most_common(N), then drop history aids; order is preserved.  Dropped entries become ~0.
+    for (int r = tid; r < n_top; r += T) {
       const uint32_t a = (uint32_t)(~w.ent[r]);
       bool keep = true;
       if (sp.drop_history)
         for (int u = 0; u < U; ++u)
           if ((uint32_t)w.H[u] == a) { keep = false; break; }
-      // mark dropped entries in place (bit 47 of the inverted key is the top count bit: use a side flag)
-      w.items[r] = keep ? 1ull : 0ull;
+      if (!keep) w.ent[r] = ~0ull;
     }
     gsync<T>();
     int32_t* oa = p.out_aid + ((int64_t)tg * p.n_sessions + s) * N;
     int32_t* os = p.out_score + ((int64_t)tg * p.n_sessions + s) * N;
-    for (int r = tid; r < N; r += T) {
-      if (r < top && w.items[r]) {
-        int at = 0;
-        for (int j = 0; j < r; ++j) at += (int)w.items[j];
-        const uint64_t key = ~w.ent[r];
-        oa[at] = (int32_t)(uint32_t)key;
-        os[at] = (int32_t)(key >> 48);
+    int kept;
+    if (n_top <= 32) {
+      // one warp: ballot compaction (the usual case: N = 20)
+      if (tid < 32) {
+        const bool has = (int)lane < n_top && w.ent[lane] != ~0ull;
+        const uint32_t m = __ballot_sync(FULL_MASK, has);
+        if (has) {
+          const uint64_t key = ~w.ent[lane];
+          const int at = __popc(m & lt);
+          oa[at] = (int32_t)(uint32_t)key;
+          os[at] = (int32_t)(key >> 48);
+        }
+        if (lane == 0) w.scal[3] = __popc(m);
+      }
+    } else {
+      for (int r = tid; r < n_top; r += T) {
+        if (w.ent[r] != ~0ull) {
+          int at = 0;
+          for (int j = 0; j < r; ++j) at += w.ent[j] != ~0ull;
+          const uint64_t key = ~w.ent[r];
+          oa[at] = (int32_t)(uint32_t)key;
+          os[at] = (int32_t)(key >> 48);
+        }
+      }
+      if (tid == 0) {
+        int c = 0;
+        for (int j = 0; j < n_top; ++j) c += w.ent[j] != ~0ull;
+        w.scal[3] = c;
       }
     }
-    if (tid == 0) {
-      int kept = 0;
-      for (int j = 0; j < top; ++j) kept += (int)w.items[j];
-      w.scal[3] = kept;
-      p.out_len[(int64_t)tg * p.n_sessions + s] = kept;
-    }
     gsync<T>();
-    const int kept = w.scal[3];
+    kept = w.scal[3];
+    if (tid == 0) {
+      p.out_len[(int64_t)tg * p.n_sessions + s] = kept;
+      w.scal[2] = 0;
+    }
     for (int r = kept + tid; r < N; r += T) {
       oa[r] = -1;
       os[r] = 0;
@@ -256,24 +354,44 @@ __device__ void process_session(const CandParams& p, int64_t s, int tid, const W
   }
 }
 
+// layout of a work area: u64 arrays first (ent[MCAP], ord[pow2 LCAP]), then the u32 / i32 arrays
 template <int LCAP, int MCAP>
-__device__ __forceinline__ Work carve(unsigned char* base) {
+__host__ __device__ constexpr size_t work_bytes() {
+  return (size_t)MCAP * 8 + (size_t)LCAP * 8 + (size_t)(2 * MCAP) * 12 + (size_t)MCAP * 4 + (size_t)LCAP * 4 * 7 + 32;
+}
+
+__device__ __forceinline__ Work carve_rt(unsigned char* base, int64_t lcap, int64_t mcap, int32_t* scal) {
   Work w;
-  w.items = (uint64_t*)base;
-  w.ent = w.items + MCAP;
-  w.ord = w.ent + MCAP;
-  w.ev_aid = (int32_t*)(w.ord + LCAP);
-  w.ev_ty = w.ev_aid + LCAP;
-  w.uidx = w.ev_ty + LCAP;
-  w.H = w.uidx + LCAP;
-  w.tmask = w.H + LCAP;
-  w.elen = w.tmask + LCAP;
-  w.estart = w.elen + LCAP;
-  w.scal = w.estart + LCAP;
+  const int64_t hs = 2 * mcap;
+  w.ent = (uint64_t*)base;
+  w.ord = w.ent + mcap;
+  w.keys = (uint32_t*)(w.ord + lcap);
+  w.cnt = w.keys + hs;
+  w.first = w.cnt + hs;
+  w.occ = w.first + hs;
+  w.ev_aid = (int32_t*)(w.occ + mcap);
+  w.ev_ty = w.ev_aid + lcap;
+  w.uidx = w.ev_ty + lcap;
+  w.H = w.uidx + lcap;
+  w.tmask = w.H + lcap;
+  w.elen = w.tmask + lcap;
+  w.estart = w.elen + lcap;
+  w.scal = scal ? scal : w.estart + lcap;
+  w.hmask = (uint32_t)(hs - 1);
+  w.hshift = 32 - (63 - __clzll((long long)hs));
   return w;
 }
-template <int LCAP, int MCAP>
-__host__ __device__ constexpr size_t work_bytes() { return (size_t)MCAP * 16 + (size_t)LCAP * 8 + (size_t)LCAP * 4 * 7 + 32; }
+
+template <int T>
+__device__ __forceinline__ void clear_table(const Work& w, int tid) {
+  for (uint32_t h = tid; h <= w.hmask; h += T) {
+    w.keys[h] = KEY_EMPTY;
+    w.cnt[h] = 0;
+    w.first[h] = 0xffffffffu;
+  }
+  if (tid == 0) w.scal[2] = 0;
+  gsync<T>();
+}
 
 __device__ __forceinline__ int64_t item_bound(const CandParams& p, int L) { return (int64_t)L * p.max_k_sum; }
 
@@ -281,7 +399,8 @@ __device__ __forceinline__ int64_t item_bound(const CandParams& p, int L) { retu
 __global__ void __launch_bounds__(CAND_WARPS * 32) candidates_warp_kernel(const CandParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const Work w = carve<W_LCAP, W_MCAP>(smem_raw + warp * work_bytes<W_LCAP, W_MCAP>());
+  const Work w = carve_rt(smem_raw + warp * work_bytes<W_LCAP, W_MCAP>(), W_LCAP, W_MCAP, nullptr);
+  clear_table<32>(w, lane);
   const int64_t n_warps = (int64_t)gridDim.x * CAND_WARPS;
   for (int64_t s = (int64_t)blockIdx.x * CAND_WARPS + warp; s < p.n_sessions; s += n_warps) {
     const int L = p.off[s + 1] - p.off[s];
@@ -293,54 +412,49 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) candidates_warp_kernel(const 
       }
       continue;
     }
-    process_session<32>(p, s, lane, w);
+    process_session<32>(p, s, lane, w, nullptr);
   }
+}
+
+static int64_t global_mcap(int max_len, int max_k_sum) {
+  const int64_t bound = (int64_t)max_len * max_k_sum;
+  int64_t mcap = 1;
+  while (mcap < bound) mcap <<= 1;
+  return mcap;
+}
+static int64_t global_lcap(int max_len) {
+  int64_t lcap = 1;
+  while (lcap < max_len) lcap <<= 1;
+  return lcap;
+}
+// u64 words of one block's slab in the global tier (same layout as work_bytes)
+static int64_t global_slab_words(int max_len, int max_k_sum) {
+  const int64_t mcap = global_mcap(max_len, max_k_sum), lcap = global_lcap(max_len);
+  return (mcap * 8 + lcap * 8 + 2 * mcap * 12 + mcap * 4 + lcap * 4 * 7 + 32 + 7) / 8;
 }
 
 // tiers 2 and 3: one 256-thread block per session
 template <bool GLOBAL>
-__global__ void __launch_bounds__(256) candidates_block_kernel(const CandParams p) {
+__global__ void __launch_bounds__(256) candidates_block_kernel(const CandParams p, int64_t g_lcap, int64_t g_mcap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_item;
+  __shared__ uint64_t s_gmax[256];
+  __shared__ __align__(8) int32_t s_scal[8];
   Work w;
-  if (GLOBAL) {
-    // carve the slab with runtime capacities
-    unsigned char* base = (unsigned char*)(p.slab + (int64_t)blockIdx.x * p.slab_words);
-    const int64_t mcap = pow2_at_least((int)min((int64_t)1 << 30, item_bound(p, p.max_len)));
-    const int64_t lcap = pow2_at_least(p.max_len > 1 ? p.max_len : 1);
-    w.items = (uint64_t*)base;
-    w.ent = w.items + mcap;
-    w.ord = w.ent + mcap;
-    w.ev_aid = (int32_t*)(w.ord + lcap);
-    w.ev_ty = w.ev_aid + lcap;
-    w.uidx = w.ev_ty + lcap;
-    w.H = w.uidx + lcap;
-    w.tmask = w.H + lcap;
-    w.elen = w.tmask + lcap;
-    w.estart = w.elen + lcap;
-    w.scal = (int32_t*)smem_raw;
-  } else {
-    w = carve<B_LCAP, B_MCAP>(smem_raw);
-  }
+  if (GLOBAL) w = carve_rt((unsigned char*)(p.slab + (int64_t)blockIdx.x * p.slab_words), g_lcap, g_mcap, s_scal);
+  else w = carve_rt(smem_raw, B_LCAP, B_MCAP, s_scal);
   const uint32_t* list = GLOBAL ? p.list_global : p.list_block;
   const uint32_t n_items = p.counters[GLOBAL ? 1 : 0];
+  if (n_items == 0) return;
+  clear_table<256>(w, threadIdx.x);
   while (true) {
     if (threadIdx.x == 0) s_item = atomicAdd(&p.counters[GLOBAL ? 3 : 2], 1u);
     __syncthreads();
     const uint32_t item = s_item;
     if (item >= n_items) break;
-    process_session<256>(p, (int64_t)list[item], threadIdx.x, w);
+    process_session<256>(p, (int64_t)list[item], threadIdx.x, w, s_gmax);
     __syncthreads();
   }
-}
-
-static int64_t global_slab_words(int max_len, int max_k_sum) {
-  int64_t bound = (int64_t)max_len * max_k_sum;
-  int64_t mcap = 1;
-  while (mcap < bound) mcap <<= 1;
-  int64_t lcap = 1;
-  while (lcap < max_len) lcap <<= 1;
-  return 2 * mcap + lcap + (lcap * 7 * 4 + 7) / 8 + 8;
 }
 
 static int spec_max_k_sum(const OttoCandidateSpec* sp) {
@@ -442,10 +556,10 @@ extern "C" int otto_candidates(const OttoSessions* sessions, int32_t max_session
   {
     constexpr size_t smem = work_bytes<B_LCAP, B_MCAP>();
     CUDA_TRY(cudaFuncSetAttribute(candidates_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    candidates_block_kernel<false><<<n_sm * 2, 256, smem, st>>>(p);
+    candidates_block_kernel<false><<<n_sm * 2, 256, smem, st>>>(p, 0, 0);
     LAUNCH_CHECK();
   }
-  candidates_block_kernel<true><<<GLOBAL_BLOCKS, 256, 64, st>>>(p);
+  candidates_block_kernel<true><<<GLOBAL_BLOCKS, 256, 0, st>>>(p, global_lcap(max_session_len), global_mcap(max_session_len, p.max_k_sum));
   LAUNCH_CHECK();
   for (int tg = 0; tg < spec->n_targets; ++tg) {
     if (dup_of[tg] < 0) continue;
