@@ -31,9 +31,10 @@ struct CandParams {
   int32_t* out_score;
   int32_t* out_len;
   // tiers
-  uint32_t* list_block;   // sessions for the block-smem tier
+  uint32_t* list_block;   // sessions for the 128-thread shared-memory tier
+  uint32_t* list_large;   // sessions for the 256-thread shared-memory tier
   uint32_t* list_global;  // sessions for the block-global tier
-  uint32_t* counters;     // [0] n_block [1] n_global [2] next_block [3] next_global
+  uint32_t* counters;     // [0] n_block [1] n_global [2] next_block [3] next_global [4] n_large [5] next_large
   uint64_t* slab;         // global tier: per-block slab
   int64_t slab_words;     // u64 words per block
   int32_t max_k_sum;      // max over targets of the sum of table_k over its sources
@@ -43,7 +44,8 @@ struct CandParams {
 };
 
 constexpr int W_LCAP = 32, W_MCAP = 256;        // warp tier: events, gathered items
-constexpr int B_LCAP = 256, B_MCAP = 2048;      // block-smem tier
+constexpr int B_LCAP = 64, B_MCAP = 1024;       // 128-thread shared-memory tier (5 CTAs per SM)
+constexpr int X_LCAP = 256, X_MCAP = 4096;      // 256-thread shared-memory tier (1 CTA per SM)
 constexpr int CAND_WARPS = 4;
 
 template <int T>
@@ -408,6 +410,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) candidates_warp_kernel(const 
     if (L > W_LCAP || bound > W_MCAP) {
       if (lane == 0) {
         if (L <= B_LCAP && bound <= B_MCAP) p.list_block[atomicAdd(&p.counters[0], 1u)] = (uint32_t)s;
+        else if (L <= X_LCAP && bound <= X_MCAP) p.list_large[atomicAdd(&p.counters[4], 1u)] = (uint32_t)s;
         else p.list_global[atomicAdd(&p.counters[1], 1u)] = (uint32_t)s;
       }
       continue;
@@ -433,26 +436,30 @@ static int64_t global_slab_words(int max_len, int max_k_sum) {
   return (mcap * 8 + lcap * 8 + 2 * mcap * 12 + mcap * 4 + lcap * 4 * 7 + 32 + 7) / 8;
 }
 
-// tiers 2 and 3: one 256-thread block per session
-template <bool GLOBAL>
-__global__ void __launch_bounds__(256) candidates_block_kernel(const CandParams p, int64_t g_lcap, int64_t g_mcap) {
+// tiers 2 and 3: one block per session (64 threads over shared memory: sessions of 6 .. 40 events keep few
+// lanes busy and a wide block mostly waits at its barriers - profiles/r01_cand_v2; 256 threads over the slab)
+// TIER 0: 128-thread shared memory, 1: 256-thread shared memory, 2: 256 threads over the global slab
+template <int TIER, int T>
+__global__ void __launch_bounds__(T) candidates_block_kernel(const CandParams p, int64_t g_lcap, int64_t g_mcap) {
+  constexpr bool GLOBAL = TIER == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t s_item;
-  __shared__ uint64_t s_gmax[256];
+  __shared__ uint64_t s_gmax[T];
   __shared__ __align__(8) int32_t s_scal[8];
   Work w;
   if (GLOBAL) w = carve_rt((unsigned char*)(p.slab + (int64_t)blockIdx.x * p.slab_words), g_lcap, g_mcap, s_scal);
+  else if (TIER == 1) w = carve_rt(smem_raw, X_LCAP, X_MCAP, s_scal);
   else w = carve_rt(smem_raw, B_LCAP, B_MCAP, s_scal);
-  const uint32_t* list = GLOBAL ? p.list_global : p.list_block;
-  const uint32_t n_items = p.counters[GLOBAL ? 1 : 0];
+  const uint32_t* list = GLOBAL ? p.list_global : TIER == 1 ? p.list_large : p.list_block;
+  const uint32_t n_items = p.counters[GLOBAL ? 1 : TIER == 1 ? 4 : 0];
   if (n_items == 0) return;
-  clear_table<256>(w, threadIdx.x);
+  clear_table<T>(w, threadIdx.x);
   while (true) {
-    if (threadIdx.x == 0) s_item = atomicAdd(&p.counters[GLOBAL ? 3 : 2], 1u);
+    if (threadIdx.x == 0) s_item = atomicAdd(&p.counters[GLOBAL ? 3 : TIER == 1 ? 5 : 2], 1u);
     __syncthreads();
     const uint32_t item = s_item;
     if (item >= n_items) break;
-    process_session<256>(p, (int64_t)list[item], threadIdx.x, w, s_gmax);
+    process_session<T>(p, (int64_t)list[item], threadIdx.x, w, s_gmax);
     __syncthreads();
   }
 }
@@ -495,7 +502,7 @@ extern "C" int64_t otto_candidates_scratch_bytes(int64_t n_sessions, int32_t max
     otto_set_error("session too long: positions are 16-bit (max_session_len * sum of k must be < 65535)");
     return -1;
   }
-  const int64_t lists = align_up((n_sessions + 1) * 4, 256) * 2 + 256;
+  const int64_t lists = align_up((n_sessions + 1) * 4, 256) * 3 + 256;
   return lists + GLOBAL_BLOCKS * global_slab_words(max_session_len, spec_max_k_sum(spec)) * 8 + 256;
 }
 
@@ -523,8 +530,9 @@ extern "C" int otto_candidates(const OttoSessions* sessions, int32_t max_session
   const int64_t list_bytes = align_up((S + 1) * 4, 256);
   p.list_block = (uint32_t*)sc;
   p.list_global = (uint32_t*)(sc + list_bytes);
-  p.counters = (uint32_t*)(sc + 2 * list_bytes);
-  p.slab = (uint64_t*)(sc + 2 * list_bytes + 256);
+  p.list_large = (uint32_t*)(sc + 2 * list_bytes);
+  p.counters = (uint32_t*)(sc + 3 * list_bytes);
+  p.slab = (uint64_t*)(sc + 3 * list_bytes + 256);
   p.max_k_sum = spec_max_k_sum(spec);
   p.max_len = max_session_len;
   p.slab_words = global_slab_words(max_session_len, p.max_k_sum);
@@ -555,11 +563,17 @@ extern "C" int otto_candidates(const OttoSessions* sessions, int32_t max_session
   }
   {
     constexpr size_t smem = work_bytes<B_LCAP, B_MCAP>();
-    CUDA_TRY(cudaFuncSetAttribute(candidates_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    candidates_block_kernel<false><<<n_sm * 2, 256, smem, st>>>(p, 0, 0);
+    CUDA_TRY(cudaFuncSetAttribute(candidates_block_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    candidates_block_kernel<0, 128><<<n_sm * 5, 128, smem, st>>>(p, 0, 0);
     LAUNCH_CHECK();
   }
-  candidates_block_kernel<true><<<GLOBAL_BLOCKS, 256, 0, st>>>(p, global_lcap(max_session_len), global_mcap(max_session_len, p.max_k_sum));
+  {
+    constexpr size_t smem = work_bytes<X_LCAP, X_MCAP>();
+    CUDA_TRY(cudaFuncSetAttribute(candidates_block_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    candidates_block_kernel<1, 256><<<n_sm, 256, smem, st>>>(p, 0, 0);
+    LAUNCH_CHECK();
+  }
+  candidates_block_kernel<2, 256><<<GLOBAL_BLOCKS, 256, 0, st>>>(p, global_lcap(max_session_len), global_mcap(max_session_len, p.max_k_sum));
   LAUNCH_CHECK();
   for (int tg = 0; tg < spec->n_targets; ++tg) {
     if (dup_of[tg] < 0) continue;
