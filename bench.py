@@ -239,7 +239,11 @@ def run_b200(args):
         return float(t.item())
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    import ctypes as C
     phases = ["count_begin", "count_finish", "scatter", "reduce"]
+    reduce_ms = []
+    if world == 1:
+        N.check(lib.otto_profile_enable(1))
     last = {}
     dist_timing = {}
 
@@ -261,6 +265,9 @@ def run_b200(args):
         if m: m[4].record()
         if marks is not None:
             marks.append(m)
+            r5 = (C.c_float * 5)()
+            N.check(lib.otto_profile_reduce_ms(r5))
+            reduce_ms.append(list(r5))
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -308,12 +315,38 @@ def run_b200(args):
              "frac": bytes_all / world / (ms_step * 1e-3) / 1e9 / peak}
     if world == 1:
         phase_ms = {p: statistics.mean(m[i].elapsed_time(m[i + 1]) for m in marks) for i, p in enumerate(phases)}
-        dom = max(phase_ms, key=phase_ms.get)
-        achieved = alg[dom] / (phase_ms[dom] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": kernel_of[dom], "phase": dom, "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes": alg[dom], "phase_ms": phase_ms,
-                    "phase_gbs": {p: alg[p] / (phase_ms[p] * 1e-3) / 1e9 for p in phases}, "whole_build": whole}
+        # per-kernel view: the count / scatter phases are one hot kernel each (plus scans of a few us); the reduce
+        # phase is five launches that the library brackets with CUDA events on this stream (otto_profile_reduce_ms)
+        tiers = ["reduce_small_kernel", "reduce_block_kernel<128 threads>", "reduce_block_kernel<256 threads>",
+                 "reduce_block_kernel<512 threads>", "merge_split_rows_kernel"]
+        red_ms = [statistics.mean(r[i] for r in reduce_ms) for i in range(5)] if reduce_ms else [0.0] * 5
+        tr = stats.get("tier_records", [0, 0, 0, 0])
+        kernels = {
+            "tail_copy_all_kernel": (phase_ms["count_begin"], alg["count_begin"]),
+            "pairgen_kernel<count>": (phase_ms["count_finish"], alg["count_finish"]),
+            "pairgen_kernel<scatter>": (phase_ms["scatter"], alg["scatter"]),
+        }
+        for i in range(4):       # a tier reads its records once and writes the rows of its bins
+            kernels[tiers[i]] = (red_ms[i], 8 * tr[i] + (8 * A * K * tr[i]) // max(1, sum(tr)))
+        kernels[tiers[4]] = (red_ms[4], 20 * K * 2 * stats["split_rows"])
+        dom = max(kernels, key=lambda k: kernels[k][0])
+        dom_ms, dom_bytes = kernels[dom]
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        traffic = None
+        try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+            tj = json.load(open(ROOT / "profiles" / "r01_dram_traffic.json"))
+            if abs(args.scale - tj.get("scale", -1)) < 1e-9 and args.variant == tj.get("variant"):
+                traffic = tj["kernels"].get(dom)
+        except (OSError, ValueError, KeyError):
+            pass
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": dom_bytes,
+                    "kernel_ms": dom_ms, "timing": "CUDA events on the launching stream, mean over the timed steps",
+                    "kernels": {k: {"ms": round(v[0], 4), "algorithmic_bytes": int(v[1]),
+                                    "gbs": round(v[1] / (v[0] * 1e-3) / 1e9, 1) if v[0] > 0 else None,
+                                    "frac": round(v[1] / (v[0] * 1e-3) / 1e9 / peak, 4) if v[0] > 0 else None}
+                                for k, v in kernels.items()},
+                    "phase_ms": phase_ms, "whole_build": whole}
     else:
         sent = allsum(P * 8)
         roofline = {"bound": "hbm", "kernel": "whole build (phases interleave with collectives)", "achieved":

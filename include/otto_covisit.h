@@ -92,6 +92,7 @@ typedef struct {
   int64_t distinct;          /* D: distinct (aid_x, aid_y) accumulated by this rank (after reduce) */
   int64_t pair_checksum;     /* sum of counts over all accumulated entries (== pairs received) */
   int64_t table_overflow;    /* != 0: a hash table overflowed (result invalid) */
+  int64_t tier_records[4];   /* records accumulated by the warp / 128- / 256- / 512-thread reduce kernels */
 } OttoBuildStats;
 
 /* Pair records of one producer for a contiguous range of bins (multi-GPU: one segment per sender). */
@@ -117,6 +118,12 @@ const char* otto_last_error(void);
 int otto_version(void);
 /* Kernels this library has launched so far in this process (bench.py reports the per-step delta). */
 uint64_t otto_launch_count(void);
+
+/* Measurement aid for bench.py: with profiling on, otto_covisit_reduce brackets each of its kernels with CUDA
+ * events on the caller's stream; otto_profile_reduce_ms synchronises the last one and returns the five
+ * durations of the most recent call (small, medium, large, extra-large, merge_split_rows) in milliseconds. */
+int otto_profile_enable(int on);
+int otto_profile_reduce_ms(float* ms_host /* [5] */);
 
 /* ---- ingest: frame columns -> CSR (replaces the sort + chunk writers of
  *      utilities/split_dataset_writer_parquet.py:13-33 and builder step 2) ---- */

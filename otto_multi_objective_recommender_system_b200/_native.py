@@ -39,10 +39,12 @@ class OttoBuildSizes(C.Structure):
 
 class OttoBuildStats(C.Structure):
     _fields_ = [("tail_events", i64), ("pairs", i64), ("bins", i64), ("split_rows", i64), ("distinct", i64),
-                ("pair_checksum", i64), ("table_overflow", i64)]
+                ("pair_checksum", i64), ("table_overflow", i64), ("tier_records", i64 * 4)]
 
     def as_dict(self) -> dict:
-        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+        d = {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "tier_records"}
+        d["tier_records"] = [int(x) for x in self.tier_records]
+        return d
 
 
 class OttoPairSegment(C.Structure):
@@ -74,6 +76,8 @@ _SIGNATURES = {
     "otto_last_error": (C.c_char_p, []),
     "otto_version": (C.c_int, []),
     "otto_launch_count": (C.c_uint64, []),
+    "otto_profile_enable": (C.c_int, [C.c_int]),
+    "otto_profile_reduce_ms": (C.c_int, [P(C.c_float)]),
     "otto_frame_is_sorted": (C.c_int, [vp, vp, i64, vp, P(i32), vp]),
     "otto_ingest_desc": (C.c_int, [vp, i64, vp, vp, vp, i64, vp, vp, vp, vp]),
     "otto_covisit_sizes": (C.c_int, [i64, i64, P(OttoCovisitSpec), P(OttoBuildSizes)]),

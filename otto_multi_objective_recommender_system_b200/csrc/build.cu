@@ -472,6 +472,29 @@ extern "C" int64_t otto_covisit_reduce_scratch_bytes(const OttoCovisitSpec* spec
   return make_scratch(spec->k, n_bins, n_aids_range).total;
 }
 
+static int g_profile = 0;
+static cudaEvent_t g_prof_ev[6];
+static bool g_prof_ready = false, g_prof_valid = false;
+
+extern "C" int otto_profile_enable(int on) {
+  if (on && !g_prof_ready) {
+    for (auto& e : g_prof_ev) CUDA_TRY(cudaEventCreate(&e));
+    g_prof_ready = true;
+  }
+  g_profile = on;
+  return OTTO_OK;
+}
+extern "C" int otto_profile_reduce_ms(float* ms_host) {
+  if (!g_prof_valid) { otto_set_error("no profiled otto_covisit_reduce call yet"); return OTTO_EINVAL; }
+  CUDA_TRY(cudaEventSynchronize(g_prof_ev[5]));
+  for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventElapsedTime(&ms_host[i], g_prof_ev[i], g_prof_ev[i + 1]));
+  return OTTO_OK;
+}
+#define PROF_MARK(i)                                                  \
+  do {                                                                \
+    if (g_profile) CUDA_TRY(cudaEventRecord(g_prof_ev[i], st));       \
+  } while (0)
+
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
   CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -486,14 +509,17 @@ static int launch_reduce(const ReduceParams& p, int n_sm, cudaStream_t st) {
   const int64_t n_bins = p.bin_hi - p.bin_lo;
   int64_t small_blocks = ceil_div(n_bins, SMALL_WARPS);
   if (small_blocks > (int64_t)n_sm * 64) small_blocks = (int64_t)n_sm * 64;
+  PROF_MARK(0);
   reduce_small_kernel<TIME><<<(unsigned)small_blocks, SMALL_WARPS * 32, small_smem, st>>>(p);
   LAUNCH_CHECK();
+  PROF_MARK(1);
   {
     auto kern = reduce_block_kernel<TIME, 128, 11, 0>;
     constexpr size_t smem = reduce_block_smem<TIME, 128, 11, 0>();
     if ((rc = set_smem(kern, smem))) return rc;
     kern<<<n_sm * 7, 128, smem, st>>>(p);
     LAUNCH_CHECK();
+    PROF_MARK(2);
   }
   {
     auto kern = reduce_block_kernel<TIME, 256, 12, 1>;
@@ -501,6 +527,7 @@ static int launch_reduce(const ReduceParams& p, int n_sm, cudaStream_t st) {
     if ((rc = set_smem(kern, smem))) return rc;
     kern<<<n_sm * 3, 256, smem, st>>>(p);
     LAUNCH_CHECK();
+    PROF_MARK(3);
   }
   {
     auto kern = reduce_block_kernel<TIME, 512, 13, 2>;
@@ -508,9 +535,12 @@ static int launch_reduce(const ReduceParams& p, int n_sm, cudaStream_t st) {
     if ((rc = set_smem(kern, smem))) return rc;
     kern<<<n_sm, 512, smem, st>>>(p);
     LAUNCH_CHECK();
+    PROF_MARK(4);
   }
   merge_split_rows_kernel<<<n_sm * 4, 256, 0, st>>>(p);
   LAUNCH_CHECK();
+  PROF_MARK(5);
+  g_prof_valid = g_profile != 0;
   return OTTO_OK;
 }
 
@@ -569,12 +599,13 @@ extern "C" int otto_covisit_reduce(const OttoCovisitSpec* spec, const uint32_t* 
     if (rc) return rc;
   }
   if (stats_host) {
-    unsigned long long h[3];
+    unsigned long long h[8];
     CUDA_TRY(cudaMemcpyAsync(h, p.stats, sizeof(h), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     stats_host->distinct = (int64_t)h[0];
     stats_host->pair_checksum = (int64_t)h[1];
     stats_host->table_overflow = (int64_t)h[2];
+    for (int i = 0; i < 4; ++i) stats_host->tier_records[i] = (int64_t)h[4 + i];
     if (h[2]) {
       otto_set_error("a shared-memory hash table overflowed; lower split_ub");
       return OTTO_EOVERFLOW;

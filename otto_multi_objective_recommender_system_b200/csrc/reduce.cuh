@@ -57,7 +57,7 @@ struct ReduceParams {
   uint32_t* list_l;
   uint32_t* list_x;
   uint32_t* counters;        // [0] n_m  [1] n_l  [2] next_m  [3] next_l  [4] n_x  [5] next_x
-  unsigned long long* stats; // [0] distinct  [1] checksum  [2] overflow  [3] slow-path selections
+  unsigned long long* stats; // [0] distinct  [1] checksum  [2] overflow  [3] slow-path selections  [4..7] records per tier
 };
 
 constexpr uint32_t TINY_MAX = 32;      // records: one step of one warp, no table at all
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const Re
   t.clear_all(lane, 32);
   __syncwarp();
 
-  uint64_t st_occ = 0, st_pay = 0;
+  uint64_t st_occ = 0, st_pay = 0, st_rec = 0;
   uint32_t st_slow = 0;
   bool overflow = false;
   const int64_t n_warps = (int64_t)gridDim.x * SMALL_WARPS;
@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const Re
       emit_finish(p, o, 0);
       continue;
     }
+    if (lane == 0) st_rec += n;
     if (n <= TINY_MAX) {
       // the whole bin is one step: fold duplicates with match_any, rank the group leaders, done
       const bool has = lane < n;
@@ -454,6 +455,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const Re
     atomicAdd(&p.stats[1], (unsigned long long)st_pay);
     if (st_slow) atomicAdd(&p.stats[3], (unsigned long long)(st_slow / 32));
   }
+  if (lane == 0 && st_rec) atomicAdd(&p.stats[4], (unsigned long long)st_rec);
   if (overflow) atomicOr(&p.stats[2], 1ull);
 }
 
@@ -494,7 +496,7 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
 
   const uint32_t* list = TIER == 0 ? p.list_m : TIER == 1 ? p.list_l : p.list_x;
   const uint32_t n_items = p.counters[TIER == 0 ? 0 : TIER == 1 ? 1 : 4];
-  uint64_t st_occ = 0, st_pay = 0;
+  uint64_t st_occ = 0, st_pay = 0, st_rec = 0;
   uint32_t st_slow = 0;
   bool overflow = false;
   t.clear_all(threadIdx.x, THREADS);
@@ -507,6 +509,7 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
     const uint32_t n = bin_records(p, b);
     const uint32_t n_pass = n > SINGLE_CAP ? (n + SLOTS / 2 - 1) / (SLOTS / 2) : 1;
     const BinOut o = bin_out(p, b);
+    if (threadIdx.x == 0) st_rec += n;
     int n_best = 0;  // meaningful in warp 0
     for (uint32_t pass = 0; pass < n_pass; ++pass) {
       const bool last = pass + 1 == n_pass;
@@ -657,6 +660,7 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
     atomicAdd(&p.stats[1], (unsigned long long)st_pay);
     if (st_slow) atomicAdd(&p.stats[3], (unsigned long long)st_slow);
   }
+  if (threadIdx.x == 0 && st_rec) atomicAdd(&p.stats[5 + TIER], (unsigned long long)st_rec);
   if (overflow) atomicOr(&p.stats[2], 1ull);
 }
 
