@@ -121,7 +121,9 @@ uint64_t otto_launch_count(void);
 
 /* Measurement aid for bench.py: with profiling on, otto_covisit_reduce brackets each of its kernels with CUDA
  * events on the caller's stream; otto_profile_reduce_ms synchronises the last one and returns the five
- * durations of the most recent call (small, medium, large, extra-large, merge_split_rows) in milliseconds. */
+ * durations of the most recent call (warp kernel, 512-, 256-, 128-thread block kernels, merge_split_rows) in
+ * milliseconds.  Profiled calls run the block kernels back to back on the caller's stream; unprofiled calls run
+ * them concurrently on two internal side streams (forked from and joined to the caller's stream). */
 int otto_profile_enable(int on);
 int otto_profile_reduce_ms(float* ms_host /* [5] */);
 

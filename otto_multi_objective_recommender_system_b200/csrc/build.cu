@@ -501,9 +501,29 @@ static int set_smem(K kernel, size_t bytes) {
   return OTTO_OK;
 }
 
+// The three block kernels work on disjoint bin lists, so they run concurrently on two side streams (forked
+// after the warp kernel has built the lists, joined before the split-row merge): each of them alone leaves SMs
+// idle in its tail and the 512-thread kernel fills only a quarter of the warp slots.  OTTO_REDUCE_SERIAL=1 keeps
+// everything on the caller's stream.
+static cudaStream_t g_side[2];
+static cudaEvent_t g_fork, g_join[2];
+static bool g_side_ready = false;
+
+static int side_streams_init() {
+  if (g_side_ready) return OTTO_OK;
+  for (auto& s : g_side) CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+  for (auto& e : g_join) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  g_side_ready = true;
+  return OTTO_OK;
+}
+
 template <bool TIME>
 static int launch_reduce(const ReduceParams& p, int n_sm, cudaStream_t st) {
   int rc;
+  static const bool serial = getenv("OTTO_REDUCE_SERIAL") != nullptr;
+  const bool fork = !serial && !g_profile;
+  if (fork && (rc = side_streams_init())) return rc;
   constexpr size_t small_smem = (size_t)SMALL_WARPS * SMALL_PER_WARP;
   if ((rc = set_smem(reduce_small_kernel<TIME>, small_smem))) return rc;
   const int64_t n_bins = p.bin_hi - p.bin_lo;
@@ -513,29 +533,43 @@ static int launch_reduce(const ReduceParams& p, int n_sm, cudaStream_t st) {
   reduce_small_kernel<TIME><<<(unsigned)small_blocks, SMALL_WARPS * 32, small_smem, st>>>(p);
   LAUNCH_CHECK();
   PROF_MARK(1);
+  cudaStream_t s_l = st, s_x = st;
+  if (fork) {
+    CUDA_TRY(cudaEventRecord(g_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(g_side[0], g_fork, 0));
+    CUDA_TRY(cudaStreamWaitEvent(g_side[1], g_fork, 0));
+    s_l = g_side[0];
+    s_x = g_side[1];
+  }
+  {
+    auto kern = reduce_block_kernel<TIME, 512, 13, 2>;
+    constexpr size_t smem = reduce_block_smem<TIME, 512, 13, 2>();
+    if ((rc = set_smem(kern, smem))) return rc;
+    kern<<<n_sm, 512, smem, s_x>>>(p);
+    LAUNCH_CHECK();
+    if (!fork) PROF_MARK(2);
+  }
+  {
+    auto kern = reduce_block_kernel<TIME, 256, 12, 1>;
+    constexpr size_t smem = reduce_block_smem<TIME, 256, 12, 1>();
+    if ((rc = set_smem(kern, smem))) return rc;
+    kern<<<n_sm * 3, 256, smem, s_l>>>(p);
+    LAUNCH_CHECK();
+    if (!fork) PROF_MARK(3);
+  }
   {
     auto kern = reduce_block_kernel<TIME, 128, 11, 0>;
     constexpr size_t smem = reduce_block_smem<TIME, 128, 11, 0>();
     if ((rc = set_smem(kern, smem))) return rc;
     kern<<<n_sm * 7, 128, smem, st>>>(p);
     LAUNCH_CHECK();
-    PROF_MARK(2);
+    if (!fork) PROF_MARK(4);
   }
-  {
-    auto kern = reduce_block_kernel<TIME, 256, 12, 1>;
-    constexpr size_t smem = reduce_block_smem<TIME, 256, 12, 1>();
-    if ((rc = set_smem(kern, smem))) return rc;
-    kern<<<n_sm * 3, 256, smem, st>>>(p);
-    LAUNCH_CHECK();
-    PROF_MARK(3);
-  }
-  {
-    auto kern = reduce_block_kernel<TIME, 512, 13, 2>;
-    constexpr size_t smem = reduce_block_smem<TIME, 512, 13, 2>();
-    if ((rc = set_smem(kern, smem))) return rc;
-    kern<<<n_sm, 512, smem, st>>>(p);
-    LAUNCH_CHECK();
-    PROF_MARK(4);
+  if (fork) {
+    CUDA_TRY(cudaEventRecord(g_join[0], g_side[0]));
+    CUDA_TRY(cudaEventRecord(g_join[1], g_side[1]));
+    CUDA_TRY(cudaStreamWaitEvent(st, g_join[0], 0));
+    CUDA_TRY(cudaStreamWaitEvent(st, g_join[1], 0));
   }
   merge_split_rows_kernel<<<n_sm * 4, 256, 0, st>>>(p);
   LAUNCH_CHECK();
