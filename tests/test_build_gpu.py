@@ -224,3 +224,25 @@ def test_linearity_over_session_halves(cv):
         stats.append(b.stats.as_dict())
     assert stats[0]["pairs"] == stats[1]["pairs"] + stats[2]["pairs"]
     assert stats[0]["pair_checksum"] == stats[1]["pair_checksum"] + stats[2]["pair_checksum"]
+
+
+def test_bin_arrays_guard_refuses_more_bins_than_sized(cv):
+    """Multi-GPU contract: bins come from the all-reduced bounds, so a rank whose workspace was sized for its own
+    shard only (global_events = 0) must be refused before anything is written past the bin arrays."""
+    from dataclasses import replace
+    frame = synth_frame(400, 60, seed=3)
+    csr = cv.ingest(frame, "desc", device="cuda:0")
+    b = cv.CovisitBuilder(csr, replace(cv.CLICKS, split_ub=16))
+    b.count_begin()
+    b.stats.bins = 0
+    ub = b.views()["pair_ub"]
+    ub.mul_(1000)                      # what an all-reduce over many more ranks would do to the bounds
+    with pytest.raises(cv.N.OttoError) as e:
+        b.count_finish()
+    assert e.value.code == cv.N.OTTO_ENOSPC and "global_events" in str(e.value)
+    # sized for the global frame, the same bounds are fine
+    b2 = cv.CovisitBuilder(csr, replace(cv.CLICKS, split_ub=16, global_events=1000 * csr.n_events))
+    b2.count_begin()
+    b2.stats.bins = 0
+    b2.views()["pair_ub"].mul_(1000)
+    assert b2.count_finish()["bins"] > csr.n_aids
