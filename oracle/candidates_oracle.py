@@ -86,6 +86,38 @@ def standalone_predictions(session_aids, session_event_types, tables, popular, n
     return out
 
 
+def recency_predictions(session_aids, session_event_types, tables, n: int = 20):
+    """One long session (>= 20 unique aids) of covisitation/inference.py:142-199 (= :336-392), statement for
+    statement, without the fastText / Annoy bonus (:165-170)."""
+    event_type_coefficient = {0: 1, 1: 9, 2: 6}                                             # :72
+    t = {s: tables.get(s, {}) for s in STEMS}
+    a = np.array(session_aids)
+    e = np.array(session_event_types)
+    session_unique_click_aids = np.unique(a[e == 0]).tolist()
+    session_unique_click_and_cart_aids = np.unique(a[e <= 1]).tolist()
+    session_unique_cart_and_order_aids = np.unique(a[e >= 1]).tolist()
+    click_recency_weights = np.logspace(0.1, 1, len(session_aids), base=2, endpoint=True) - 1
+    cart_recency_weights = np.logspace(0.5, 1, len(session_aids), base=2, endpoint=True) - 1
+    order_recency_weights = np.logspace(0.5, 1, len(session_aids), base=2, endpoint=True) - 1
+    session_aid_click_weights = Counter()
+    session_aid_cart_weights = Counter()
+    session_aid_order_weights = Counter()
+    for aid, event_type, cw, kw, ow in zip(session_aids, session_event_types, click_recency_weights, cart_recency_weights, order_recency_weights):
+        session_aid_click_weights[aid] += (cw * event_type_coefficient[event_type])
+        session_aid_cart_weights[aid] += (kw * event_type_coefficient[event_type])
+        session_aid_order_weights[aid] += (ow * event_type_coefficient[event_type])
+    for aid in itertools.chain(*[t["time_weighted"][x] for x in session_unique_click_aids if x in t["time_weighted"]]):
+        session_aid_click_weights[aid] += 0.05
+    sorted_click_aids = [aid for aid, weight in session_aid_click_weights.most_common(n)]
+    for aid in itertools.chain(*[t["cart_weighted"][x] for x in session_unique_click_and_cart_aids if x in t["cart_weighted"]]):
+        session_aid_cart_weights[aid] += 0.05
+    sorted_cart_aids = [aid for aid, weight in session_aid_cart_weights.most_common(n)]
+    for aid in itertools.chain(*[t["cart_order"][x] for x in session_unique_cart_and_order_aids if x in t["cart_order"]]):
+        session_aid_order_weights[aid] += 0.15
+    sorted_order_aids = [aid for aid, weight in session_aid_order_weights.most_common(n)]
+    return [sorted_click_aids, sorted_cart_aids, sorted_order_aids]
+
+
 def ranker_frame(df_events: pd.DataFrame, tables: dict, n: int = 100) -> dict:
     """All sessions -> the three exploded candidate frames the ranker script pickles (:177-197 / :290-307):
     columns session, candidates uint64, candidate_scores float32."""

@@ -67,6 +67,12 @@ class OttoCandidateSpec(C.Structure):
                 ("top_n", i32), ("drop_history", i32)]
 
 
+class OttoRecencySpec(C.Structure):
+    _fields_ = [("n_aids", i32), ("n", i32), ("table_aid_y", vp * 3), ("table_len", vp * 3), ("table_k", i32 * 3),
+                ("hist", i32 * 3), ("bonus", C.c_double * 3), ("type_coefficient", C.c_double * 3), ("w_click", vp),
+                ("w_cart", vp), ("w_offset", vp)]
+
+
 class OttoCandidates(C.Structure):
     _fields_ = [("aid", vp), ("score", vp), ("len", vp)]
 
@@ -103,6 +109,8 @@ _SIGNATURES = {
     "otto_rows_to_topk": (C.c_int, [vp, vp, vp, i64, P(OttoTopK), vp]),
     "otto_candidates_scratch_bytes": (i64, [i64, i32, P(OttoCandidateSpec)]),
     "otto_candidates": (C.c_int, [P(OttoSessions), i32, P(OttoCandidateSpec), vp, i64, P(OttoCandidates), vp]),
+    "otto_recency_scratch_bytes": (i64, [i32, i32]),
+    "otto_recency_long": (C.c_int, [P(OttoSessions), vp, i32, i32, P(OttoRecencySpec), vp, i64, vp, vp]),
     "otto_assemble_predictions": (C.c_int, [P(OttoSessions), P(OttoCandidates), i32, i32, vp, i32, i32, vp, vp, vp]),
 }
 

@@ -12,8 +12,8 @@ Mirrors the reference script's file contract (covisitation/inference.py:44-52,76
   any other mode raises ValueError('Invalid mode'), like the reference.
 --build first builds the three graded matrices (the builder the reference ships without) from
 train ∪ val (validation) or train ∪ test (submission) and writes the part files.
-Differences, stated: the fastText/Annoy neighbour term (:223-224) is not on this path; sessions with >= 20
-unique aids keep their 20 most recent unique aids (the reference routes them to its recency branch, :128-131).
+Difference, stated: the fastText / Annoy neighbour terms (:165-170, :223-224) are not on this path (no model
+offline).  Sessions with >= 20 unique aids take the recency-weight branch (:128-131, :142-199) like the reference.
 """
 from __future__ import annotations
 
@@ -106,6 +106,9 @@ def main(argv=None) -> dict:
     sess = covisit.ingest(test_frame, "asc", device=dev)
     cand = candidates.generate_candidates(sess, tables, candidates.reference_spec(tables.keys(), 20))
     pred, long_session = candidates.assemble_predictions(sess, cand, popular, 20)
+    # sessions with >= 20 unique aids: recency-weighted ranking (covisitation/inference.py:128-131,142-199)
+    candidates.recency_long_predictions(sess, tables, pred, long_session, 20)
+    logging.info(f"{int(long_session.sum())} sessions are predicted with recency weight")
     logging.info(f"{int((~long_session).sum())} sessions are predicted with covisitation")
     result = {"sessions": sess.n_sessions, "long_sessions": int(long_session.sum()), "session_ids": sess.session_ids,
               "pred": pred, "long_session": long_session}

@@ -159,3 +159,45 @@ def test_candidate_edge_cases(mods):
     frame = synth.EventFrame.from_pandas(df, n_aids)
     compare(cand_mod, cv, frame, df, tables, otables, tables.keys(), 100)
     compare(cand_mod, cv, frame, df, tables, otables, tables.keys(), 1)
+
+
+def test_long_session_recency_branch_matches_reference_loop(mods):
+    """covisitation/inference.py:142-199: sessions with >= 20 unique aids, fp64 scores, bit-exact ranking."""
+    cv, cand_mod, synth = mods
+    rng = np.random.default_rng(11)
+    n_aids = 400
+    tables, otables = {}, {}
+    for stem, k in (("time_weighted", 15), ("cart_weighted", 15), ("cart_order", 15)):
+        tables[stem], otables[stem] = random_table(cv, rng, n_aids, k)
+    rows = []
+    for s, L in enumerate([25, 40, 64, 130, 300, 22, 3, 21]):
+        aids = rng.integers(0, n_aids if L > 10 else 3, L)
+        if L == 22:
+            aids = np.arange(22) * 3                      # exactly 22 unique aids, one event each
+        types = rng.choice([0, 1, 2], L, p=[0.8, 0.15, 0.05])
+        rows += [(100 + s, int(a), i, int(t)) for i, (a, t) in enumerate(zip(aids, types))]
+    df = pd.DataFrame(rows, columns=["session", "aid", "ts", "type"])
+    sess = cv.ingest(synth.EventFrame.from_pandas(df, n_aids), "asc", device="cuda:0")
+    lists = oc.session_lists(df)
+    uniq = np.array([len(set(a)) for a in lists["aid"]])
+    long_session = torch.tensor(uniq >= 20, device="cuda:0")
+    assert int(long_session.sum()) >= 6 and not bool(long_session.all())
+    pred = torch.full((3, sess.n_sessions, 20), -7, dtype=torch.int32, device="cuda:0")
+    cand_mod.recency_long_predictions(sess, tables, pred, long_session, 20)
+    got = pred.cpu().numpy()
+    for i, t in enumerate(lists.itertuples()):
+        if uniq[i] >= 20:
+            want = oc.recency_predictions(t.aid, t.type, otables, 20)
+            for ti in range(3):
+                assert got[ti, i].tolist() == want[ti], (t.session, ti)
+        else:
+            assert (got[:, i] == -7).all()                # short sessions are not touched
+    # a table may be absent (the reference's `if aid in table` guards): only the recency scores remain
+    pred2 = torch.full((3, sess.n_sessions, 20), -7, dtype=torch.int32, device="cuda:0")
+    cand_mod.recency_long_predictions(sess, {"time_weighted": tables["time_weighted"]}, pred2, long_session, 20)
+    got2 = pred2.cpu().numpy()
+    for i, t in enumerate(lists.itertuples()):
+        if uniq[i] >= 20:
+            want = oc.recency_predictions(t.aid, t.type, {"time_weighted": otables["time_weighted"]}, 20)
+            for ti in range(3):
+                assert got2[ti, i].tolist() == want[ti], (t.session, ti)

@@ -136,3 +136,19 @@ def test_covisitation_df_to_dict_matches_reference_source():
         ns = {}
         exec(body, ns)
         assert ns["covisitation_df_to_dict"](df) == ours
+
+
+def test_recency_branch_restatement_properties():
+    """covisitation/inference.py:142-199: later events weigh more, carts / orders count 9x / 6x, bonuses break ties."""
+    from oracle import candidates_oracle as oc
+    aids = list(range(25))
+    types = [0] * 25
+    clicks, carts, orders = oc.recency_predictions(aids, types, {}, 20)
+    assert clicks == list(range(24, 4, -1)) and carts == clicks and orders == clicks      # most recent first
+    types2 = [0] * 25
+    types2[0] = 1                                        # the oldest event is a cart: 9x lifts it to the top of the cart list
+    _, carts2, _ = oc.recency_predictions(aids, types2, {}, 20)
+    assert carts2[0] == 0
+    tables = {"time_weighted": {24: [7, 7]}}             # two +0.05 bonuses for aid 7 in the click ranking only
+    c3, k3, _ = oc.recency_predictions(aids, types, tables, 20)
+    assert c3.index(7) < clicks.index(7) and k3 == carts
