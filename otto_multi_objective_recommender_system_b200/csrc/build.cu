@@ -1,6 +1,7 @@
 // C-ABI entry points of the covisitation build (include/otto_covisit.h) and the small kernels around
 // the two hot ones (pairgen.cuh, reduce.cuh): ingest, tail CSR, per-aid pair upper bounds, bins.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"

@@ -77,6 +77,12 @@ __device__ __forceinline__ uint32_t bin_records(const ReduceParams& p, int64_t b
   return n;
 }
 
+// single-segment fast path: the bin's run (NULL when the bin is spread over several segments)
+__device__ __forceinline__ const uint2* bin_run(const ReduceParams& p, int64_t b) {
+  if (p.n_seg != 1) return nullptr;
+  return (const uint2*)p.seg[0].records + (p.seg[0].offsets[b - p.bin_lo] - p.seg[0].offsets[0]);
+}
+
 // record i of bin b in the concatenation of the segments' runs (i < bin_records)
 __device__ __forceinline__ uint2 bin_record(const ReduceParams& p, int64_t b, uint32_t i) {
   for (int s = 0; s < p.n_seg; ++s) {
@@ -152,6 +158,49 @@ struct Table {
       if (TIME) atomicAdd(&hc[h], 1u + ((old + v < old) ? (1u << 24) : 0u));
     }
     return state != 0 || !has;
+  }
+  // Two records per lane with their probe sequences interleaved: both CAS are in flight together, and the loop
+  // control, the reconvergence, the occupied-list append (one atomic for both) are paid once per 64 records.
+  // A lane's two records may carry the same aid_y: the second CAS then finds the first one's claim.
+  __device__ __forceinline__ bool insert2(bool has0, uint32_t y0, uint32_t v0, bool has1, uint32_t y1, uint32_t v1) {
+    uint32_t h0 = (y0 * 0x9E3779B1u) >> (32 - LOG), h1 = (y1 * 0x9E3779B1u) >> (32 - LOG);
+    const uint32_t step0 = ((y0 * 0x85EBCA6Bu) >> (32 - LOG)) | 1u, step1 = ((y1 * 0x85EBCA6Bu) >> (32 - LOG)) | 1u;
+    uint32_t prev0 = 0x80000000u, prev1 = 0x80000000u;
+    bool p0 = has0, p1 = has1;
+#pragma unroll 1
+    for (uint32_t probe = SLOTS; probe && (p0 || p1); --probe) {
+      if (p0) prev0 = atomicCAS(&keys[h0], KEY_EMPTY, y0);
+      if (p1) prev1 = atomicCAS(&keys[h1], KEY_EMPTY, y1);
+      if (p0) {
+        if (prev0 == KEY_EMPTY || prev0 == y0) p0 = false;
+        else h0 = (h0 + step0) & (SLOTS - 1);
+      }
+      if (p1) {
+        if (prev1 == KEY_EMPTY || prev1 == y1) p1 = false;
+        else h1 = (h1 + step1) & (SLOTS - 1);
+      }
+    }
+    const int state0 = (!has0 || p0) ? 0 : prev0 == KEY_EMPTY ? 2 : 1;
+    const int state1 = (!has1 || p1) ? 0 : prev1 == KEY_EMPTY ? 2 : 1;
+    __syncwarp();
+    const uint32_t fresh0 = __ballot_sync(FULL_MASK, state0 == 2), fresh1 = __ballot_sync(FULL_MASK, state1 == 2);
+    if (fresh0 | fresh1) {
+      uint32_t base = 0;
+      if (lane_id() == 0) base = atomicAdd(n_occ, (uint32_t)(__popc(fresh0) + __popc(fresh1)));
+      base = __shfl_sync(FULL_MASK, base, 0);
+      const uint32_t lt = lanemask_lt();
+      if (state0 == 2) occ[base + __popc(fresh0 & lt)] = (uint16_t)h0;
+      if (state1 == 2) occ[base + __popc(fresh0) + __popc(fresh1 & lt)] = (uint16_t)h1;
+    }
+    if (state0 != 0) {
+      const uint32_t old = atomicAdd(&lo[h0], v0);
+      if (TIME) atomicAdd(&hc[h0], 1u + ((old + v0 < old) ? (1u << 24) : 0u));
+    }
+    if (state1 != 0) {
+      const uint32_t old = atomicAdd(&lo[h1], v1);
+      if (TIME) atomicAdd(&hc[h1], 1u + ((old + v1 < old) ? (1u << 24) : 0u));
+    }
+    return (state0 != 0 || !has0) && (state1 != 0 || !has1);
   }
   __device__ __forceinline__ uint32_t count(uint32_t h) const { return TIME ? (hc[h] & 0xffffffu) : 0u; }
   __device__ __forceinline__ uint64_t sum(uint32_t h) const {
@@ -343,17 +392,39 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const Re
   uint32_t st_slow = 0;
   bool overflow = false;
   const int64_t n_warps = (int64_t)gridDim.x * SMALL_WARPS;
-  for (int64_t b = p.bin_lo + (int64_t)blockIdx.x * SMALL_WARPS + warp; b < p.bin_hi; b += n_warps) {
-    const uint32_t n = bin_records(p, b);
-    if (n > SMALL_MAX) {  // hand over to a block kernel
-      if (lane == 0) {
-        if (n <= MEDIUM_MAX) p.list_m[atomicAdd(&p.counters[0], 1u)] = (uint32_t)(b - p.bin_lo);
-        else if (n <= LARGE_MAX) p.list_l[atomicAdd(&p.counters[1], 1u)] = (uint32_t)(b - p.bin_lo);
-        else p.list_x[atomicAdd(&p.counters[4], 1u)] = (uint32_t)(b - p.bin_lo);
-      }
-      continue;
+  // A warp takes 32 consecutive bins at a time: lane l walks the dependent metadata loads of bin c0 + l (record
+  // offsets, bin -> aid_x, first bin of the row), so their latency is paid once per 32 bins instead of once per
+  // bin (r01: with one chain per bin the kernels were bound by exactly these round trips), then the bins are
+  // processed one by one with the metadata coming from registers.
+  for (int64_t c0 = p.bin_lo + ((int64_t)blockIdx.x * SMALL_WARPS + warp) * 32; c0 < p.bin_hi; c0 += n_warps * 32) {
+    const int64_t bl = c0 + lane;
+    const bool inb = bl < p.bin_hi;
+    const uint32_t n_l = inb ? bin_records(p, bl) : 0u;
+    if (inb && n_l > SMALL_MAX) {  // hand over to a block kernel
+      if (n_l <= MEDIUM_MAX) p.list_m[atomicAdd(&p.counters[0], 1u)] = (uint32_t)(bl - p.bin_lo);
+      else if (n_l <= LARGE_MAX) p.list_l[atomicAdd(&p.counters[1], 1u)] = (uint32_t)(bl - p.bin_lo);
+      else p.list_x[atomicAdd(&p.counters[4], 1u)] = (uint32_t)(bl - p.bin_lo);
     }
-    const BinOut o = bin_out(p, b);
+    BinOut o_l;
+    o_l.whole = true;
+    o_l.row = 0;
+    o_l.x = 0;
+    const uint2* run_l = nullptr;
+    if (inb && n_l <= SMALL_MAX) {
+      o_l = bin_out(p, bl);
+      run_l = bin_run(p, bl);
+    }
+    uint32_t todo = __ballot_sync(FULL_MASK, inb && n_l <= SMALL_MAX);
+    while (todo) {
+    const int srcl = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int64_t b = c0 + srcl;
+    const uint32_t n = __shfl_sync(FULL_MASK, n_l, srcl);
+    BinOut o;
+    o.whole = __shfl_sync(FULL_MASK, (int)o_l.whole, srcl) != 0;
+    o.row = (int64_t)shfl_u64((uint64_t)o_l.row, srcl);
+    o.x = __shfl_sync(FULL_MASK, o_l.x, srcl);
+    const uint2* run = (const uint2*)shfl_u64((uint64_t)(uintptr_t)run_l, srcl);
     if (n == 0) {
       emit_finish(p, o, 0);
       continue;
@@ -363,7 +434,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const Re
       // the whole bin is one step: fold duplicates with match_any, rank the group leaders, done
       const bool has = lane < n;
       uint2 r = make_uint2(0x80000000u | lane, 0);
-      if (has) r = bin_record(p, b, lane);
+      if (has) r = run ? ld_stream_u2(run + lane) : bin_record(p, b, lane);
       const uint32_t lt = lanemask_lt();
       const uint32_t peers = __match_any_sync(FULL_MASK, r.x);
       const bool lead = has && (peers & lt) == 0;
@@ -390,15 +461,21 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const Re
       continue;
     }
     if (lane == 0) *n_cand = 0;
-    for (int s = 0; s < p.n_seg; ++s) {
-      const uint64_t o0 = p.seg[s].offsets[0];
-      const uint64_t beg = p.seg[s].offsets[b - p.bin_lo] - o0, end = p.seg[s].offsets[b - p.bin_lo + 1] - o0;
-      const uint2* rec = (const uint2*)p.seg[s].records;
-      for (uint64_t i0 = beg; i0 < end; i0 += 32) {
-        const bool has = i0 + lane < end;
-        uint2 r = make_uint2(0, 0);
-        if (has) r = ld_stream_u2(rec + i0 + lane);
-        if (!t.insert(has, r.x, r.y)) overflow = true;
+    for (int s = 0; s < (run ? 1 : p.n_seg); ++s) {
+      uint64_t beg = 0, end = n;
+      const uint2* rec = run;
+      if (!run) {
+        const uint64_t o0 = p.seg[s].offsets[0];
+        beg = p.seg[s].offsets[b - p.bin_lo] - o0;
+        end = p.seg[s].offsets[b - p.bin_lo + 1] - o0;
+        rec = (const uint2*)p.seg[s].records;
+      }
+      for (uint64_t i0 = beg; i0 < end; i0 += 64) {
+        const bool has0 = i0 + lane < end, has1 = i0 + 32 + lane < end;
+        uint2 r0 = make_uint2(0, 0), r1 = make_uint2(0, 0);
+        if (has0) r0 = ld_stream_u2(rec + i0 + lane);
+        if (has1) r1 = ld_stream_u2(rec + i0 + 32 + lane);
+        if (!t.insert2(has0, r0.x, r0.y, has1, r1.x, r1.y)) overflow = true;
       }
     }
     __syncwarp();
@@ -443,6 +520,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const Re
     t.clear_dirty(lane, 32, d);
     if (lane == 0) *t.n_occ = 0;
     __syncwarp();
+    }
   }
   // one stats update per warp
   for (int off = 16; off > 0; off >>= 1) {
@@ -470,7 +548,7 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
   constexpr int WARPS = THREADS / 32;
   constexpr uint32_t SLOTS = 1u << LOG;
   constexpr int NC = BLOCK_CANDS + OTTO_MAX_K;     // candidates + room for the carried best list
-  __shared__ uint32_t s_item, s_ncand, s_nocc;
+  __shared__ uint32_t s_ncand, s_nocc;
   __shared__ uint64_t s_gmax[WARPS][32];
   __shared__ uint64_t s_thr;
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
@@ -500,37 +578,84 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
   uint32_t st_slow = 0;
   bool overflow = false;
   t.clear_all(threadIdx.x, THREADS);
-  if (threadIdx.x == 0) s_item = atomicAdd(&p.counters[CUR], 1u);
+  // Work items are taken BATCH at a time and their metadata (dependent loads: list -> record offsets -> bin ->
+  // aid_x -> first bin of the row) is fetched by BATCH threads in parallel into shared memory: one chain of round
+  // trips per batch instead of one per bin (the ablation in profiles/README.md: with empty tables and no inserts
+  // the block kernels still took half their time, all of it in these chains).
+  constexpr int BATCH = 8;
+  __shared__ uint32_t s_first;
+  __shared__ uint32_t s_mn[BATCH], s_mx[BATCH], s_mwhole[BATCH];
+  __shared__ int64_t s_mb[BATCH], s_mrow[BATCH];
+  __shared__ const uint2* s_mrun[BATCH];
+  if (threadIdx.x == 0) s_first = atomicAdd(&p.counters[CUR], (uint32_t)BATCH);
   __syncthreads();
   while (true) {
-    const uint32_t item = s_item;
-    if (item >= n_items) break;
-    const int64_t b = p.bin_lo + list[item];
-    const uint32_t n = bin_records(p, b);
+    const uint32_t first = s_first;
+    if (first >= n_items) break;
+    const uint32_t n_batch = min((uint32_t)BATCH, n_items - first);
+    if (threadIdx.x < n_batch) {
+      const int64_t bb = p.bin_lo + list[first + threadIdx.x];
+      const BinOut ob = bin_out(p, bb);
+      s_mb[threadIdx.x] = bb;
+      s_mn[threadIdx.x] = bin_records(p, bb);
+      s_mx[threadIdx.x] = ob.x;
+      s_mwhole[threadIdx.x] = ob.whole ? 1u : 0u;
+      s_mrow[threadIdx.x] = ob.row;
+      s_mrun[threadIdx.x] = bin_run(p, bb);
+    }
+    __syncthreads();
+    for (uint32_t k = 0; k < n_batch; ++k) {
+    const int64_t b = s_mb[k];
+    const uint32_t n = s_mn[k];
     const uint32_t n_pass = n > SINGLE_CAP ? (n + SLOTS / 2 - 1) / (SLOTS / 2) : 1;
-    const BinOut o = bin_out(p, b);
+    BinOut o;
+    o.x = s_mx[k];
+    o.whole = s_mwhole[k] != 0;
+    o.row = s_mrow[k];
+    const uint2* run = s_mrun[k];
     if (threadIdx.x == 0) st_rec += n;
     int n_best = 0;  // meaningful in warp 0
     for (uint32_t pass = 0; pass < n_pass; ++pass) {
       const bool last = pass + 1 == n_pass;
       if (threadIdx.x == 0) s_ncand = 0;
       uint32_t n_st = 0;   // records staged by this warp (multi-pass only)
-      for (int s = 0; s < p.n_seg; ++s) {
-        const uint64_t o0 = p.seg[s].offsets[0];
-        const uint64_t beg = p.seg[s].offsets[b - p.bin_lo] - o0, end = p.seg[s].offsets[b - p.bin_lo + 1] - o0;
-        const uint2* rec = (const uint2*)p.seg[s].records;
-        // software pipeline: the next record is in flight while the current one is inserted
-        bool has_n = beg + threadIdx.x < end;
-        uint2 r_n = make_uint2(0, 0);
-        if (has_n) r_n = ld_stream_u2(rec + beg + threadIdx.x);
-        for (uint64_t i0 = beg; i0 < end; i0 += THREADS) {
-          bool has = has_n;
-          const uint2 r = r_n;
-          has_n = i0 + THREADS + threadIdx.x < end;
-          if (has_n) r_n = ld_stream_u2(rec + i0 + THREADS + threadIdx.x);
-          if (n_pass == 1) {
-            if (!t.insert(has, r.x, r.y)) overflow = true;
-          } else {
+      for (int s = 0; s < (run ? 1 : p.n_seg); ++s) {
+        uint64_t beg = 0, end = n;
+        const uint2* rec = run;
+        if (!run) {
+          const uint64_t o0 = p.seg[s].offsets[0];
+          beg = p.seg[s].offsets[b - p.bin_lo] - o0;
+          end = p.seg[s].offsets[b - p.bin_lo + 1] - o0;
+          rec = (const uint2*)p.seg[s].records;
+        }
+        if (n_pass == 1) {
+          // two records per thread and step, the next two in flight while the current ones are inserted
+          auto fetch = [&](uint64_t i0, bool& h0, uint2& q0, bool& h1, uint2& q1) {
+            h0 = i0 + threadIdx.x < end;
+            h1 = i0 + THREADS + threadIdx.x < end;
+            q0 = q1 = make_uint2(0, 0);
+            if (h0) q0 = ld_stream_u2(rec + i0 + threadIdx.x);
+            if (h1) q1 = ld_stream_u2(rec + i0 + THREADS + threadIdx.x);
+          };
+          bool n0, n1;
+          uint2 q0, q1;
+          fetch(beg, n0, q0, n1, q1);
+          for (uint64_t i0 = beg; i0 < end; i0 += 2 * THREADS) {
+            const bool h0 = n0, h1 = n1;
+            const uint2 r0 = q0, r1 = q1;
+            fetch(i0 + 2 * THREADS, n0, q0, n1, q1);
+            if (!t.insert2(h0, r0.x, r0.y, h1, r1.x, r1.y)) overflow = true;
+          }
+        } else {
+          // hash passes: a pass takes 1 / n_pass of the records; compact them per warp so that every insert is 32 wide
+          bool has_n = beg + threadIdx.x < end;
+          uint2 r_n = make_uint2(0, 0);
+          if (has_n) r_n = ld_stream_u2(rec + beg + threadIdx.x);
+          for (uint64_t i0 = beg; i0 < end; i0 += THREADS) {
+            bool has = has_n;
+            const uint2 r = r_n;
+            has_n = i0 + THREADS + threadIdx.x < end;
+            if (has_n) r_n = ld_stream_u2(rec + i0 + THREADS + threadIdx.x);
             has = has && __umulhi(hash32b(r.x), n_pass) == pass;
             const uint32_t m = __ballot_sync(FULL_MASK, has);
             if (has) stage[n_st + __popc(m & lt)] = r;
@@ -643,12 +768,12 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
           __syncwarp();
         }
       }
-      if (threadIdx.x == THREADS - 1) {
-        s_nocc = 0;
-        if (last) s_item = atomicAdd(&p.counters[CUR], 1u);
-      }
+      if (threadIdx.x == THREADS - 1) s_nocc = 0;
       __syncthreads();
     }
+    }
+    if (threadIdx.x == 0) s_first = atomicAdd(&p.counters[CUR], (uint32_t)BATCH);
+    __syncthreads();
   }
   for (int off = 16; off > 0; off >>= 1) {
     st_occ += shfl_u64(st_occ, lane ^ off);
