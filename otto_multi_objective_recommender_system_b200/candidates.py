@@ -206,8 +206,10 @@ def recency_long_predictions(sessions: EventCSR, tables: dict, pred: torch.Tenso
     if pred.shape[0] != 3 or pred.shape[2] != n:
         raise ValueError("pred must be [3, sessions, n] for the targets click, cart, order")
     max_len = max_session_len(sessions)
-    wc, wk, offs = recency_weights(max_len)
-    wc_d, wk_d, off_d = (torch.from_numpy(a).to(dev) for a in (wc, wk, offs))
+    dkey = (max_len, str(dev))
+    if dkey not in _WEIGHT_CACHE:
+        _WEIGHT_CACHE[dkey] = tuple(torch.from_numpy(a).to(dev) for a in recency_weights(max_len))
+    wc_d, wk_d, off_d = _WEIGHT_CACHE[dkey]
     spec = N.OttoRecencySpec()
     spec.n_aids, spec.n = sessions.n_aids, n
     max_k = 1

@@ -596,17 +596,17 @@ __global__ void assemble_kernel(const int32_t* __restrict__ off, const int32_t* 
   for (int tg = 0; tg < n_targets; ++tg) {
     int32_t* out = pred + ((int64_t)tg * S + s) * n;
     int len = 0, uniq = 0;
-    // unique aids, most recent first (the first n are kept, the rest only counted)
-    for (int32_t i = end - 1; i >= beg; --i) {
+    // unique aids, most recent first.  Only the first n matter (and whether there are at least n), so an aid is
+    // checked against the <= n kept so far and the walk stops at n: a 458-event session costs a few hundred
+    // compares instead of 458^2 / 2, which used to stall its whole warp.
+    for (int32_t i = end - 1; i >= beg && len < n; --i) {
       const int32_t a = aid[i];
       bool seen = false;
-      for (int32_t j = end - 1; j > i; --j)
-        if (aid[j] == a) { seen = true; break; }
-      if (!seen) {
-        if (len < n) out[len++] = a;
-        ++uniq;
-      }
+      for (int j = 0; j < len; ++j)
+        if (out[j] == a) { seen = true; break; }
+      if (!seen) out[len++] = a;
     }
+    uniq = len;     // == n means "n or more"
     if (tg == 0 && long_session) long_session[s] = uniq >= n;
     // sorted_aids[:n - len(unique)]: only when the history is shorter than n
     const int32_t* ca = cand_aid + ((int64_t)tg * S + s) * top_n;
