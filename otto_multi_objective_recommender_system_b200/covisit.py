@@ -286,7 +286,9 @@ class CovisitBuilder:
         need = int(self.lib.otto_covisit_reduce_scratch_bytes(C.byref(self.cspec), bin_hi - bin_lo, aid_hi - aid_lo))
         if self.scratch is None or self.scratch.numel() < need:
             self.scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
-        segs = (N.OttoPairSegment * len(segments))(*[N.OttoPairSegment(r.data_ptr(), o.data_ptr()) for r, o in segments])
+        # a segment's records are a tensor, or (device pointer, n_records) for a peer's slab mapped over NVLink
+        ptr = lambda r: r[0] if isinstance(r, tuple) else r.data_ptr()
+        segs = (N.OttoPairSegment * len(segments))(*[N.OttoPairSegment(ptr(r), o.data_ptr()) for r, o in segments])
         tc = table.to_c()
         with torch.cuda.device(self.device):
             N.check(self.lib.otto_covisit_reduce(C.byref(self.cspec), v["bin_base"].data_ptr(), v["bin_x"].data_ptr(),

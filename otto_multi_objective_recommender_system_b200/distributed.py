@@ -27,6 +27,7 @@ import torch
 import torch.distributed as dist
 
 import ctypes as C
+import os
 
 from . import _native as N
 from .covisit import CovisitBuilder, CovisitSpec, EventCSR, TopKTable
@@ -124,7 +125,9 @@ class GpuRankBackend:
         return self.b.scatter()
 
     def reduce(self, segments, bin_lo, bin_hi, aid_lo, aid_hi) -> TopKTable:
-        if len(segments) > 1:    # one run per bin for the reduce kernels
+        # one run per bin for the reduce kernels once a bin is spread over more than two senders (with two the extra
+        # copy of the merge costs more than the second run per bin)
+        if len(segments) >= int(os.environ.get("OTTO_MERGE_MIN_SEGMENTS", "3")):
             segments = [self.b.merge_segments(segments, bin_hi - bin_lo)]
         return self.b.reduce(segments, bin_lo, bin_hi, aid_lo, aid_hi)
 
