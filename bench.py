@@ -465,7 +465,7 @@ def run_b200(args):
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "u32/u64 accumulate, f32 weights", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u32/u64", "data": "synthetic",
             "config": {"workload": workload_name(args), "sessions_rank0": S, "events_rank0": E, "aids": A,
                        "tail_events_rank0": E30, "pairs_rank0": P, "distinct_pairs_rank0": D, "bins": B,
                        "split_rows": stats["split_rows"], "k": K, "events_all_ranks": events_all,
