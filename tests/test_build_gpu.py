@@ -246,3 +246,32 @@ def test_bin_arrays_guard_refuses_more_bins_than_sized(cv):
     b2.stats.bins = 0
     b2.views()["pair_ub"].mul_(1000)
     assert b2.count_finish()["bins"] > csr.n_aids
+
+
+def test_one_shot_c_entry_point_with_workspace_retry(cv):
+    """otto_covisit_build through raw ctypes, the way INTEGRATION.md shows it: a first call with a workspace that is
+    too small answers OTTO_ENOSPC with the pair count filled in, otto_covisit_build_bytes sizes the retry."""
+    import ctypes as C
+    N = cv.N
+    lib = N.lib()
+    frame = synth_frame(3000, 500, seed=7)
+    csr = cv.ingest(frame, "desc", device="cuda:0")
+    spec = cv.CARTS_ORDERS
+    cspec = spec.to_c(csr.n_aids)
+    ev = N.OttoEvents(csr.n_sessions, csr.n_events, csr.offsets.data_ptr(), csr.aid.data_ptr(), csr.ts.data_ptr(), csr.type.data_ptr())
+    sizes = N.OttoBuildSizes()
+    N.check(lib.otto_covisit_sizes(csr.n_sessions, csr.n_events, C.byref(cspec), C.byref(sizes)))
+    table = cv.TopKTable.empty(csr.n_aids, spec.k, "cuda:0")
+    tc = table.to_c()
+    stats = N.OttoBuildStats()
+    st = torch.cuda.current_stream().cuda_stream
+    ws = torch.empty(sizes.workspace_bytes, dtype=torch.uint8, device="cuda:0")
+    rc = lib.otto_covisit_build(C.byref(ev), C.byref(cspec), ws.data_ptr(), ws.numel(), C.byref(tc), C.byref(stats), st)
+    assert rc == N.OTTO_ENOSPC and stats.pairs > 0 and b"workspace too small" in lib.otto_last_error()
+    need = lib.otto_covisit_build_bytes(csr.n_sessions, csr.n_events, C.byref(cspec), stats.pairs, stats.bins)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda:0")
+    N.check(lib.otto_covisit_build(C.byref(ev), C.byref(cspec), ws.data_ptr(), ws.numel(), C.byref(tc), C.byref(stats), st))
+    torch.cuda.synchronize()
+    want = co.build(frame.to_pandas(), H.oracle_spec(spec))
+    H.assert_int_table_equal(table.to_pandas(), want, "one-shot build")
+    assert stats.distinct > 0 and stats.table_overflow == 0 and sum(stats.tier_records) == stats.pairs
