@@ -41,6 +41,7 @@ struct RecencyParams {
   uint64_t* slab;
   int64_t slab_words;
   int32_t lcap, hs;           // events capacity, hash slots (power of two)
+  int32_t max_k;              // largest table_k among the present tables
 };
 
 struct RecWork {
@@ -94,8 +95,6 @@ __global__ void __launch_bounds__(256) recency_long_kernel(const RecencyParams p
   w.sidx = (int32_t*)(w.first + hs);
   w.occ = (uint32_t*)(w.sidx + hs);
   w.pos = w.occ + hs;
-  const uint32_t hmask = (uint32_t)(hs - 1);
-  const int hshift = 32 - (63 - __clzll((long long)hs));
 
   // the slab is sized for the longest session (tens of thousands of slots): clear it once, afterwards only the
   // claimed slots are reset (a full reset per session and target wrote 40 GB for 27 k sessions)
@@ -112,6 +111,12 @@ __global__ void __launch_bounds__(256) recency_long_kernel(const RecencyParams p
     const int L = end - beg;
     const double* wc = p.w_click + p.w_offset[L];
     const double* wk = p.w_cart + p.w_offset[L];
+    // this session's share of the table: the slab is sized for the longest session, but a typical long session has
+    // ~50 events, and 4 k slots stay in L2 where 32 k slots per block (1.3 GB over all blocks) went to DRAM
+    int64_t hs_s = 64;
+    while (hs_s < 2 * (int64_t)L * (1 + p.max_k) && hs_s < hs) hs_s <<= 1;
+    const uint32_t hmask = (uint32_t)(hs_s - 1);
+    const int hshift = 32 - (63 - __clzll((long long)hs_s));
     // unique aids in FILE order of first occurrence (Counter insertion order) + type masks
     if (tid == 0) s_U = 0;
     __syncthreads();
@@ -310,6 +315,7 @@ extern "C" int otto_recency_long(const OttoSessions* sessions, const int32_t* se
   recency_caps(max_session_len, max_k, &lcap, &hs);
   p.lcap = (int32_t)lcap;
   p.hs = (int32_t)hs;
+  p.max_k = max_k;
   p.slab = (uint64_t*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
   p.slab_words = recency_slab_words(lcap, hs);
   const int blocks = n_list < RECENCY_BLOCKS ? n_list : RECENCY_BLOCKS;
