@@ -46,6 +46,7 @@ struct PairGenParams {
   int32_t weight_mode;
   int32_t ts_min;
   uint32_t type_weight[3];
+  int32_t scatter_part;       // pass 2: 0 = everything, 1 = ordinary rows only, 2 = split (hot) rows only
 };
 
 constexpr int PAIRGEN_WARPS = 8;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairG
       const uint32_t cnt = __popc(mywm);
       const bool split_row = active && nbx > 1;
       uint32_t slot = 0;
-      if (active && cnt && nbx == 1) slot = atomicAdd(&p.cursor[bb0], cnt);
+      if (p.scatter_part != 2 && active && cnt && nbx == 1) slot = atomicAdd(&p.cursor[bb0], cnt);
       uint32_t v = 1;
       if (p.weight_mode == OTTO_WEIGHT_TYPE) v = ty == 0 ? p.type_weight[0] : (ty == 1 ? p.type_weight[1] : p.type_weight[2]);
       const bool time_mode = p.weight_mode == OTTO_WEIGHT_TIME;
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairG
       // column view (lane j walks the split rows it won) with the atomics of a chunk issued back to back
       // and the stores behind them, so that one round trip covers SPLIT_CHUNK pairs (a row loop with the
       // atomic inside serialised one round trip per row: profiles/r01_pairgen_v4).
-      const uint32_t spl = __ballot_sync(FULL_MASK, split_row && cnt);
+      const uint32_t spl = p.scatter_part == 1 ? 0u : __ballot_sync(FULL_MASK, split_row && cnt);
       if (spl) {
         constexpr int SPLIT_CHUNK = 4;
         uint32_t rem = warp_transpose32(mywm) & spl;
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairG
       }
       // ordinary rows: row i's winners write one contiguous run
       const uint32_t wm_run = split_row ? 0u : mywm;
+      if (p.scatter_part == 2) continue;
       for (int i = 0; i < maxn; ++i) {
         const int src = (active && i < n) ? base + i : (int)lane;   // own row mask never holds the own lane
         const uint32_t wmi = __shfl_sync(FULL_MASK, wm_run, src);
