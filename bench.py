@@ -303,9 +303,10 @@ def run_b200(args):
     E30, P, B, D = stats["tail_events"], stats["pairs"], stats["bins"], stats["distinct"]
     K = spec.k
     alg = {
-        "count_begin": 4 * (S + 1) + 9 * E30 + 4 * (S + 1) + 8 * E30,     # read offsets + tail events, write tail CSR
-        "count_finish": 4 * (S + 1) + 8 * E30 + 4 * E30,                  # read tail CSR, write winner masks
-        "scatter": 4 * (S + 1) + 12 * E30 + 8 * P,                        # read tail CSR + masks, write records
+        # tail CSR (read offsets + tail events, write 8 B / tail event) + dedupe pass (read tail CSR, write row masks)
+        "count_begin": 4 * (S + 1) + 9 * E30 + 4 * (S + 1) + 8 * E30 + 4 * (S + 1) + 8 * E30 + 4 * E30,
+        "count_finish": 3 * 4 * A + 8 * A,                                # bins, offsets, cursors from the row counts
+        "scatter": 4 * (S + 1) + 12 * E30 + 8 * P,                        # read tail CSR + masks, write records (staging of hot rows not counted)
         "reduce": 8 * P + 8 * (B + 1) + 8 * A * K + 4 * A,                # read records + offsets, write table
     }
     kernel_of = {"count_begin": "tail_copy_kernel", "count_finish": "pairgen_kernel<count>",
@@ -330,9 +331,8 @@ def run_b200(args):
         red_ms = [statistics.mean(r[i] for r in reduce_ms) for i in range(5)] if reduce_ms else [0.0] * 5
         tr = stats.get("tier_records", [0, 0, 0, 0])
         kernels = {
-            "tail_copy_all_kernel": (phase_ms["count_begin"], alg["count_begin"]),
-            "pairgen_kernel<count>": (phase_ms["count_finish"], alg["count_finish"]),
-            "pairgen_kernel<scatter>": (phase_ms["scatter"], alg["scatter"]),
+            "tail_copy + pairgen_kernel<count>": (phase_ms["count_begin"], alg["count_begin"]),
+            "pairgen_kernel<scatter> + partition_kernel x2": (phase_ms["scatter"], alg["scatter"]),
         }
         for i in range(4):       # a tier reads its records once and writes the rows of its bins
             n_rec = tr[tier_of[i]]

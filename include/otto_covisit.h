@@ -71,7 +71,7 @@ typedef struct {
   int32_t k;                 /* rows kept per aid_x (15 / 20) */
   int32_t ts_min;            /* OTTO_WEIGHT_TIME constants: 1659304800, 1662328791 */
   int32_t ts_max;
-  int32_t split_ub;          /* rows whose pair upper bound exceeds this are split into y-hash sub-bins; 0 = default */
+  int32_t split_ub;          /* rows with more pairs than this are split into aid_y-hash sub-bins of ~split_ub / 2; 0 = default */
   int64_t global_events;     /* multi-GPU: events of ALL ranks (bins are formed from the all-reduced bounds, so the
                                 bin arrays must be sized for the global frame); 0 = this rank's frame is the whole frame */
 } OttoCovisitSpec;
@@ -93,6 +93,8 @@ typedef struct {
   int64_t pair_checksum;     /* sum of counts over all accumulated entries (== pairs received) */
   int64_t table_overflow;    /* != 0: a hash table overflowed (result invalid) */
   int64_t tier_records[4];   /* records accumulated by the warp / 128- / 256- / 512-thread reduce kernels */
+  int64_t hot_pairs;         /* pairs of hot (split) rows: they pass through a staging area behind the P final records,
+                                so the record buffer must hold pairs + hot_pairs records */
 } OttoBuildStats;
 
 /* Pair records of one producer for a contiguous range of bins (multi-GPU: one segment per sender). */
@@ -143,11 +145,13 @@ int otto_ingest_desc(const int32_t* session_offsets, int64_t n_sessions, const i
 /* ---- build (the missing builder) ----
  *
  * Phases (all on one stream, one rank):
- *   count_begin   tail CSR (steps 1-3) + per-aid pair upper bounds
- *   [multi-GPU: all-reduce the upper bounds so that every rank forms identical bins]
- *   count_finish  bins, in-session dedupe (steps 4-5, winner masks), exact per-bin pair counts + scan
- *   scatter       8-byte pair records {aid_y, v} grouped by bin (step 6 in integer form)
- *   [multi-GPU: all-to-all of the per-owner bin ranges]
+ *   count_begin   tail CSR (steps 1-3), in-session dedupe (steps 4-5, row masks), pairs per aid_x row
+ *   [multi-GPU: all-reduce the row totals so that every rank forms identical bins]
+ *   count_finish  bins (a row whose total exceeds split_ub is split into aid_y-hash sub-bins), record offsets
+ *   scatter       8-byte pair records {aid_y, v} (step 6 in integer form): ordinary rows at their final position,
+ *                 hot rows into a staging area and from there, partitioned by aid_y hash, into their sub-bins;
+ *                 bin_offsets are valid after this phase
+ *   [multi-GPU: owners read the per-owner bin ranges of every rank (otto_covisit_merge_segments)]
  *   reduce        accumulate per (aid_x, aid_y) + top-k per aid_x (steps 7-8) -> OttoTopK
  * otto_covisit_build runs all of them for one GPU. */
 
@@ -155,7 +159,7 @@ int otto_covisit_sizes(int64_t n_sessions, int64_t n_events, const OttoCovisitSp
 
 int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
                              int64_t workspace_bytes, void* stream);
-/* Fills stats_host->{tail_events,pairs,bins,split_rows}; synchronises when stats_host != NULL. */
+/* Fills stats_host->{tail_events,pairs,bins,split_rows,hot_pairs}; synchronises. */
 int otto_covisit_count_finish(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
                               int64_t workspace_bytes, OttoBuildStats* stats_host, void* stream);
 /* count_begin + count_finish */
@@ -163,14 +167,15 @@ int otto_covisit_count(const OttoEvents* ev, const OttoCovisitSpec* spec, void* 
                        OttoBuildStats* stats_host, void* stream);
 
 /* Device views into the workspace (valid after the phase that writes them):
- *   pair_ub     uint32 [n_aids]      after count_begin (all-reduce target for multi-GPU)
+ *   row_total   uint32 [n_aids]      pairs per aid_x row, after count_begin (all-reduce target for multi-GPU)
  *   bin_base    uint32 [n_aids + 1]  first bin of each aid_x row, after count_finish
- *   bin_x       uint32 [bins]        bin -> aid_x
- *   bin_offsets uint64 [bins + 1]    record offsets of this rank's bins */
+ *   bin_x       uint32 [bins]        bin -> aid_x, after count_finish
+ *   bin_offsets uint64 [bins + 1]    record offsets of this rank's bins, after scatter */
 int otto_covisit_views(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
-                       uint64_t** bin_offsets, uint32_t** bin_base, uint32_t** bin_x, uint32_t** pair_ub);
+                       uint64_t** bin_offsets, uint32_t** bin_base, uint32_t** bin_x, uint32_t** row_total);
 
-/* Writes the pair records, grouped by bin, into `records` (>= stats.pairs * 8 bytes). */
+/* Writes the pair records, grouped by bin, into `records`: capacity >= (stats.pairs + stats.hot_pairs) records of
+ * 8 bytes; the first stats.pairs of them are the result, the rest is the staging area of the hot rows. */
 int otto_covisit_scatter(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
                          void* records, int64_t records_capacity, void* stream);
 
@@ -207,7 +212,7 @@ int otto_peer_close(void* ptr);
 
 /* One-shot single-GPU build; the pair records and the reduce scratch are carved from the workspace after
  * the fixed part.  Returns OTTO_ENOSPC (stats_host->pairs / bins set) when the workspace cannot hold
- * them; otto_covisit_build_bytes gives the size to retry with. */
+ * them; otto_covisit_build_bytes (pairs = stats.pairs + stats.hot_pairs) gives the size to retry with. */
 int otto_covisit_build(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
                        const OttoTopK* out, OttoBuildStats* stats_host, void* stream);
 int64_t otto_covisit_build_bytes(int64_t n_sessions, int64_t n_events, const OttoCovisitSpec* spec, int64_t pairs,

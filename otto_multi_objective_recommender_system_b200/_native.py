@@ -39,7 +39,7 @@ class OttoBuildSizes(C.Structure):
 
 class OttoBuildStats(C.Structure):
     _fields_ = [("tail_events", i64), ("pairs", i64), ("bins", i64), ("split_rows", i64), ("distinct", i64),
-                ("pair_checksum", i64), ("table_overflow", i64), ("tier_records", i64 * 4)]
+                ("pair_checksum", i64), ("table_overflow", i64), ("tier_records", i64 * 4), ("hot_pairs", i64)]
 
     def as_dict(self) -> dict:
         d = {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "tier_records"}

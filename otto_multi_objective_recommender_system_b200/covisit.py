@@ -259,10 +259,12 @@ class CovisitBuilder:
             off = ptr.value - base
             return self.workspace[off: off + n * torch.empty(0, dtype=dtype).element_size()].view(dtype)
         return {"bin_offsets": view(ptrs[0], torch.int64, B + 1), "bin_base": view(ptrs[1], torch.int32, A + 1),
-                "bin_x": view(ptrs[2], torch.int32, max(B, 1)), "pair_ub": view(ptrs[3], torch.int32, A)}
+                "bin_x": view(ptrs[2], torch.int32, max(B, 1)), "row_total": view(ptrs[3], torch.int32, A)}
 
     def scatter(self) -> torch.Tensor:
-        P = int(self.stats.pairs)
+        """Records grouped by bin; bin offsets (views()["bin_offsets"]) are valid afterwards.  The buffer holds the
+        P final records followed by the staging area of the hot rows."""
+        P = int(self.stats.pairs) + int(self.stats.hot_pairs)
         if self.records is None or self.records.numel() < max(P, 1):
             self.records = torch.empty(max(P, 1), dtype=torch.int64, device=self.device)   # 8-byte {aid_y, v}
         with torch.cuda.device(self.device):

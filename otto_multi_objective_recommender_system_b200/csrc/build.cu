@@ -82,11 +82,17 @@ extern "C" int otto_ingest_desc(const int32_t* session_offsets, int64_t n_sessio
 // ------------------------------------------------------------------ workspace layout
 
 struct Layout {
-  int64_t S, E, Ecap, A, Bmax;
-  int64_t tail_off, tail_aw, tail_ts, winmask, pair_ub, bin_base, bin_x, hist, bin_off, cursor, scan, stats, total;
+  int64_t S, E, Ecap, A, Bmax, Hmax;
+  int64_t tail_off, tail_aw, tail_ts, winmask, row_count, row_total, bin_base, bin_x, bin_cnt, bin_off, row_off, hot_off, cursor,
+      hot_rows, scan, stats, total;
 };
 
+// A row whose pair count (over all ranks) exceeds split_ub is "hot": it is split into aid_y-hash sub-bins of
+// about split_ub / 4 records (2048 by default), which the 256-thread reduce kernel - the most efficient tier -
+// takes in one pass; sub-bins of ~4096 records all landed in the 512-thread kernel and doubled its time.
 static int32_t effective_split_ub(const OttoCovisitSpec* spec) { return spec->split_ub > 0 ? spec->split_ub : 8192; }
+static int32_t sub_bin_target(const OttoCovisitSpec* spec) { return effective_split_ub(spec) >= 4 ? effective_split_ub(spec) / 4 : 1; }
+constexpr uint32_t MAX_SUB_BINS = 4096;   // shared-memory cursors of the partition kernels
 
 static int check_spec(const OttoCovisitSpec* spec) {
   if (!spec) { otto_set_error("spec is NULL"); return OTTO_EINVAL; }
@@ -115,24 +121,31 @@ static Layout make_layout(int64_t S, int64_t E, const OttoCovisitSpec* spec) {
   L.A = spec->n_aids;
   L.Ecap = E < S * spec->tail_n ? E : S * spec->tail_n;
   if (L.Ecap < 1) L.Ecap = 1;
-  // extra bins = sum over rows of (ceil(ub / split_ub) - 1) <= (sum of ub) / split_ub <= events * (tail_n - 1) / split_ub,
-  // with the events of every rank when the bounds are all-reduced (multi-GPU)
+  // extra bins = sum over hot rows of (sub-bins - 1) <= (pairs of all ranks) / target <= events * (tail_n - 1) / target,
+  // with the events of every rank when the row counts are all-reduced (multi-GPU); hot rows <= extra bins
   const int64_t Eg = spec->global_events > E ? spec->global_events : L.Ecap;
-  L.Bmax = L.A + (Eg * (spec->tail_n - 1)) / effective_split_ub(spec) + 1;
+  L.Hmax = (Eg * (spec->tail_n - 1)) / sub_bin_target(spec) + 1;
+  if (L.Hmax > L.A) L.Hmax = L.A + 1;
+  L.Bmax = L.A + (Eg * (spec->tail_n - 1)) / sub_bin_target(spec) + 1;
   int64_t o = 0;
   auto take = [&](int64_t bytes) { int64_t at = o; o = align_up(o + bytes, 256); return at; };
   L.tail_off = take((S + 2) * 4);
   L.tail_aw = take(L.Ecap * 4);
   L.tail_ts = take(L.Ecap * 4);
   L.winmask = take(L.Ecap * 4);
-  L.pair_ub = take((L.A + 1) * 4);
+  L.row_count = take((L.A + 1) * 4);
+  L.row_total = take((L.A + 1) * 4);
   L.bin_base = take((L.A + 2) * 4);
   L.bin_x = take(L.Bmax * 4);
-  L.hist = take((L.Bmax + 1) * 4);
+  L.bin_cnt = take((L.Bmax + 1) * 4);
   L.bin_off = take((L.Bmax + 2) * 8);
-  L.cursor = take((L.Bmax + 1) * 8);
+  L.row_off = take((L.A + 2) * 8);
+  L.hot_off = take((L.A + 2) * 8);
+  L.cursor = take((L.A + 1) * 4);
+  L.hot_rows = take((L.Hmax + 1) * 4);
   int64_t scan_elems = scan_scratch_elems(S + 1);
   if (scan_scratch_elems(L.Bmax + 1) > scan_elems) scan_elems = scan_scratch_elems(L.Bmax + 1);
+  if (scan_scratch_elems(L.A + 1) > scan_elems) scan_elems = scan_scratch_elems(L.A + 1);
   L.scan = take(scan_elems * 8);
   L.stats = take(256);
   L.total = o;
@@ -179,7 +192,7 @@ __global__ void tail_count_kernel(const int32_t* __restrict__ off, const uint8_t
 __global__ void __launch_bounds__(256)
     tail_copy_filtered_kernel(const int32_t* __restrict__ off, const int32_t* __restrict__ aid, const int32_t* __restrict__ ts,
                               const uint8_t* __restrict__ type, int64_t S, uint32_t mask, const uint32_t* __restrict__ tail_off,
-                              uint32_t* __restrict__ tail_aw, int32_t* __restrict__ tail_ts, uint32_t* __restrict__ pair_ub) {
+                              uint32_t* __restrict__ tail_aw, int32_t* __restrict__ tail_ts) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
   const uint32_t tb = tail_off[s];
@@ -193,7 +206,6 @@ __global__ void __launch_bounds__(256)
       const int32_t a = aid[p];
       tail_aw[tb + taken] = (uint32_t)a | (ty << 30);
       tail_ts[tb + taken] = ts[p];
-      if (n > 1) atomicAdd(&pair_ub[a], n - 1);
       ++taken;
     }
   }
@@ -207,7 +219,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     tail_copy_all_kernel(const int32_t* __restrict__ off, const int32_t* __restrict__ aid, const int32_t* __restrict__ ts,
                          const uint8_t* __restrict__ type, int64_t S, const uint32_t* __restrict__ tail_off,
-                         uint32_t* __restrict__ tail_aw, int32_t* __restrict__ tail_ts, uint32_t* __restrict__ pair_ub) {
+                         uint32_t* __restrict__ tail_aw, int32_t* __restrict__ tail_ts) {
   const int64_t s0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
   if (s0 >= S) return;
   const int lane = (int)lane_id();
@@ -227,26 +239,37 @@ __global__ void __launch_bounds__(256)
       if (c < ns && tc - T0 <= q) u = c;
     }
     const uint32_t tu = __shfl_sync(FULL_MASK, to, u);
-    const uint32_t n = __shfl_sync(FULL_MASK, to_next, u) - tu;
     const int32_t src = __shfl_sync(FULL_MASK, src0, u) + (int32_t)(q - (tu - T0));
     if (q < total) {
-      const int32_t a = aid[src];
-      tail_aw[T0 + q] = (uint32_t)a | ((uint32_t)type[src] << 30);
+      tail_aw[T0 + q] = (uint32_t)aid[src] | ((uint32_t)type[src] << 30);
       tail_ts[T0 + q] = ts[src];
-      if (n > 1) atomicAdd(&pair_ub[a], n - 1);
     }
   }
 }
 
-// sub-bins per aid_x row: ceil(ub / split_ub), at least 1
-__global__ void bins_count_kernel(const uint32_t* __restrict__ pair_ub, int64_t A, uint32_t split_ub,
-                                  uint32_t* __restrict__ nb, unsigned long long* stats) {
+// Bins of a row: 1, or ceil(total / target) aid_y-hash sub-bins when the row is hot (total over ALL ranks above
+// split_ub).  Hot rows are also listed (any order) for the partition kernels; hot_cnt = the rank's own pairs of a
+// hot row (its share of the staging area), 0 for ordinary rows.
+__global__ void bins_count_kernel(const uint32_t* __restrict__ row_total, const uint32_t* __restrict__ row_count, int64_t A,
+                                  uint32_t split_ub, uint32_t target, uint32_t* __restrict__ nb,
+                                  unsigned long long* __restrict__ hot_cnt, uint32_t* __restrict__ hot_rows, int64_t hot_cap,
+                                  unsigned long long* stats) {
   const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= A) return;
-  const uint32_t ub = pair_ub[x];
-  const uint32_t n = ub <= split_ub ? 1u : (ub + split_ub - 1) / split_ub;
+  const uint32_t tot = row_total[x];
+  uint32_t n = 1;
+  unsigned long long hc = 0;
+  if (tot > split_ub) {
+    n = (tot + target - 1) / target;
+    if (n > MAX_SUB_BINS) n = MAX_SUB_BINS;
+    if (n > 1) {
+      hc = row_count[x];
+      const unsigned long long at = atomicAdd(&stats[3], 1ull);
+      if ((int64_t)at < hot_cap) hot_rows[at] = (uint32_t)x;
+    }
+  }
   nb[x] = n;
-  if (n > 1) atomicAdd(&stats[3], 1ull);
+  hot_cnt[x] = hc;
 }
 
 __global__ void bins_fill_kernel(const uint32_t* __restrict__ bin_base, int64_t A, uint32_t* __restrict__ bin_x) {
@@ -255,25 +278,171 @@ __global__ void bins_fill_kernel(const uint32_t* __restrict__ bin_base, int64_t 
   for (uint32_t b = bin_base[x]; b < bin_base[x + 1]; ++b) bin_x[b] = (uint32_t)x;
 }
 
-// record positions fit 32 bits (otto_covisit_scatter rejects P >= 2^32)
-__global__ void init_cursor_kernel(const unsigned long long* __restrict__ bin_off, const uint32_t* __restrict__ bin_base,
-                                   int64_t A, uint32_t* __restrict__ cursor) {
-  const int64_t B = bin_base[A];
-  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x)
-    cursor[b] = (uint32_t)bin_off[b];
+// scatter cursor of a row: its final position for an ordinary row, its slice of the staging area (behind the
+// P final records) for a hot row
+__global__ void init_cursor_kernel(const unsigned long long* __restrict__ row_off, const unsigned long long* __restrict__ hot_off,
+                                   const uint32_t* __restrict__ bin_base, int64_t A, uint32_t* __restrict__ cursor) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= A) return;
+  const bool hot = bin_base[x + 1] - bin_base[x] > 1;
+  cursor[x] = hot ? (uint32_t)(row_off[A] + hot_off[x]) : (uint32_t)row_off[x];
 }
 
-// stats[0] tail events, [1] pairs, [2] bins ([3] split rows is counted by bins_count_kernel)
+// stats[0] tail events, [1] pairs, [2] bins, [3] hot rows (counted by bins_count_kernel), [4] staged (hot) pairs
 __global__ void count_stats_kernel(const uint32_t* tail_off, int64_t S, const uint32_t* bin_base, int64_t A,
-                                   const unsigned long long* bin_off, unsigned long long* stats) {
-  const uint32_t B = bin_base[A];
+                                   const unsigned long long* row_off, const unsigned long long* hot_off,
+                                   unsigned long long* stats) {
   stats[0] = tail_off[S];
-  stats[1] = bin_off[B];
-  stats[2] = B;
+  stats[1] = row_off[A];
+  stats[2] = bin_base[A];
+  stats[4] = hot_off[A];
 }
 
-// scan over a device-resident length: hist[0..B) with B = bin_base[A] only known on the device.  We scan the
-// full Bmax-sized array instead (entries >= B are zero), which keeps the host out of the loop.
+// records per bin of the ordinary rows (the sub-bins of hot rows are counted by partition_count_kernel)
+__global__ void bin_cnt_rows_kernel(const uint32_t* __restrict__ row_count, const uint32_t* __restrict__ bin_base, int64_t A,
+                                    uint32_t* __restrict__ bin_cnt) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= A) return;
+  const uint32_t b0 = bin_base[x];
+  if (bin_base[x + 1] - b0 == 1) bin_cnt[b0] = row_count[x];
+}
+
+// ---- hot rows: staging area -> aid_y-hash sub-bins.  One CTA owns a hot row, so the sub-bin cursors live in
+// shared memory (no global atomic on the path), and the few hundred open write lines of a CTA stay in L2 until
+// they are complete.  Pass 1 counts, an exclusive scan over all bins gives the final offsets, pass 2 moves.
+constexpr int PART_THREADS = 512;
+
+struct PartParams {
+  const uint32_t* hot_rows;
+  const unsigned long long* n_hot;     // stats[3]
+  int64_t hot_cap;
+  const uint32_t* bin_base;
+  const uint32_t* row_count;
+  const unsigned long long* row_off;   // row_off[A] = P: start of the staging area
+  const unsigned long long* hot_off;
+  int64_t A;
+  uint32_t* bin_cnt;
+  const unsigned long long* bin_off;
+  uint2* records;
+};
+
+// pass 1: records per sub-bin
+__global__ void __launch_bounds__(PART_THREADS) partition_count_kernel(const PartParams p) {
+  __shared__ uint32_t s_cnt[MAX_SUB_BINS];
+  unsigned long long n_hot = *p.n_hot;
+  if ((int64_t)n_hot > p.hot_cap) n_hot = (unsigned long long)p.hot_cap;
+  const uint2* stage = p.records + p.row_off[p.A];
+  for (unsigned long long i = blockIdx.x; i < n_hot; i += gridDim.x) {
+    const uint32_t x = p.hot_rows[i];
+    const uint32_t b0 = p.bin_base[x], nb = p.bin_base[x + 1] - b0;
+    const uint32_t n = p.row_count[x];
+    const uint2* src = stage + p.hot_off[x];
+    for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS) s_cnt[j] = 0u;
+    __syncthreads();
+    // four loads in flight per thread: the loop is otherwise one dependent chain load -> atomic
+    for (uint32_t j0 = 0; j0 < n; j0 += 4 * PART_THREADS) {
+      uint2 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t j = j0 + u * PART_THREADS + threadIdx.x;
+        r[u] = j < n ? ld_stream_u2(src + j) : make_uint2(0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u * PART_THREADS + threadIdx.x < n) atomicAdd(&s_cnt[sub_bin(r[u].x, nb)], 1u);
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS) p.bin_cnt[b0 + j] = s_cnt[j];
+    __syncthreads();
+  }
+}
+
+// pass 2: move.  A tile of PART_TILE records is grouped by sub-bin in shared memory first, so that consecutive
+// threads write consecutive records of one sub-bin (one lone 8-byte store per record ran at 2.5 ms for 2.4 GB).
+// Two instantiations: rows with up to 512 sub-bins (nearly all; 52 KB of shared memory, four CTAs per SM) and
+// the few hottest rows (up to MAX_SUB_BINS sub-bins).
+constexpr int PART_TILE = 4096;
+constexpr int PART_PER_THREAD = PART_TILE / PART_THREADS;
+constexpr uint32_t PART_NB_SMALL = 512;
+template <uint32_t NBCAP>
+constexpr size_t part_move_smem() { return (size_t)NBCAP * 4 * 2 + (size_t)PART_TILE * 12; }
+
+template <uint32_t NBCAP>
+__global__ void __launch_bounds__(PART_THREADS) partition_move_kernel(const PartParams p) {
+  extern __shared__ __align__(16) unsigned char part_smem[];
+  uint2* s_rec = (uint2*)part_smem;                              // [PART_TILE] records grouped by sub-bin
+  uint32_t* s_dst = (uint32_t*)(s_rec + PART_TILE);              // [PART_TILE] their final positions
+  uint32_t* s_cur = s_dst + PART_TILE;                           // [nb] next free position of every sub-bin
+  uint32_t* s_hist = s_cur + NBCAP;                              // [nb] tile histogram -> tile offsets
+  __shared__ uint32_t s_warp[PART_THREADS / 32];
+  unsigned long long n_hot = *p.n_hot;
+  if ((int64_t)n_hot > p.hot_cap) n_hot = (unsigned long long)p.hot_cap;
+  const uint2* stage = p.records + p.row_off[p.A];
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  for (unsigned long long i = blockIdx.x; i < n_hot; i += gridDim.x) {
+    const uint32_t x = p.hot_rows[i];
+    const uint32_t b0 = p.bin_base[x], nb = p.bin_base[x + 1] - b0;
+    if ((nb <= PART_NB_SMALL) != (NBCAP == PART_NB_SMALL)) continue;     // the other instantiation's row
+    const uint32_t n = p.row_count[x];
+    const uint2* src = stage + p.hot_off[x];
+    for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS) s_cur[j] = (uint32_t)p.bin_off[b0 + j];
+    for (uint32_t t0 = 0; t0 < n; t0 += PART_TILE) {
+      for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS) s_hist[j] = 0u;
+      __syncthreads();
+      uint2 r[PART_PER_THREAD];
+      uint32_t sub[PART_PER_THREAD], rank[PART_PER_THREAD];
+#pragma unroll
+      for (int u = 0; u < PART_PER_THREAD; ++u) {
+        const uint32_t j = t0 + u * PART_THREADS + threadIdx.x;
+        r[u] = j < n ? ld_stream_u2(src + j) : make_uint2(0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < PART_PER_THREAD; ++u) {
+        sub[u] = sub_bin(r[u].x, nb);
+        rank[u] = t0 + u * PART_THREADS + threadIdx.x < n ? atomicAdd(&s_hist[sub[u]], 1u) : 0u;
+      }
+      __syncthreads();
+      // exclusive scan of the tile histogram (nb <= MAX_SUB_BINS): thread-local chunk, warp scan, block scan
+      {
+        const uint32_t per = (nb + PART_THREADS - 1) / PART_THREADS;
+        const uint32_t lo = threadIdx.x * per, hi = min(nb, lo + per);
+        uint32_t tot = 0;
+        for (uint32_t j = lo; j < hi; ++j) tot += s_hist[j];
+        uint32_t inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(FULL_MASK, inc, o);
+          if (lane >= (uint32_t)o) inc += v;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (uint32_t w = 0; w < warp; ++w) wbase += s_warp[w];
+        uint32_t ex = wbase + inc - tot;
+        for (uint32_t j = lo; j < hi; ++j) {
+          const uint32_t c = s_hist[j];
+          s_hist[j] = ex;
+          ex += c;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < PART_PER_THREAD; ++u) {
+        if (t0 + u * PART_THREADS + threadIdx.x < n) {
+          const uint32_t at = s_hist[sub[u]] + rank[u];
+          s_rec[at] = r[u];
+          s_dst[at] = s_cur[sub[u]] + rank[u];
+        }
+      }
+      __syncthreads();
+      const uint32_t m = min((uint32_t)PART_TILE, n - t0);
+      // advance the cursors by the tile's counts: count of sub-bin j = next offset - own offset
+      for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS) s_cur[j] += (j + 1 < nb ? s_hist[j + 1] : m) - s_hist[j];
+      for (uint32_t j = threadIdx.x; j < m; j += PART_THREADS) st_stream_u2(p.records + s_dst[j], s_rec[j]);
+      __syncthreads();
+    }
+  }
+}
 
 #define WS(type, field) ((type*)((char*)workspace + L.field))
 
@@ -286,6 +455,26 @@ static int check_ws(const Layout& L, void* workspace, int64_t workspace_bytes) {
   return OTTO_OK;
 }
 
+static PairGenParams make_pairgen(const Layout& L, const OttoCovisitSpec* spec, void* workspace) {
+  PairGenParams p;
+  p.tail_off = WS(uint32_t, tail_off);
+  p.tail_aw = WS(uint32_t, tail_aw);
+  p.tail_ts = WS(int32_t, tail_ts);
+  p.winmask = WS(uint32_t, winmask);
+  p.row_hist = WS(uint32_t, row_count);
+  p.cursor = WS(uint32_t, cursor);
+  p.records = nullptr;
+  p.n_sessions = L.S;
+  p.window = (uint32_t)spec->window_s;
+  p.x_type_mask = spec->x_type_mask;
+  p.y_type_mask = spec->y_type_mask;
+  p.weight_mode = spec->weight_mode;
+  p.ts_min = spec->ts_min;
+  for (int i = 0; i < 3; ++i) p.type_weight[i] = (uint32_t)spec->type_weight[i];
+  return p;
+}
+
+// tail CSR (steps 1-3) + in-session dedupe (steps 4-5: row masks) + pairs per aid_x row
 extern "C" int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
                                         int64_t workspace_bytes, void* stream) {
   int rc = check_spec(spec);
@@ -295,7 +484,7 @@ extern "C" int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitS
   if ((rc = check_ws(L, workspace, workspace_bytes))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t S = L.S;
-  CUDA_TRY(cudaMemsetAsync(WS(uint32_t, pair_ub), 0, (L.A + 1) * 4, st));
+  CUDA_TRY(cudaMemsetAsync(WS(uint32_t, row_count), 0, (L.A + 1) * 4, st));
   CUDA_TRY(cudaMemsetAsync(WS(char, stats), 0, 256, st));
   CUDA_TRY(cudaMemsetAsync(WS(uint32_t, tail_off), 0, (S + 2) * 4, st));
   if (S > 0) {
@@ -309,39 +498,26 @@ extern "C" int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitS
   if (S > 0 && (spec->event_type_mask & 7u) == 7u) {
     tail_copy_all_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(ev->session_offsets, ev->aid, ev->ts, ev->type, S,
                                                                      WS(uint32_t, tail_off), WS(uint32_t, tail_aw),
-                                                                     WS(int32_t, tail_ts), WS(uint32_t, pair_ub));
+                                                                     WS(int32_t, tail_ts));
     LAUNCH_CHECK();
   } else if (S > 0) {
     tail_copy_filtered_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(ev->session_offsets, ev->aid, ev->ts, ev->type, S,
                                                                           spec->event_type_mask, WS(uint32_t, tail_off),
-                                                                          WS(uint32_t, tail_aw), WS(int32_t, tail_ts),
-                                                                          WS(uint32_t, pair_ub));
+                                                                          WS(uint32_t, tail_aw), WS(int32_t, tail_ts));
     LAUNCH_CHECK();
   }
+  if (S > 0) {
+    PairGenParams p = make_pairgen(L, spec, workspace);
+    const int64_t warps = ceil_div(S, 32);
+    pairgen_kernel<false><<<(unsigned)ceil_div(warps, PAIRGEN_WARPS), PAIRGEN_WARPS * 32, 0, st>>>(p);
+    LAUNCH_CHECK();
+  }
+  // the copy that a multi-GPU host all-reduces; the rank's own counts stay in row_count
+  CUDA_TRY(cudaMemcpyAsync(WS(uint32_t, row_total), WS(uint32_t, row_count), (L.A + 1) * 4, cudaMemcpyDeviceToDevice, st));
   return OTTO_OK;
 }
 
-static PairGenParams make_pairgen(const Layout& L, const OttoCovisitSpec* spec, void* workspace) {
-  PairGenParams p;
-  p.tail_off = WS(uint32_t, tail_off);
-  p.tail_aw = WS(uint32_t, tail_aw);
-  p.tail_ts = WS(int32_t, tail_ts);
-  p.winmask = WS(uint32_t, winmask);
-  p.bin_base = WS(uint32_t, bin_base);
-  p.hist = WS(uint32_t, hist);
-  p.cursor = WS(uint32_t, cursor);
-  p.records = nullptr;
-  p.n_sessions = L.S;
-  p.window = (uint32_t)spec->window_s;
-  p.x_type_mask = spec->x_type_mask;
-  p.y_type_mask = spec->y_type_mask;
-  p.weight_mode = spec->weight_mode;
-  p.ts_min = spec->ts_min;
-  for (int i = 0; i < 3; ++i) p.type_weight[i] = (uint32_t)spec->type_weight[i];
-  p.scatter_part = 0;
-  return p;
-}
-
+// bins from the (all-reduced) row totals, record offsets of this rank's rows, scatter cursors
 extern "C" int otto_covisit_count_finish(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
                                          int64_t workspace_bytes, OttoBuildStats* stats_host, void* stream) {
   int rc = check_spec(spec);
@@ -350,55 +526,53 @@ extern "C" int otto_covisit_count_finish(const OttoEvents* ev, const OttoCovisit
   if ((rc = check_ws(L, workspace, workspace_bytes))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t A = L.A;
-  // bins: nb[x] lands in bin_base, scanned in place
   CUDA_TRY(cudaMemsetAsync(WS(uint32_t, bin_base), 0, (A + 2) * 4, st));
-  bins_count_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(WS(uint32_t, pair_ub), A,
-                                                                (uint32_t)effective_split_ub(spec),
-                                                                WS(uint32_t, bin_base), WS(unsigned long long, stats));
+  CUDA_TRY(cudaMemsetAsync(WS(unsigned long long, stats) + 3, 0, 8, st));
+  bins_count_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(
+      WS(uint32_t, row_total), WS(uint32_t, row_count), A, (uint32_t)effective_split_ub(spec), (uint32_t)sub_bin_target(spec),
+      WS(uint32_t, bin_base), WS(unsigned long long, hot_off), WS(uint32_t, hot_rows), L.Hmax, WS(unsigned long long, stats));
   LAUNCH_CHECK();
   if ((rc = exclusive_scan<uint32_t, uint32_t>(WS(uint32_t, bin_base), A, WS(uint32_t, bin_base), WS(uint32_t, scan), st)))
     return rc;
-  {
-    // the bin arrays were sized from the event count: refuse before anything is written past them
-    uint32_t n_bins = 0;
-    CUDA_TRY(cudaMemcpyAsync(&n_bins, WS(uint32_t, bin_base) + A, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if ((int64_t)n_bins > L.Bmax) {
-      otto_set_error("%u bins exceed the %lld the workspace was sized for: set spec.global_events to the event count of all ranks",
-                     n_bins, (long long)L.Bmax);
-      return OTTO_ENOSPC;
-    }
+  if ((rc = exclusive_scan<uint32_t, unsigned long long>(WS(uint32_t, row_count), A, WS(unsigned long long, row_off),
+                                                         WS(unsigned long long, scan), st)))
+    return rc;
+  if ((rc = exclusive_scan<unsigned long long, unsigned long long>(WS(unsigned long long, hot_off), A, WS(unsigned long long, hot_off),
+                                                                   WS(unsigned long long, scan), st)))
+    return rc;
+  count_stats_kernel<<<1, 1, 0, st>>>(WS(uint32_t, tail_off), L.S, WS(uint32_t, bin_base), A, WS(unsigned long long, row_off),
+                                      WS(unsigned long long, hot_off), WS(unsigned long long, stats));
+  LAUNCH_CHECK();
+  unsigned long long h[5];
+  CUDA_TRY(cudaMemcpyAsync(h, WS(char, stats), sizeof(h), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  // the bin arrays were sized from the event count: refuse before anything is written past them
+  if ((int64_t)h[2] > L.Bmax || (int64_t)h[3] > L.Hmax) {
+    otto_set_error("%llu bins / %llu hot rows exceed the %lld / %lld the workspace was sized for: set spec.global_events to the "
+                   "event count of all ranks", h[2], h[3], (long long)L.Bmax, (long long)L.Hmax);
+    return OTTO_ENOSPC;
+  }
+  if (h[1] + h[4] >= (1ull << 32)) {
+    otto_set_error("a rank is limited to 2^32 - 1 pair records including its staged hot rows (32 GiB); shard the sessions");
+    return OTTO_EINVAL;
   }
   bins_fill_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(WS(uint32_t, bin_base), A, WS(uint32_t, bin_x));
   LAUNCH_CHECK();
-  // pass 1: winner masks + per-bin pair counts
-  CUDA_TRY(cudaMemsetAsync(WS(uint32_t, hist), 0, (L.Bmax + 1) * 4, st));
-  if (L.S > 0) {
-    PairGenParams p = make_pairgen(L, spec, workspace);
-    const int64_t warps = ceil_div(L.S, 32);
-    pairgen_kernel<false><<<(unsigned)ceil_div(warps, PAIRGEN_WARPS), PAIRGEN_WARPS * 32, 0, st>>>(p);
-    LAUNCH_CHECK();
-  }
-  if ((rc = exclusive_scan<uint32_t, unsigned long long>(WS(uint32_t, hist), L.Bmax, WS(unsigned long long, bin_off),
-                                                         WS(unsigned long long, scan), st)))
-    return rc;
-  count_stats_kernel<<<1, 1, 0, st>>>(WS(uint32_t, tail_off), L.S, WS(uint32_t, bin_base), A,
-                                      WS(unsigned long long, bin_off), WS(unsigned long long, stats));
+  init_cursor_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(WS(unsigned long long, row_off), WS(unsigned long long, hot_off),
+                                                                 WS(uint32_t, bin_base), A, WS(uint32_t, cursor));
   LAUNCH_CHECK();
   if (stats_host) {
-    unsigned long long h[4];
-    CUDA_TRY(cudaMemcpyAsync(h, WS(char, stats), sizeof(h), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
     stats_host->tail_events = (int64_t)h[0];
     stats_host->pairs = (int64_t)h[1];
     stats_host->bins = (int64_t)h[2];
     stats_host->split_rows = (int64_t)h[3];
+    stats_host->hot_pairs = (int64_t)h[4];
   }
   return OTTO_OK;
 }
 
-extern "C" int otto_covisit_count(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
-                                  int64_t workspace_bytes, OttoBuildStats* stats_host, void* stream) {
+extern "C" int otto_covisit_count(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
+                                  OttoBuildStats* stats_host, void* stream) {
   int rc = otto_covisit_count_begin(ev, spec, workspace, workspace_bytes, stream);
   if (rc) return rc;
   return otto_covisit_count_finish(ev, spec, workspace, workspace_bytes, stats_host, stream);
@@ -406,7 +580,7 @@ extern "C" int otto_covisit_count(const OttoEvents* ev, const OttoCovisitSpec* s
 
 extern "C" int otto_covisit_views(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
                                   int64_t workspace_bytes, uint64_t** bin_offsets, uint32_t** bin_base,
-                                  uint32_t** bin_x, uint32_t** pair_ub) {
+                                  uint32_t** bin_x, uint32_t** row_total) {
   int rc = check_spec(spec);
   if (rc) return rc;
   const Layout L = make_layout(ev->n_sessions, ev->n_events, spec);
@@ -414,10 +588,11 @@ extern "C" int otto_covisit_views(const OttoEvents* ev, const OttoCovisitSpec* s
   if (bin_offsets) *bin_offsets = WS(uint64_t, bin_off);
   if (bin_base) *bin_base = WS(uint32_t, bin_base);
   if (bin_x) *bin_x = WS(uint32_t, bin_x);
-  if (pair_ub) *pair_ub = WS(uint32_t, pair_ub);
+  if (row_total) *row_total = WS(uint32_t, row_total);
   return OTTO_OK;
 }
 
+// records of ordinary rows at their final positions, hot rows through the staging area into their sub-bins
 extern "C" int otto_covisit_scatter(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
                                     int64_t workspace_bytes, void* records, int64_t records_capacity, void* stream) {
   int rc = check_spec(spec);
@@ -427,35 +602,46 @@ extern "C" int otto_covisit_scatter(const OttoEvents* ev, const OttoCovisitSpec*
   if (!records && records_capacity > 0) { otto_set_error("records is NULL"); return OTTO_EINVAL; }
   if (records_capacity >= (1ll << 32)) { otto_set_error("a rank is limited to 2^32 - 1 pair records (32 GiB); shard the sessions"); return OTTO_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
-  init_cursor_kernel<<<592, 256, 0, st>>>(WS(unsigned long long, bin_off), WS(uint32_t, bin_base), L.A,
-                                          WS(uint32_t, cursor));
-  LAUNCH_CHECK();
+  const int64_t A = L.A;
   if (L.S > 0) {
     PairGenParams p = make_pairgen(L, spec, workspace);
     p.records = (uint2*)records;
     const int64_t warps = ceil_div(L.S, 32);
-    static const bool one = getenv("OTTO_SCATTER_ONE_KERNEL") != nullptr;
-    if (one) {
-      p.scatter_part = 0;
-      pairgen_kernel<true><<<(unsigned)ceil_div(warps, PAIRGEN_WARPS), PAIRGEN_WARPS * 32, 0, st>>>(p);
-      LAUNCH_CHECK();
-    } else {
-      // the memory-bound runs of the ordinary rows and the latency-bound per-pair path of the hot rows as two
-      // kernels side by side (9.9 -> 9.4 ms; each re-reads the 1.6 GB tail CSR)
-      int rc2 = side_streams_init();
-      if (rc2) return rc2;
-      CUDA_TRY(cudaEventRecord(g_fork, st));
-      CUDA_TRY(cudaStreamWaitEvent(g_side[0], g_fork, 0));
-      p.scatter_part = 2;
-      pairgen_kernel<true><<<(unsigned)ceil_div(warps, PAIRGEN_WARPS), PAIRGEN_WARPS * 32, 0, g_side[0]>>>(p);
-      LAUNCH_CHECK();
-      p.scatter_part = 1;
-      pairgen_kernel<true><<<(unsigned)ceil_div(warps, PAIRGEN_WARPS), PAIRGEN_WARPS * 32, 0, st>>>(p);
-      LAUNCH_CHECK();
-      CUDA_TRY(cudaEventRecord(g_join[0], g_side[0]));
-      CUDA_TRY(cudaStreamWaitEvent(st, g_join[0], 0));
-    }
+    pairgen_kernel<true><<<(unsigned)ceil_div(warps, PAIRGEN_WARPS), PAIRGEN_WARPS * 32, 0, st>>>(p);
+    LAUNCH_CHECK();
   }
+  CUDA_TRY(cudaMemsetAsync(WS(uint32_t, bin_cnt), 0, (L.Bmax + 1) * 4, st));
+  bin_cnt_rows_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(WS(uint32_t, row_count), WS(uint32_t, bin_base), A,
+                                                                  WS(uint32_t, bin_cnt));
+  LAUNCH_CHECK();
+  PartParams pp;
+  pp.hot_rows = WS(uint32_t, hot_rows);
+  pp.n_hot = WS(unsigned long long, stats) + 3;
+  pp.hot_cap = L.Hmax;
+  pp.bin_base = WS(uint32_t, bin_base);
+  pp.row_count = WS(uint32_t, row_count);
+  pp.row_off = WS(unsigned long long, row_off);
+  pp.hot_off = WS(unsigned long long, hot_off);
+  pp.A = A;
+  pp.bin_cnt = WS(uint32_t, bin_cnt);
+  pp.bin_off = WS(unsigned long long, bin_off);
+  pp.records = (uint2*)records;
+  int dev = 0, n_sm = 148;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  partition_count_kernel<<<n_sm * 4, PART_THREADS, 0, st>>>(pp);
+  LAUNCH_CHECK();
+  if ((rc = exclusive_scan<uint32_t, unsigned long long>(WS(uint32_t, bin_cnt), L.Bmax, WS(unsigned long long, bin_off),
+                                                         WS(unsigned long long, scan), st)))
+    return rc;
+  CUDA_TRY(cudaFuncSetAttribute(partition_move_kernel<PART_NB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)part_move_smem<PART_NB_SMALL>()));
+  partition_move_kernel<PART_NB_SMALL><<<n_sm * 4, PART_THREADS, part_move_smem<PART_NB_SMALL>(), st>>>(pp);
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaFuncSetAttribute(partition_move_kernel<MAX_SUB_BINS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)part_move_smem<MAX_SUB_BINS>()));
+  partition_move_kernel<MAX_SUB_BINS><<<n_sm, PART_THREADS, part_move_smem<MAX_SUB_BINS>(), st>>>(pp);
+  LAUNCH_CHECK();
   return OTTO_OK;
 }
 
@@ -785,14 +971,14 @@ extern "C" int otto_covisit_build(const OttoEvents* ev, const OttoCovisitSpec* s
   const Layout L = make_layout(ev->n_sessions, ev->n_events, spec);
   const ScratchLayout SL = make_scratch(spec->k, stp->bins, L.A);
   const int64_t rec_at = align_up(L.total, 256);
-  const int64_t scratch_at = align_up(rec_at + stp->pairs * 8, 256);
+  const int64_t scratch_at = align_up(rec_at + (stp->pairs + stp->hot_pairs) * 8, 256);
   const int64_t need = scratch_at + SL.total;
   if (workspace_bytes < need) {
     otto_set_error("workspace too small for %lld pair records: need %lld bytes", (long long)stp->pairs, (long long)need);
     return OTTO_ENOSPC;
   }
   char* ws = (char*)workspace;
-  if ((rc = otto_covisit_scatter(ev, spec, workspace, workspace_bytes, ws + rec_at, stp->pairs, stream))) return rc;
+  if ((rc = otto_covisit_scatter(ev, spec, workspace, workspace_bytes, ws + rec_at, stp->pairs + stp->hot_pairs, stream))) return rc;
   OttoPairSegment seg;
   seg.records = ws + rec_at;
   seg.offsets = WS(uint64_t, bin_off);

@@ -23,11 +23,14 @@
 //           row with the same aid is in U_j.  Only lanes that repeat an aid can be dropped, so this is a
 //           loop over the (few) repeat lanes of the batch, not over rows.
 // A 5-step butterfly transposes the column masks into ROW masks (bit j of row i), which are stored
-// (4 B per tail event) and whose popcounts feed the bin histogram: one RED per (session, row) for ordinary
-// rows, one per pair for rows that are split into aid_y-hash sub-bins (hot aid_x).
+// (4 B per tail event) and whose popcounts feed the per-aid_x pair histogram: one RED per (session, row).
 // Pass 2 (scatter) re-reads events + row masks, reserves the row's slots with one atomic per
-// (session, row) and writes 8-byte records {aid_y, v}; aid_x is implicit in the bin.
+// (session, row) and writes 8-byte records {aid_y, v} as one contiguous run; aid_x is implicit in the position.
 // v = ts_x - ts_min (time), type_weight[type_y] (type) or 1 (unit).
+// Neither pass knows about sub-bins: the runs of a hot aid_x land in a staging area and are partitioned by
+// aid_y hash afterwards (build.cu, partition_*_kernel).  v1-v4 of this kernel took one returning global atomic
+// and one lone 8-byte store per PAIR of a hot row (30 % of all pairs); that path held 35 % of the scatter's
+// stall samples and most of its partial-sector DRAM traffic (profiles/r01_final_scatter_lines.txt).
 #pragma once
 #include "common.cuh"
 
@@ -36,9 +39,8 @@ struct PairGenParams {
   const uint32_t* tail_aw;    // [E30]
   const int32_t* tail_ts;     // [E30]
   uint32_t* winmask;          // [E30]
-  const uint32_t* bin_base;   // [A + 1]
-  uint32_t* hist;             // [B]      pass 1
-  uint32_t* cursor;           // [B]      pass 2 (starts as the exclusive scan of hist; P < 2^32)
+  uint32_t* row_hist;         // [A]      pass 1: pairs per aid_x
+  uint32_t* cursor;           // [A]      pass 2: next free record slot of the row (staging area for hot rows)
   uint2* records;             //          pass 2
   int64_t n_sessions;
   uint32_t window;
@@ -46,7 +48,6 @@ struct PairGenParams {
   int32_t weight_mode;
   int32_t ts_min;
   uint32_t type_weight[3];
-  int32_t scatter_part;       // pass 2: 0 = everything, 1 = ordinary rows only, 2 = split (hot) rows only
 };
 
 constexpr int PAIRGEN_WARPS = 8;
@@ -104,13 +105,6 @@ __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairG
     const uint32_t aid = aw & AID_MASK;
     const uint32_t ty = aw >> 30;
 
-    // row-owner view: bins of my aid_x
-    uint32_t bb0 = 0, nbx = 1;
-    if (active) {
-      bb0 = p.bin_base[aid];
-      nbx = p.bin_base[aid + 1] - bb0;
-    }
-
     if (!SCATTER) {
       const uint32_t grpmask = active ? (lowmask(n) << base) : 0u;
       const uint32_t same = __match_any_sync(FULL_MASK, active ? aid : (0x80000000u | lane)) & grpmask;
@@ -161,71 +155,24 @@ __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairG
           if (((V >> i) & 1u) && (ei & U)) V &= ~(1u << i);
         }
       }
-      // split rows: one RED per pair into the aid_y-hash sub-bin of the row
-      const uint32_t spl = __ballot_sync(FULL_MASK, active && nbx > 1);
-      if (spl) {
-        uint32_t rem = V & spl;
-        const uint32_t hy = hash32(aid);
-        while (__any_sync(FULL_MASK, rem != 0)) {
-          const int i = rem ? __ffs(rem) - 1 : (int)lane;
-          const uint32_t nbi = __shfl_sync(FULL_MASK, nbx, i);
-          const uint32_t bbi = __shfl_sync(FULL_MASK, bb0, i);
-          if (rem) {
-            atomicAdd(&p.hist[bbi + __umulhi(hy, nbi)], 1u);
-            rem &= rem - 1;
-          }
-        }
-      }
       // column masks -> row masks; lane i now owns the winners of row i
       const uint32_t R = warp_transpose32(V);
       if (active) p.winmask[e0 + lane] = R >> base;
       const uint32_t cnt = __popc(R);
-      if (active && cnt && nbx == 1) atomicAdd(&p.hist[bb0], cnt);
+      if (active && cnt) atomicAdd(&p.row_hist[aid], cnt);
     } else {
       const uint32_t mywm = active ? (p.winmask[e0 + lane] << base) : 0u;
       const uint32_t cnt = __popc(mywm);
-      const bool split_row = active && nbx > 1;
       uint32_t slot = 0;
-      if (p.scatter_part != 2 && active && cnt && nbx == 1) slot = atomicAdd(&p.cursor[bb0], cnt);
+      if (active && cnt) slot = atomicAdd(&p.cursor[aid], cnt);
       uint32_t v = 1;
       if (p.weight_mode == OTTO_WEIGHT_TYPE) v = ty == 0 ? p.type_weight[0] : (ty == 1 ? p.type_weight[1] : p.type_weight[2]);
       const bool time_mode = p.weight_mode == OTTO_WEIGHT_TIME;
       const int32_t tv = t - p.ts_min;
-      // Split rows: every pair takes its own slot in the aid_y-hash sub-bin of the row.  Done from the
-      // column view (lane j walks the split rows it won) with the atomics of a chunk issued back to back
-      // and the stores behind them, so that one round trip covers SPLIT_CHUNK pairs (a row loop with the
-      // atomic inside serialised one round trip per row: profiles/r01_pairgen_v4).
-      const uint32_t spl = p.scatter_part == 1 ? 0u : __ballot_sync(FULL_MASK, split_row && cnt);
-      if (spl) {
-        constexpr int SPLIT_CHUNK = 4;
-        uint32_t rem = warp_transpose32(mywm) & spl;
-        const uint32_t hy = hash32(aid);
-        while (__any_sync(FULL_MASK, rem != 0)) {
-          uint32_t pos[SPLIT_CHUNK], val[SPLIT_CHUNK], todo = 0;
-#pragma unroll
-          for (int k = 0; k < SPLIT_CHUNK; ++k) {
-            const int i = rem ? __ffs(rem) - 1 : (int)lane;
-            const uint32_t nbi = __shfl_sync(FULL_MASK, nbx, i);
-            const uint32_t bbi = __shfl_sync(FULL_MASK, bb0, i);
-            val[k] = time_mode ? (uint32_t)__shfl_sync(FULL_MASK, tv, i) : v;
-            pos[k] = 0;
-            if (rem) {
-              pos[k] = atomicAdd(&p.cursor[bbi + __umulhi(hy, nbi)], 1u);
-              todo |= 1u << k;
-              rem &= rem - 1;
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < SPLIT_CHUNK; ++k)
-            if ((todo >> k) & 1u) st_stream_u2(p.records + pos[k], make_uint2(aid, val[k]));
-        }
-      }
-      // ordinary rows: row i's winners write one contiguous run
-      const uint32_t wm_run = split_row ? 0u : mywm;
-      if (p.scatter_part == 2) continue;
+      // row i's winners write one contiguous run
       for (int i = 0; i < maxn; ++i) {
         const int src = (active && i < n) ? base + i : (int)lane;   // own row mask never holds the own lane
-        const uint32_t wmi = __shfl_sync(FULL_MASK, wm_run, src);
+        const uint32_t wmi = __shfl_sync(FULL_MASK, mywm, src);
         const uint32_t sloti = __shfl_sync(FULL_MASK, slot, src);
         const uint32_t val = time_mode ? (uint32_t)__shfl_sync(FULL_MASK, tv, src) : v;
         if ((wmi >> lane) & 1u) st_stream_u2(p.records + (sloti + __popc(wmi & lt)), make_uint2(aid, val));

@@ -3,11 +3,11 @@ exchanged by one all-to-all keyed on aid_x ownership.
 
     rank r                                   collective (torch.distributed, NCCL over NVLink)
     ------                                   -----------------------------------------------
-    count_begin  (tails, local upper bounds)
-                                             all-reduce  pair_ub [A] uint32   -> identical bins everywhere
-    count_finish (winner masks, local per-bin pair counts)
-                                             all-reduce  bin counts [B] int64 -> balanced aid_x ranges
+    count_begin  (tails, in-session dedupe, local pairs per aid_x row)
+                                             all-reduce  row totals [A] uint32 -> identical bins everywhere
+    count_finish (bins, local record offsets)
     scatter      (records grouped by bin; an owner's bins are one contiguous slab)
+                                             all-reduce  bin counts [B] int64 -> balanced aid_x ranges
                                              all-to-all  record slabs + their bin offsets
     reduce       (accumulate + top-k over the G received segments of my aid range)
                                              broadcast   each owner's rows (gather_table) for candidate-gen
@@ -112,17 +112,18 @@ class GpuRankBackend:
     def count_begin(self) -> torch.Tensor:
         self.b.count_begin()
         self.b.stats.bins = 0
-        return self.b.views()["pair_ub"]            # int32 view of the uint32 bounds, reduced in place
+        return self.b.views()["row_total"]          # int32 view of the uint32 pair counts per row, reduced in place
 
     def count_finish(self):
         stats = self.b.count_finish()
-        v = self.b.views()
-        return stats, v["bin_offsets"], v["bin_base"]
+        return stats, self.b.views()["bin_base"]
 
-    def scatter(self) -> torch.Tensor:
+    def scatter(self):
+        """-> (records, bin_offsets); the offsets exist only now (the sub-bins of hot rows are sized while scattering)."""
         if self.peer is not None:
-            self.b.records = self.peer.ensure(int(self.b.stats.pairs))     # collective
-        return self.b.scatter()
+            self.b.records = self.peer.ensure(int(self.b.stats.pairs) + int(self.b.stats.hot_pairs))     # collective
+        records = self.b.scatter()
+        return records, self.b.views()["bin_offsets"]
 
     def reduce(self, segments, bin_lo, bin_hi, aid_lo, aid_hi) -> TopKTable:
         # one run per bin for the reduce kernels once a bin is spread over more than two senders (with two the extra
@@ -179,16 +180,16 @@ def build_topk_distributed(backend, group=None, timing: dict | None = None):
     if world > 1:
         dist.all_reduce(ub, group=group)
     mark("allreduce_ub")
-    stats, bin_off, bin_base = backend.count_finish()
+    stats, bin_base = backend.count_finish()
     mark("count_finish")
+    records, bin_off = backend.scatter()
+    mark("scatter")
     B = int(stats["bins"])
     counts = (bin_off[1:B + 1] - bin_off[:B]).clone()
     if world > 1:
         dist.all_reduce(counts, group=group)
     plan = plan_owners(counts, bin_base, world)
     mark("allreduce_counts+plan")
-    records = backend.scatter()
-    mark("scatter")
     lo, hi = plan.bin_cuts[rank], plan.bin_cuts[rank + 1]
     peer = getattr(backend, "peer", None)
     if world == 1:

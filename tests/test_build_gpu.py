@@ -235,8 +235,8 @@ def test_bin_arrays_guard_refuses_more_bins_than_sized(cv):
     b = cv.CovisitBuilder(csr, replace(cv.CLICKS, split_ub=16))
     b.count_begin()
     b.stats.bins = 0
-    ub = b.views()["pair_ub"]
-    ub.mul_(1000)                      # what an all-reduce over many more ranks would do to the bounds
+    ub = b.views()["row_total"]
+    ub.mul_(1000)                      # what an all-reduce over many more ranks would do to the row totals
     with pytest.raises(cv.N.OttoError) as e:
         b.count_finish()
     assert e.value.code == cv.N.OTTO_ENOSPC and "global_events" in str(e.value)
@@ -244,7 +244,7 @@ def test_bin_arrays_guard_refuses_more_bins_than_sized(cv):
     b2 = cv.CovisitBuilder(csr, replace(cv.CLICKS, split_ub=16, global_events=1000 * csr.n_events))
     b2.count_begin()
     b2.stats.bins = 0
-    b2.views()["pair_ub"].mul_(1000)
+    b2.views()["row_total"].mul_(1000)
     assert b2.count_finish()["bins"] > csr.n_aids
 
 

@@ -1,6 +1,6 @@
 """World-size-2 gloo tests of the multi-GPU exchange logic (owner planning, slab all-to-all, segment
 assembly) with a numpy stand-in for the rank-local CUDA phases.  The stand-in follows the same interface as
-distributed.GpuRankBackend and forms the same bins (upper bounds, split_ub, aid_y-hash slices)."""
+distributed.GpuRankBackend and forms the same bins (row totals, split_ub, aid_y-hash slices)."""
 import os
 import socket
 
@@ -34,30 +34,30 @@ class NumpyRankBackend:
         self.df, self.spec, self.n_aids, self.split_ub = df, spec, n_aids, split_ub
 
     def count_begin(self):
-        d = self.df.sort_values(["session", "ts"], ascending=[True, False], kind="stable")
-        d = d.loc[d.groupby("session").cumcount() < self.spec.tail_n]
-        n = d.groupby("session")["aid"].transform("size").to_numpy()
-        self.ub = torch.from_numpy(np.bincount(d["aid"].to_numpy(), weights=n - 1, minlength=self.n_aids).astype(np.int32))
-        return self.ub
+        # local pairs per aid_x row (after the in-session dedupe); the driver all-reduces this tensor in place
+        self.pairs = co.dedup_pairs(self.df, self.spec)
+        self.local = np.bincount(self.pairs["aid_x"].to_numpy(), minlength=self.n_aids).astype(np.int64)
+        self.total = torch.from_numpy(self.local.astype(np.int32).copy())
+        return self.total
 
     def count_finish(self):
-        ub = self.ub.numpy().astype(np.int64)
-        nb = np.maximum(1, -(-ub // self.split_ub))
-        self.bin_base = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
-        pairs = co.dedup_pairs(self.df, self.spec)
-        x, y = pairs["aid_x"].to_numpy().astype(np.int64), pairs["aid_y"].to_numpy().astype(np.int64)
-        nbx = nb[x]
+        tot = self.total.numpy().astype(np.int64)
+        target = max(1, self.split_ub // 2)
+        self.nb = np.where(tot > self.split_ub, np.maximum(1, -(-tot // target)), 1).astype(np.int64)
+        self.bin_base = np.concatenate([[0], np.cumsum(self.nb)]).astype(np.int64)
+        self.bin_x = np.repeat(np.arange(self.n_aids), self.nb)
+        stats = {"bins": int(self.bin_base[-1]), "pairs": len(self.pairs)}
+        return stats, torch.from_numpy(self.bin_base.astype(np.int32))
+
+    def scatter(self):
+        x, y = self.pairs["aid_x"].to_numpy().astype(np.int64), self.pairs["aid_y"].to_numpy().astype(np.int64)
+        nbx = self.nb[x]
         b = self.bin_base[x] + np.where(nbx > 1, _sub_bin(y, nbx).astype(np.int64), 0)
         order = np.argsort(b, kind="stable")
         self.rec = (y[order] | (np.ones_like(y) << 32)).astype(np.int64)       # v = 1 (unit weights)
         B = int(self.bin_base[-1])
         self.bin_off = np.concatenate([[0], np.cumsum(np.bincount(b, minlength=B))]).astype(np.int64)
-        self.bin_x = np.repeat(np.arange(self.n_aids), nb)
-        stats = {"bins": B, "pairs": len(self.rec)}
-        return stats, torch.from_numpy(self.bin_off), torch.from_numpy(self.bin_base.astype(np.int32))
-
-    def scatter(self):
-        return torch.from_numpy(self.rec)
+        return torch.from_numpy(self.rec), torch.from_numpy(self.bin_off)
 
     def reduce(self, segments, bin_lo, bin_hi, aid_lo, aid_hi):
         rows = []
