@@ -84,7 +84,7 @@ extern "C" int otto_ingest_desc(const int32_t* session_offsets, int64_t n_sessio
 struct Layout {
   int64_t S, E, Ecap, A, Bmax, Hmax;
   int64_t tail_off, tail_aw, tail_ts, winmask, row_count, row_total, bin_base, bin_x, bin_cnt, bin_off, row_off, hot_off, cursor,
-      hot_rows, scan, stats, total;
+      hot_rows, sub_cur, tile_row, tile_idx, Tmax, scan, stats, total;
 };
 
 // A row whose pair count (over all ranks) exceeds split_ub is "hot": it is split into aid_y-hash sub-bins of
@@ -143,6 +143,11 @@ static Layout make_layout(int64_t S, int64_t E, const OttoCovisitSpec* spec) {
   L.hot_off = take((L.A + 2) * 8);
   L.cursor = take((L.A + 1) * 4);
   L.hot_rows = take((L.Hmax + 1) * 4);
+  L.sub_cur = take((L.Bmax + 1) * 4);
+  // tiles of the staging area: every hot row rounds up once
+  L.Tmax = (Eg * (spec->tail_n - 1)) / 2048 + L.Hmax + 1;
+  L.tile_row = take(L.Tmax * 4);
+  L.tile_idx = take(L.Tmax * 4);
   int64_t scan_elems = scan_scratch_elems(S + 1);
   if (scan_scratch_elems(L.Bmax + 1) > scan_elems) scan_elems = scan_scratch_elems(L.Bmax + 1);
   if (scan_scratch_elems(L.A + 1) > scan_elems) scan_elems = scan_scratch_elems(L.A + 1);
@@ -307,10 +312,15 @@ __global__ void bin_cnt_rows_kernel(const uint32_t* __restrict__ row_count, cons
   if (bin_base[x + 1] - b0 == 1) bin_cnt[b0] = row_count[x];
 }
 
-// ---- hot rows: staging area -> aid_y-hash sub-bins.  One CTA owns a hot row, so the sub-bin cursors live in
-// shared memory (no global atomic on the path), and the few hundred open write lines of a CTA stay in L2 until
-// they are complete.  Pass 1 counts, an exclusive scan over all bins gives the final offsets, pass 2 moves.
-constexpr int PART_THREADS = 512;
+// ---- hot rows: staging area -> aid_y-hash sub-bins.  Work unit = a tile of PART_TILE staged records of one hot
+// row, so the hottest rows (millions of records) spread over the whole GPU.  Pass 1 histograms a tile in shared
+// memory and adds the non-zero counts to the bins; an exclusive scan over all bins gives the final offsets; pass 2
+// histograms again (rank of every record inside its tile and sub-bin), reserves each sub-bin's chunk with one
+// global atomic per tile and writes.  The sub-bin chunks of a tile are written within microseconds by one CTA, so
+// their lines complete in L2.
+constexpr int PART_THREADS = 256;
+constexpr int PART_PER_THREAD = 8;
+constexpr int PART_TILE = PART_THREADS * PART_PER_THREAD;
 
 struct PartParams {
   const uint32_t* hot_rows;
@@ -322,125 +332,79 @@ struct PartParams {
   const unsigned long long* hot_off;
   int64_t A;
   uint32_t* bin_cnt;
-  const unsigned long long* bin_off;
+  uint32_t* sub_cur;                   // [B] next free record slot of every bin (pass 2)
+  uint32_t* tile_row;                  // [tiles] index into hot_rows
+  uint32_t* tile_idx;                  // [tiles] tile number inside the row
+  unsigned long long* n_tiles;         // stats[5]
+  int64_t tile_cap;
   uint2* records;
 };
 
-// pass 1: records per sub-bin
-__global__ void __launch_bounds__(PART_THREADS) partition_count_kernel(const PartParams p) {
-  __shared__ uint32_t s_cnt[MAX_SUB_BINS];
+// one thread per hot row: its tiles, appended to the tile list (any order)
+__global__ void partition_tiles_kernel(const PartParams p) {
   unsigned long long n_hot = *p.n_hot;
   if ((int64_t)n_hot > p.hot_cap) n_hot = (unsigned long long)p.hot_cap;
-  const uint2* stage = p.records + p.row_off[p.A];
-  for (unsigned long long i = blockIdx.x; i < n_hot; i += gridDim.x) {
-    const uint32_t x = p.hot_rows[i];
-    const uint32_t b0 = p.bin_base[x], nb = p.bin_base[x + 1] - b0;
-    const uint32_t n = p.row_count[x];
-    const uint2* src = stage + p.hot_off[x];
-    for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS) s_cnt[j] = 0u;
-    __syncthreads();
-    // four loads in flight per thread: the loop is otherwise one dependent chain load -> atomic
-    for (uint32_t j0 = 0; j0 < n; j0 += 4 * PART_THREADS) {
-      uint2 r[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t j = j0 + u * PART_THREADS + threadIdx.x;
-        r[u] = j < n ? ld_stream_u2(src + j) : make_uint2(0, 0);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (j0 + u * PART_THREADS + threadIdx.x < n) atomicAdd(&s_cnt[sub_bin(r[u].x, nb)], 1u);
-    }
-    __syncthreads();
-    for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS) p.bin_cnt[b0 + j] = s_cnt[j];
-    __syncthreads();
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_hot) return;
+  const uint32_t n = p.row_count[p.hot_rows[i]];
+  const uint32_t nt = (n + PART_TILE - 1) / PART_TILE;
+  if (nt == 0) return;
+  const unsigned long long at = atomicAdd(p.n_tiles, (unsigned long long)nt);
+  for (uint32_t t = 0; t < nt && (int64_t)(at + t) < p.tile_cap; ++t) {
+    p.tile_row[at + t] = (uint32_t)i;
+    p.tile_idx[at + t] = t;
   }
 }
 
-// pass 2: move.  A tile of PART_TILE records is grouped by sub-bin in shared memory first, so that consecutive
-// threads write consecutive records of one sub-bin (one lone 8-byte store per record ran at 2.5 ms for 2.4 GB).
-// Two instantiations: rows with up to 512 sub-bins (nearly all; 52 KB of shared memory, four CTAs per SM) and
-// the few hottest rows (up to MAX_SUB_BINS sub-bins).
-constexpr int PART_TILE = 4096;
-constexpr int PART_PER_THREAD = PART_TILE / PART_THREADS;
-constexpr uint32_t PART_NB_SMALL = 512;
-template <uint32_t NBCAP>
-constexpr size_t part_move_smem() { return (size_t)NBCAP * 4 * 2 + (size_t)PART_TILE * 12; }
+__global__ void init_sub_cur_kernel(const unsigned long long* __restrict__ bin_off, const uint32_t* __restrict__ bin_base,
+                                    int64_t A, uint32_t* __restrict__ sub_cur) {
+  const int64_t B = bin_base[A];
+  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x)
+    sub_cur[b] = (uint32_t)bin_off[b];
+}
 
-template <uint32_t NBCAP>
-__global__ void __launch_bounds__(PART_THREADS) partition_move_kernel(const PartParams p) {
-  extern __shared__ __align__(16) unsigned char part_smem[];
-  uint2* s_rec = (uint2*)part_smem;                              // [PART_TILE] records grouped by sub-bin
-  uint32_t* s_dst = (uint32_t*)(s_rec + PART_TILE);              // [PART_TILE] their final positions
-  uint32_t* s_cur = s_dst + PART_TILE;                           // [nb] next free position of every sub-bin
-  uint32_t* s_hist = s_cur + NBCAP;                              // [nb] tile histogram -> tile offsets
-  __shared__ uint32_t s_warp[PART_THREADS / 32];
-  unsigned long long n_hot = *p.n_hot;
-  if ((int64_t)n_hot > p.hot_cap) n_hot = (unsigned long long)p.hot_cap;
+template <bool MOVE>
+__global__ void __launch_bounds__(PART_THREADS) partition_kernel(const PartParams p) {
+  __shared__ uint32_t s_hist[MAX_SUB_BINS];
+  __shared__ uint32_t s_base[MOVE ? MAX_SUB_BINS : 1];
+  unsigned long long n_tiles = *p.n_tiles;
+  if ((int64_t)n_tiles > p.tile_cap) n_tiles = (unsigned long long)p.tile_cap;
   const uint2* stage = p.records + p.row_off[p.A];
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  for (unsigned long long i = blockIdx.x; i < n_hot; i += gridDim.x) {
-    const uint32_t x = p.hot_rows[i];
+  for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const uint32_t x = p.hot_rows[p.tile_row[t]];
     const uint32_t b0 = p.bin_base[x], nb = p.bin_base[x + 1] - b0;
-    if ((nb <= PART_NB_SMALL) != (NBCAP == PART_NB_SMALL)) continue;     // the other instantiation's row
     const uint32_t n = p.row_count[x];
-    const uint2* src = stage + p.hot_off[x];
-    for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS) s_cur[j] = (uint32_t)p.bin_off[b0 + j];
-    for (uint32_t t0 = 0; t0 < n; t0 += PART_TILE) {
-      for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS) s_hist[j] = 0u;
-      __syncthreads();
-      uint2 r[PART_PER_THREAD];
-      uint32_t sub[PART_PER_THREAD], rank[PART_PER_THREAD];
+    const uint32_t t0 = p.tile_idx[t] * PART_TILE;
+    const uint2* src = stage + p.hot_off[x] + t0;
+    const uint32_t m = min((uint32_t)PART_TILE, n - t0);
+    for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS) s_hist[j] = 0u;
+    uint2 r[PART_PER_THREAD];
 #pragma unroll
-      for (int u = 0; u < PART_PER_THREAD; ++u) {
-        const uint32_t j = t0 + u * PART_THREADS + threadIdx.x;
-        r[u] = j < n ? ld_stream_u2(src + j) : make_uint2(0, 0);
-      }
-#pragma unroll
-      for (int u = 0; u < PART_PER_THREAD; ++u) {
-        sub[u] = sub_bin(r[u].x, nb);
-        rank[u] = t0 + u * PART_THREADS + threadIdx.x < n ? atomicAdd(&s_hist[sub[u]], 1u) : 0u;
-      }
-      __syncthreads();
-      // exclusive scan of the tile histogram (nb <= MAX_SUB_BINS): thread-local chunk, warp scan, block scan
-      {
-        const uint32_t per = (nb + PART_THREADS - 1) / PART_THREADS;
-        const uint32_t lo = threadIdx.x * per, hi = min(nb, lo + per);
-        uint32_t tot = 0;
-        for (uint32_t j = lo; j < hi; ++j) tot += s_hist[j];
-        uint32_t inc = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t v = __shfl_up_sync(FULL_MASK, inc, o);
-          if (lane >= (uint32_t)o) inc += v;
-        }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        uint32_t wbase = 0;
-        for (uint32_t w = 0; w < warp; ++w) wbase += s_warp[w];
-        uint32_t ex = wbase + inc - tot;
-        for (uint32_t j = lo; j < hi; ++j) {
-          const uint32_t c = s_hist[j];
-          s_hist[j] = ex;
-          ex += c;
-        }
-      }
-      __syncthreads();
-#pragma unroll
-      for (int u = 0; u < PART_PER_THREAD; ++u) {
-        if (t0 + u * PART_THREADS + threadIdx.x < n) {
-          const uint32_t at = s_hist[sub[u]] + rank[u];
-          s_rec[at] = r[u];
-          s_dst[at] = s_cur[sub[u]] + rank[u];
-        }
-      }
-      __syncthreads();
-      const uint32_t m = min((uint32_t)PART_TILE, n - t0);
-      // advance the cursors by the tile's counts: count of sub-bin j = next offset - own offset
-      for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS) s_cur[j] += (j + 1 < nb ? s_hist[j + 1] : m) - s_hist[j];
-      for (uint32_t j = threadIdx.x; j < m; j += PART_THREADS) st_stream_u2(p.records + s_dst[j], s_rec[j]);
-      __syncthreads();
+    for (int u = 0; u < PART_PER_THREAD; ++u) {
+      const uint32_t j = u * PART_THREADS + threadIdx.x;
+      r[u] = j < m ? ld_stream_u2(src + j) : make_uint2(0, 0);
     }
+    __syncthreads();
+    uint32_t sub[PART_PER_THREAD], rank[PART_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < PART_PER_THREAD; ++u) {
+      sub[u] = sub_bin(r[u].x, nb);
+      rank[u] = 0;
+      if (u * PART_THREADS + threadIdx.x < m) rank[u] = atomicAdd(&s_hist[sub[u]], 1u);
+    }
+    __syncthreads();
+    if (!MOVE) {
+      for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS)
+        if (s_hist[j]) atomicAdd(&p.bin_cnt[b0 + j], s_hist[j]);
+    } else {
+      for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS)
+        if (s_hist[j]) s_base[j] = atomicAdd(&p.sub_cur[b0 + j], s_hist[j]);
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < PART_PER_THREAD; ++u)
+        if (u * PART_THREADS + threadIdx.x < m) p.records[s_base[sub[u]] + rank[u]] = r[u];
+    }
+    __syncthreads();
   }
 }
 
@@ -624,23 +588,26 @@ extern "C" int otto_covisit_scatter(const OttoEvents* ev, const OttoCovisitSpec*
   pp.hot_off = WS(unsigned long long, hot_off);
   pp.A = A;
   pp.bin_cnt = WS(uint32_t, bin_cnt);
-  pp.bin_off = WS(unsigned long long, bin_off);
+  pp.sub_cur = WS(uint32_t, sub_cur);
+  pp.tile_row = WS(uint32_t, tile_row);
+  pp.tile_idx = WS(uint32_t, tile_idx);
+  pp.n_tiles = WS(unsigned long long, stats) + 5;
+  pp.tile_cap = L.Tmax;
   pp.records = (uint2*)records;
   int dev = 0, n_sm = 148;
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  partition_count_kernel<<<n_sm * 4, PART_THREADS, 0, st>>>(pp);
+  CUDA_TRY(cudaMemsetAsync(WS(unsigned long long, stats) + 5, 0, 8, st));
+  partition_tiles_kernel<<<(unsigned)ceil_div(L.Hmax, 256), 256, 0, st>>>(pp);
+  LAUNCH_CHECK();
+  partition_kernel<false><<<n_sm * 6, PART_THREADS, 0, st>>>(pp);
   LAUNCH_CHECK();
   if ((rc = exclusive_scan<uint32_t, unsigned long long>(WS(uint32_t, bin_cnt), L.Bmax, WS(unsigned long long, bin_off),
                                                          WS(unsigned long long, scan), st)))
     return rc;
-  CUDA_TRY(cudaFuncSetAttribute(partition_move_kernel<PART_NB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)part_move_smem<PART_NB_SMALL>()));
-  partition_move_kernel<PART_NB_SMALL><<<n_sm * 4, PART_THREADS, part_move_smem<PART_NB_SMALL>(), st>>>(pp);
+  init_sub_cur_kernel<<<592, 256, 0, st>>>(WS(unsigned long long, bin_off), WS(uint32_t, bin_base), A, WS(uint32_t, sub_cur));
   LAUNCH_CHECK();
-  CUDA_TRY(cudaFuncSetAttribute(partition_move_kernel<MAX_SUB_BINS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)part_move_smem<MAX_SUB_BINS>()));
-  partition_move_kernel<MAX_SUB_BINS><<<n_sm, PART_THREADS, part_move_smem<MAX_SUB_BINS>(), st>>>(pp);
+  partition_kernel<true><<<n_sm * 4, PART_THREADS, 0, st>>>(pp);
   LAUNCH_CHECK();
   return OTTO_OK;
 }
