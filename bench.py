@@ -243,7 +243,7 @@ def run_b200(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     import ctypes as C
     phases = ["count_begin", "count_finish", "scatter", "reduce"]
-    reduce_ms = []
+    reduce_ms, scatter_ms = [], []
     last = {}
     dist_timing = {}
 
@@ -294,6 +294,9 @@ def run_b200(args):
             r5 = (C.c_float * 5)()
             N.check(lib.otto_profile_reduce_ms(r5))
             reduce_ms.append(list(r5))
+            r3 = (C.c_float * 3)()
+            N.check(lib.otto_profile_scatter_ms(r3))
+            scatter_ms.append(list(r3))
         N.check(lib.otto_profile_enable(0))
     ms_step = allmax(t_start.elapsed_time(t_end)) / args.steps
     events_all = allsum(E)
@@ -330,9 +333,13 @@ def run_b200(args):
         tier_of = [0, 3, 2, 1]       # launch order (warp, 512, 256, 128) -> index into stats.tier_records
         red_ms = [statistics.mean(r[i] for r in reduce_ms) for i in range(5)] if reduce_ms else [0.0] * 5
         tr = stats.get("tier_records", [0, 0, 0, 0])
+        sc_ms = [statistics.mean(r[i] for r in scatter_ms) for i in range(3)] if scatter_ms else [0.0] * 3
+        Ph = stats.get("hot_pairs", 0)
         kernels = {
-            "tail_copy + pairgen_kernel<count>": (phase_ms["count_begin"], alg["count_begin"]),
-            "pairgen_kernel<scatter> + partition_kernel x2": (phase_ms["scatter"], alg["scatter"]),
+            "tail_copy_all_kernel + pairgen_kernel<count>": (phase_ms["count_begin"], alg["count_begin"]),
+            "pairgen_kernel<scatter>": (sc_ms[0], alg["scatter"]),
+            "partition_kernel<count> (+ bin offsets scan)": (sc_ms[1], 8 * Ph + 12 * B),
+            "partition_kernel<move>": (sc_ms[2], 16 * Ph),
         }
         for i in range(4):       # a tier reads its records once and writes the rows of its bins
             n_rec = tr[tier_of[i]]

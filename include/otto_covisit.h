@@ -128,6 +128,8 @@ uint64_t otto_launch_count(void);
  * them concurrently on two internal side streams (forked from and joined to the caller's stream). */
 int otto_profile_enable(int on);
 int otto_profile_reduce_ms(float* ms_host /* [5] */);
+/* Same for otto_covisit_scatter: pairgen scatter kernel; bin counts + partition count + offset scan; partition move. */
+int otto_profile_scatter_ms(float* ms_host /* [3] */);
 
 /* ---- ingest: frame columns -> CSR (replaces the sort + chunk writers of
  *      utilities/split_dataset_writer_parquet.py:13-33 and builder step 2) ---- */

@@ -84,6 +84,7 @@ _SIGNATURES = {
     "otto_launch_count": (C.c_uint64, []),
     "otto_profile_enable": (C.c_int, [C.c_int]),
     "otto_profile_reduce_ms": (C.c_int, [P(C.c_float)]),
+    "otto_profile_scatter_ms": (C.c_int, [P(C.c_float)]),
     "otto_frame_is_sorted": (C.c_int, [vp, vp, i64, vp, P(i32), vp]),
     "otto_ingest_desc": (C.c_int, [vp, i64, vp, vp, vp, i64, vp, vp, vp, vp]),
     "otto_covisit_sizes": (C.c_int, [i64, i64, P(OttoCovisitSpec), P(OttoBuildSizes)]),

@@ -169,6 +169,9 @@ extern "C" int otto_covisit_sizes(int64_t n_sessions, int64_t n_events, const Ot
   return OTTO_OK;
 }
 
+static int g_profile = 0;
+static cudaEvent_t g_prof_sc[4];
+static bool g_prof_sc_valid = false;
 static int side_streams_init();
 extern cudaStream_t g_side[2];
 extern cudaEvent_t g_fork, g_join[2];
@@ -567,6 +570,7 @@ extern "C" int otto_covisit_scatter(const OttoEvents* ev, const OttoCovisitSpec*
   if (records_capacity >= (1ll << 32)) { otto_set_error("a rank is limited to 2^32 - 1 pair records (32 GiB); shard the sessions"); return OTTO_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t A = L.A;
+  if (g_profile) CUDA_TRY(cudaEventRecord(g_prof_sc[0], st));
   if (L.S > 0) {
     PairGenParams p = make_pairgen(L, spec, workspace);
     p.records = (uint2*)records;
@@ -574,6 +578,7 @@ extern "C" int otto_covisit_scatter(const OttoEvents* ev, const OttoCovisitSpec*
     pairgen_kernel<true><<<(unsigned)ceil_div(warps, PAIRGEN_WARPS), PAIRGEN_WARPS * 32, 0, st>>>(p);
     LAUNCH_CHECK();
   }
+  if (g_profile) CUDA_TRY(cudaEventRecord(g_prof_sc[1], st));
   CUDA_TRY(cudaMemsetAsync(WS(uint32_t, bin_cnt), 0, (L.Bmax + 1) * 4, st));
   bin_cnt_rows_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(WS(uint32_t, row_count), WS(uint32_t, bin_base), A,
                                                                   WS(uint32_t, bin_cnt));
@@ -607,8 +612,13 @@ extern "C" int otto_covisit_scatter(const OttoEvents* ev, const OttoCovisitSpec*
     return rc;
   init_sub_cur_kernel<<<592, 256, 0, st>>>(WS(unsigned long long, bin_off), WS(uint32_t, bin_base), A, WS(uint32_t, sub_cur));
   LAUNCH_CHECK();
+  if (g_profile) CUDA_TRY(cudaEventRecord(g_prof_sc[2], st));
   partition_kernel<true><<<n_sm * 4, PART_THREADS, 0, st>>>(pp);
   LAUNCH_CHECK();
+  if (g_profile) {
+    CUDA_TRY(cudaEventRecord(g_prof_sc[3], st));
+    g_prof_sc_valid = true;
+  }
   return OTTO_OK;
 }
 
@@ -643,13 +653,13 @@ extern "C" int64_t otto_covisit_reduce_scratch_bytes(const OttoCovisitSpec* spec
   return make_scratch(spec->k, n_bins, n_aids_range).total;
 }
 
-static int g_profile = 0;
 static cudaEvent_t g_prof_ev[6];
 static bool g_prof_ready = false, g_prof_valid = false;
 
 extern "C" int otto_profile_enable(int on) {
   if (on && !g_prof_ready) {
     for (auto& e : g_prof_ev) CUDA_TRY(cudaEventCreate(&e));
+    for (auto& e : g_prof_sc) CUDA_TRY(cudaEventCreate(&e));
     g_prof_ready = true;
   }
   g_profile = on;
@@ -659,6 +669,12 @@ extern "C" int otto_profile_reduce_ms(float* ms_host) {
   if (!g_prof_valid) { otto_set_error("no profiled otto_covisit_reduce call yet"); return OTTO_EINVAL; }
   CUDA_TRY(cudaEventSynchronize(g_prof_ev[5]));
   for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventElapsedTime(&ms_host[i], g_prof_ev[i], g_prof_ev[i + 1]));
+  return OTTO_OK;
+}
+extern "C" int otto_profile_scatter_ms(float* ms_host) {
+  if (!g_prof_sc_valid) { otto_set_error("no profiled otto_covisit_scatter call yet"); return OTTO_EINVAL; }
+  CUDA_TRY(cudaEventSynchronize(g_prof_sc[3]));
+  for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventElapsedTime(&ms_host[i], g_prof_sc[i], g_prof_sc[i + 1]));
   return OTTO_OK;
 }
 #define PROF_MARK(i)                                                  \
