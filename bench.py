@@ -41,7 +41,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-candidates", action="store_true")
     ap.add_argument("--split-ub", type=int, default=0)
-    ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: exchange records with an NCCL all-to-all instead of NVLink peer reads")
+    ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: exchange records with an NCCL all-to-all instead of NVLink peer memory")
+    ap.add_argument("--peer-read", action="store_true", help="N > 1: owners read the senders' slabs over NVLink (the variant before the owner-direct scatter)")
     ap.add_argument("--dist-timing", action="store_true", help="N > 1: synchronise between phases and print their times (stderr)")
     return ap.parse_args()
 
@@ -217,6 +218,8 @@ def run_b200(args):
         torch.cuda.empty_cache()
     csr = covisit.ingest(frame, "desc", device=dev)
     E, S, A = csr.n_events, csr.n_sessions, csr.n_aids
+    if args.peer_read:
+        os.environ["OTTO_OWNER_DIRECT"] = "0"
     peer = distributed.PeerRecords(dev) if world > 1 and not args.nccl_exchange else None
     backend = distributed.GpuRankBackend(csr, spec, peer=peer)
     builder = backend.b

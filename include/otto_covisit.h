@@ -41,6 +41,7 @@ extern "C" {
 #define OTTO_MAX_TAIL 32       /* tail_n <= 32: one event per lane */
 #define OTTO_MAX_K 32
 #define OTTO_MAX_SEGMENTS 8    /* pair segments per bin = GPUs of one box */
+#define OTTO_MAX_OWNERS 8      /* ranks of one box that can own aid_x ranges (owner-direct scatter) */
 #define OTTO_MAX_TABLES 8
 #define OTTO_MAX_SOURCES 8
 #define OTTO_MAX_TARGETS 4
@@ -211,6 +212,38 @@ int otto_peer_free(void* ptr);
 int otto_peer_get_handle(void* ptr, uint8_t* handle_host /* [64] */);
 int otto_peer_open(const uint8_t* handle_host /* [64] */, void** ptr_host);
 int otto_peer_close(void* ptr);
+
+/* ---- owner-direct scatter (multi-GPU, the exchange of SURVEY.md §8e fused into the scatter kernel) ----
+ *
+ * Every rank writes each pair record straight into the record buffer of the rank that OWNS the aid_x row, through
+ * the peer mapping of that buffer (NVLink stores, fire and forget), at its final position: after the scatter the
+ * owner holds its rows exactly as a single-GPU build of the whole frame would (ordinary rows final, hot rows in its
+ * staging area), so partition and reduce run locally on one segment and nothing is read remotely afterwards.
+ * Host protocol (distributed.py):
+ *   count_begin -> all-gather the per-row pair counts (otto_covisit_views: row_total holds this rank's counts) ->
+ *   row_total := sum over ranks, row_before := sum over lower ranks, aid cuts balanced on the totals ->
+ *   otto_covisit_count_finish_owned (bins; layout of MY rows; scatter cursors = position inside the owner's buffer;
+ *   stats_host->pairs / hot_pairs = what MY buffer must hold) -> peers map each other's buffers ->
+ *   otto_covisit_scatter_owned -> any collective (orders "all scatters done") -> otto_covisit_partition ->
+ *   otto_covisit_reduce over bins [bin_base[aid_cuts[rank]], bin_base[aid_cuts[rank + 1]]) with ONE local segment. */
+typedef struct {
+  int32_t n_owners;                          /* G <= OTTO_MAX_OWNERS */
+  int32_t rank;                              /* this process' owner index */
+  int32_t aid_cuts[OTTO_MAX_OWNERS + 1];     /* owner o holds rows [aid_cuts[o], aid_cuts[o + 1]); [0] = 0, [G] = n_aids */
+  void* owner_records[OTTO_MAX_OWNERS];      /* record buffer of every owner as mapped on THIS device (scatter only) */
+} OttoOwnerPlan;
+
+/* row_before: device uint32 [n_aids], pairs of each row held by ranks below this one.  Synchronises; returns
+ * OTTO_EINVAL on every rank alike when any owner would exceed 2^32 - 1 records. */
+int otto_covisit_count_finish_owned(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                                    int64_t workspace_bytes, const OttoOwnerPlan* plan, const uint32_t* row_before,
+                                    OttoBuildStats* stats_host, void* stream);
+int otto_covisit_scatter_owned(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                               int64_t workspace_bytes, const OttoOwnerPlan* plan, void* stream);
+/* Second half of otto_covisit_scatter: records per bin, hot rows from the staging area into their sub-bins, bin
+ * offsets.  `records` is this rank's own buffer. */
+int otto_covisit_partition(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
+                           void* records, int64_t records_capacity, void* stream);
 
 /* One-shot single-GPU build; the pair records and the reduce scratch are carved from the workspace after
  * the fixed part.  Returns OTTO_ENOSPC (stats_host->pairs / bins set) when the workspace cannot hold

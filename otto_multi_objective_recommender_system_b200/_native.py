@@ -51,6 +51,13 @@ class OttoPairSegment(C.Structure):
     _fields_ = [("records", vp), ("offsets", vp)]
 
 
+MAX_OWNERS = 8
+
+
+class OttoOwnerPlan(C.Structure):
+    _fields_ = [("n_owners", i32), ("rank", i32), ("aid_cuts", i32 * (MAX_OWNERS + 1)), ("owner_records", vp * MAX_OWNERS)]
+
+
 class OttoTopK(C.Structure):
     _fields_ = [("n_aids", i32), ("k", i32), ("aid_y", vp), ("wgt", vp), ("len", vp), ("cnt", vp), ("tsum", vp)]
 
@@ -93,6 +100,10 @@ _SIGNATURES = {
     "otto_covisit_count": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(OttoBuildStats), vp]),
     "otto_covisit_views": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(vp), P(vp), P(vp), P(vp)]),
     "otto_covisit_scatter": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, vp, i64, vp]),
+    "otto_covisit_count_finish_owned": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(OttoOwnerPlan), vp,
+                                                  P(OttoBuildStats), vp]),
+    "otto_covisit_scatter_owned": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(OttoOwnerPlan), vp]),
+    "otto_covisit_partition": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, vp, i64, vp]),
     "otto_covisit_reduce_scratch_bytes": (i64, [P(OttoCovisitSpec), i64, i64]),
     "otto_covisit_reduce": (C.c_int, [P(OttoCovisitSpec), vp, vp, i64, i64, i32, i32, P(OttoPairSegment), i32, vp,
                                       i64, P(OttoTopK), P(OttoBuildStats), vp]),

@@ -272,6 +272,45 @@ class CovisitBuilder:
                                                   self.workspace.numel(), self.records.data_ptr(), P, self._st()))
         return self.records
 
+    # -- owner-direct scatter (multi-GPU; protocol in include/otto_covisit.h) ------------------
+    def owner_plan(self, aid_cuts, rank: int, owner_records=None) -> "N.OttoOwnerPlan":
+        G = len(aid_cuts) - 1
+        if not 1 <= G <= N.MAX_OWNERS:
+            raise ValueError(f"owner-direct scatter supports 1..{N.MAX_OWNERS} owners")
+        plan = N.OttoOwnerPlan()
+        plan.n_owners, plan.rank = G, rank
+        for i in range(N.MAX_OWNERS + 1):
+            plan.aid_cuts[i] = int(aid_cuts[min(i, G)])
+        for i in range(N.MAX_OWNERS):
+            plan.owner_records[i] = int(owner_records[i]) if owner_records is not None and i < G else None
+        return plan
+
+    def count_finish_owned(self, aid_cuts, rank: int, row_before: torch.Tensor) -> dict:
+        """views()["row_total"] must hold the totals over all ranks; row_before the pairs of lower ranks per row."""
+        _require_cuda(row_before, "row_before")
+        if row_before.numel() < self.csr.n_aids or row_before.element_size() != 4:
+            raise ValueError("row_before must hold n_aids 32-bit counts")
+        plan = self.owner_plan(aid_cuts, rank)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.otto_covisit_count_finish_owned(C.byref(self.ev), C.byref(self.cspec), self.workspace.data_ptr(),
+                                                             self.workspace.numel(), C.byref(plan), row_before.data_ptr(),
+                                                             C.byref(self.stats), self._st()))
+        return self.stats.as_dict()
+
+    def scatter_owned(self, aid_cuts, rank: int, owner_records) -> None:
+        plan = self.owner_plan(aid_cuts, rank, owner_records)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.otto_covisit_scatter_owned(C.byref(self.ev), C.byref(self.cspec), self.workspace.data_ptr(),
+                                                        self.workspace.numel(), C.byref(plan), self._st()))
+
+    def partition(self) -> torch.Tensor:
+        """Second half of scatter() on self.records (already filled, here by every rank of the box)."""
+        P = int(self.stats.pairs) + int(self.stats.hot_pairs)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.otto_covisit_partition(C.byref(self.ev), C.byref(self.cspec), self.workspace.data_ptr(),
+                                                    self.workspace.numel(), self.records.data_ptr(), P, self._st()))
+        return self.records
+
     def reduce(self, segments=None, bin_lo: int = 0, bin_hi: int | None = None, aid_lo: int = 0,
                aid_hi: int | None = None, table: TopKTable | None = None, sync: bool = True) -> TopKTable:
         """segments: list of (records tensor, offsets tensor int64 [bins + 1]); default = this rank's own."""

@@ -306,6 +306,48 @@ __global__ void count_stats_kernel(const uint32_t* tail_off, int64_t S, const ui
   stats[4] = hot_off[A];
 }
 
+// ---- owner-direct scatter (multi-GPU): every rank lays out ALL owners' buffers the same way, from the row totals.
+// E = exclusive scan of the row totals, Hs = exclusive scan of the hot rows' totals.  Owner o holds rows
+// [cut[o], cut[o + 1]): P_o = E[cut[o + 1]] - E[cut[o]] final records followed by its staging area.
+struct OwnerCuts {
+  int32_t n, rank;
+  uint32_t cut[OTTO_MAX_OWNERS + 1];
+};
+constexpr int STAT_CUT_E = 8, STAT_CUT_H = 8 + OTTO_MAX_OWNERS + 1;   // stats[] slots of E / Hs at the cuts
+
+__global__ void owner_cut_values_kernel(const OwnerCuts c, const unsigned long long* __restrict__ E,
+                                        const unsigned long long* __restrict__ Hs, unsigned long long* stats) {
+  const int o = threadIdx.x;
+  if (o <= c.n) {
+    stats[STAT_CUT_E + o] = E[c.cut[o]];
+    stats[STAT_CUT_H + o] = Hs[c.cut[o]];
+  }
+}
+
+// cursor of row x = its position inside its OWNER's buffer + the pairs that lower ranks hold of it.  The inputs of
+// the local layout are then rewritten to "my rows with their totals over all ranks, nothing else": with them the
+// single-GPU phases (offsets, partition, bin counts) describe exactly what the peers are about to write here.
+__global__ void init_cursor_owned_kernel(const OwnerCuts c, const uint32_t* __restrict__ row_total,
+                                         const uint32_t* __restrict__ row_before, const uint32_t* __restrict__ bin_base,
+                                         int64_t A, const unsigned long long* __restrict__ E, unsigned long long* hot_off,
+                                         const unsigned long long* __restrict__ stats, uint32_t* __restrict__ cursor,
+                                         uint32_t* __restrict__ row_count) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= A) return;
+  int o = 0;
+#pragma unroll
+  for (int g = 1; g < OTTO_MAX_OWNERS; ++g)
+    if (g < c.n && (uint32_t)x >= c.cut[g]) o = g;
+  const bool hot = bin_base[x + 1] - bin_base[x] > 1;
+  const unsigned long long P_o = stats[STAT_CUT_E + o + 1] - stats[STAT_CUT_E + o];
+  const unsigned long long pos = hot ? P_o + (hot_off[x] - stats[STAT_CUT_H + o]) : E[x] - stats[STAT_CUT_E + o];
+  cursor[x] = (uint32_t)(pos + row_before[x]);
+  const bool mine = o == c.rank;
+  const uint32_t tot = row_total[x];
+  row_count[x] = mine ? tot : 0u;
+  hot_off[x] = (mine && hot) ? tot : 0ull;
+}
+
 // records per bin of the ordinary rows (the sub-bins of hot rows are counted by partition_count_kernel)
 __global__ void bin_cnt_rows_kernel(const uint32_t* __restrict__ row_count, const uint32_t* __restrict__ bin_base, int64_t A,
                                     uint32_t* __restrict__ bin_cnt) {
@@ -438,6 +480,9 @@ static PairGenParams make_pairgen(const Layout& L, const OttoCovisitSpec* spec, 
   p.weight_mode = spec->weight_mode;
   p.ts_min = spec->ts_min;
   for (int i = 0; i < 3; ++i) p.type_weight[i] = (uint32_t)spec->type_weight[i];
+  p.n_owners = 1;
+  for (int o = 0; o <= OTTO_MAX_OWNERS; ++o) p.cuts[o] = 0;
+  for (int o = 0; o < OTTO_MAX_OWNERS; ++o) p.owner_rec[o] = nullptr;
   return p;
 }
 
@@ -476,7 +521,7 @@ extern "C" int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitS
   if (S > 0) {
     PairGenParams p = make_pairgen(L, spec, workspace);
     const int64_t warps = ceil_div(S, 32);
-    pairgen_kernel<false><<<(unsigned)ceil_div(warps, PAIRGEN_WARPS), PAIRGEN_WARPS * 32, 0, st>>>(p);
+    pairgen_kernel<0><<<(unsigned)ceil_div(warps, PAIRGEN_WARPS), PAIRGEN_WARPS * 32, 0, st>>>(p);
     LAUNCH_CHECK();
   }
   // the copy that a multi-GPU host all-reduces; the rank's own counts stay in row_count
@@ -545,6 +590,104 @@ extern "C" int otto_covisit_count(const OttoEvents* ev, const OttoCovisitSpec* s
   return otto_covisit_count_finish(ev, spec, workspace, workspace_bytes, stats_host, stream);
 }
 
+static int check_plan(const OttoOwnerPlan* plan, const OttoCovisitSpec* spec, bool need_ptrs) {
+  if (!plan) { otto_set_error("owner plan is NULL"); return OTTO_EINVAL; }
+  if (plan->n_owners < 1 || plan->n_owners > OTTO_MAX_OWNERS || plan->rank < 0 || plan->rank >= plan->n_owners) {
+    otto_set_error("owner plan: n_owners must be in [1, %d] and rank below it", OTTO_MAX_OWNERS);
+    return OTTO_EINVAL;
+  }
+  if (plan->aid_cuts[0] != 0 || plan->aid_cuts[plan->n_owners] != spec->n_aids) {
+    otto_set_error("owner plan: aid_cuts must run from 0 to n_aids");
+    return OTTO_EINVAL;
+  }
+  for (int o = 0; o < plan->n_owners; ++o) {
+    if (plan->aid_cuts[o + 1] < plan->aid_cuts[o]) { otto_set_error("owner plan: aid_cuts must be non-decreasing"); return OTTO_EINVAL; }
+    if (need_ptrs && !plan->owner_records[o]) { otto_set_error("owner plan: owner_records[%d] is NULL", o); return OTTO_EINVAL; }
+  }
+  return OTTO_OK;
+}
+
+static OwnerCuts make_cuts(const OttoOwnerPlan* plan) {
+  OwnerCuts c;
+  c.n = plan->n_owners;
+  c.rank = plan->rank;
+  for (int o = 0; o <= OTTO_MAX_OWNERS; ++o) c.cut[o] = (uint32_t)plan->aid_cuts[o <= plan->n_owners ? o : plan->n_owners];
+  return c;
+}
+
+// bins from the row totals (workspace row_total = sum over ranks), the layout of MY rows, and scatter cursors that
+// point into the owners' buffers
+extern "C" int otto_covisit_count_finish_owned(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                                               int64_t workspace_bytes, const OttoOwnerPlan* plan,
+                                               const uint32_t* row_before, OttoBuildStats* stats_host, void* stream) {
+  int rc = check_spec(spec);
+  if (rc) return rc;
+  if ((rc = check_plan(plan, spec, false))) return rc;
+  if (!row_before) { otto_set_error("row_before is NULL"); return OTTO_EINVAL; }
+  const Layout L = make_layout(ev->n_sessions, ev->n_events, spec);
+  if ((rc = check_ws(L, workspace, workspace_bytes))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t A = L.A;
+  const OwnerCuts cuts = make_cuts(plan);
+  unsigned long long* stats = WS(unsigned long long, stats);
+  CUDA_TRY(cudaMemsetAsync(WS(uint32_t, bin_base), 0, (A + 2) * 4, st));
+  CUDA_TRY(cudaMemsetAsync(stats + 3, 0, 8, st));
+  // hot_off := totals of the hot rows (the "own count" input is the total here)
+  bins_count_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(
+      WS(uint32_t, row_total), WS(uint32_t, row_total), A, (uint32_t)effective_split_ub(spec), (uint32_t)sub_bin_target(spec),
+      WS(uint32_t, bin_base), WS(unsigned long long, hot_off), WS(uint32_t, hot_rows), L.Hmax, stats);
+  LAUNCH_CHECK();
+  if ((rc = exclusive_scan<uint32_t, uint32_t>(WS(uint32_t, bin_base), A, WS(uint32_t, bin_base), WS(uint32_t, scan), st)))
+    return rc;
+  if ((rc = exclusive_scan<uint32_t, unsigned long long>(WS(uint32_t, row_total), A, WS(unsigned long long, row_off),
+                                                         WS(unsigned long long, scan), st)))
+    return rc;
+  if ((rc = exclusive_scan<unsigned long long, unsigned long long>(WS(unsigned long long, hot_off), A, WS(unsigned long long, hot_off),
+                                                                   WS(unsigned long long, scan), st)))
+    return rc;
+  owner_cut_values_kernel<<<1, 32, 0, st>>>(cuts, WS(unsigned long long, row_off), WS(unsigned long long, hot_off), stats);
+  LAUNCH_CHECK();
+  init_cursor_owned_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(
+      cuts, WS(uint32_t, row_total), row_before, WS(uint32_t, bin_base), A, WS(unsigned long long, row_off),
+      WS(unsigned long long, hot_off), stats, WS(uint32_t, cursor), WS(uint32_t, row_count));
+  LAUNCH_CHECK();
+  // the local layout (my rows only) - from here on identical to a single-GPU count_finish
+  if ((rc = exclusive_scan<uint32_t, unsigned long long>(WS(uint32_t, row_count), A, WS(unsigned long long, row_off),
+                                                         WS(unsigned long long, scan), st)))
+    return rc;
+  if ((rc = exclusive_scan<unsigned long long, unsigned long long>(WS(unsigned long long, hot_off), A, WS(unsigned long long, hot_off),
+                                                                   WS(unsigned long long, scan), st)))
+    return rc;
+  count_stats_kernel<<<1, 1, 0, st>>>(WS(uint32_t, tail_off), L.S, WS(uint32_t, bin_base), A, WS(unsigned long long, row_off),
+                                      WS(unsigned long long, hot_off), stats);
+  LAUNCH_CHECK();
+  unsigned long long h[32];
+  CUDA_TRY(cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if ((int64_t)h[2] > L.Bmax || (int64_t)h[3] > L.Hmax) {
+    otto_set_error("%llu bins / %llu hot rows exceed the %lld / %lld the workspace was sized for: set spec.global_events to the "
+                   "event count of all ranks", h[2], h[3], (long long)L.Bmax, (long long)L.Hmax);
+    return OTTO_ENOSPC;
+  }
+  for (int o = 0; o < plan->n_owners; ++o) {      // the same verdict on every rank
+    const unsigned long long need = (h[STAT_CUT_E + o + 1] - h[STAT_CUT_E + o]) + (h[STAT_CUT_H + o + 1] - h[STAT_CUT_H + o]);
+    if (need >= (1ull << 32)) {
+      otto_set_error("owner %d would hold %llu pair records including its staged hot rows; the limit is 2^32 - 1 (32 GiB): use more owners", o, need);
+      return OTTO_EINVAL;
+    }
+  }
+  bins_fill_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(WS(uint32_t, bin_base), A, WS(uint32_t, bin_x));
+  LAUNCH_CHECK();
+  if (stats_host) {
+    stats_host->tail_events = (int64_t)h[0];
+    stats_host->pairs = (int64_t)h[1];
+    stats_host->bins = (int64_t)h[2];
+    stats_host->split_rows = (int64_t)h[3];
+    stats_host->hot_pairs = (int64_t)h[4];
+  }
+  return OTTO_OK;
+}
+
 extern "C" int otto_covisit_views(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
                                   int64_t workspace_bytes, uint64_t** bin_offsets, uint32_t** bin_base,
                                   uint32_t** bin_x, uint32_t** row_total) {
@@ -559,26 +702,33 @@ extern "C" int otto_covisit_views(const OttoEvents* ev, const OttoCovisitSpec* s
   return OTTO_OK;
 }
 
-// records of ordinary rows at their final positions, hot rows through the staging area into their sub-bins
-extern "C" int otto_covisit_scatter(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
-                                    int64_t workspace_bytes, void* records, int64_t records_capacity, void* stream) {
-  int rc = check_spec(spec);
-  if (rc) return rc;
-  const Layout L = make_layout(ev->n_sessions, ev->n_events, spec);
-  if ((rc = check_ws(L, workspace, workspace_bytes))) return rc;
-  if (!records && records_capacity > 0) { otto_set_error("records is NULL"); return OTTO_EINVAL; }
-  if (records_capacity >= (1ll << 32)) { otto_set_error("a rank is limited to 2^32 - 1 pair records (32 GiB); shard the sessions"); return OTTO_EINVAL; }
-  cudaStream_t st = (cudaStream_t)stream;
-  const int64_t A = L.A;
+// pair records: ordinary rows at their final positions, hot rows into the staging area.  plan == NULL: into `records`
+// (single GPU, or multi-GPU with the owners reading the slabs afterwards); else into the owners' buffers.
+static int scatter_records(const Layout& L, const OttoCovisitSpec* spec, void* workspace, void* records,
+                           const OttoOwnerPlan* plan, cudaStream_t st) {
   if (g_profile) CUDA_TRY(cudaEventRecord(g_prof_sc[0], st));
   if (L.S > 0) {
     PairGenParams p = make_pairgen(L, spec, workspace);
     p.records = (uint2*)records;
     const int64_t warps = ceil_div(L.S, 32);
-    pairgen_kernel<true><<<(unsigned)ceil_div(warps, PAIRGEN_WARPS), PAIRGEN_WARPS * 32, 0, st>>>(p);
+    if (plan) {
+      p.n_owners = plan->n_owners;
+      for (int o = 0; o <= OTTO_MAX_OWNERS; ++o) p.cuts[o] = (uint32_t)plan->aid_cuts[o <= plan->n_owners ? o : plan->n_owners];
+      for (int o = 0; o < OTTO_MAX_OWNERS; ++o) p.owner_rec[o] = (uint2*)plan->owner_records[o < plan->n_owners ? o : 0];
+      pairgen_kernel<2><<<(unsigned)ceil_div(warps, PAIRGEN_WARPS), PAIRGEN_WARPS * 32, 0, st>>>(p);
+    } else {
+      pairgen_kernel<1><<<(unsigned)ceil_div(warps, PAIRGEN_WARPS), PAIRGEN_WARPS * 32, 0, st>>>(p);
+    }
     LAUNCH_CHECK();
   }
   if (g_profile) CUDA_TRY(cudaEventRecord(g_prof_sc[1], st));
+  return OTTO_OK;
+}
+
+// records per bin; hot rows from the staging area into their aid_y-hash sub-bins; bin offsets
+static int partition_records(const Layout& L, void* workspace, void* records, cudaStream_t st) {
+  int rc;
+  const int64_t A = L.A;
   CUDA_TRY(cudaMemsetAsync(WS(uint32_t, bin_cnt), 0, (L.Bmax + 1) * 4, st));
   bin_cnt_rows_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(WS(uint32_t, row_count), WS(uint32_t, bin_base), A,
                                                                   WS(uint32_t, bin_cnt));
@@ -620,6 +770,48 @@ extern "C" int otto_covisit_scatter(const OttoEvents* ev, const OttoCovisitSpec*
     g_prof_sc_valid = true;
   }
   return OTTO_OK;
+}
+
+static int scatter_args(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes, Layout* L) {
+  int rc = check_spec(spec);
+  if (rc) return rc;
+  if (!ev) { otto_set_error("events is NULL"); return OTTO_EINVAL; }
+  *L = make_layout(ev->n_sessions, ev->n_events, spec);
+  return check_ws(*L, workspace, workspace_bytes);
+}
+
+static int check_records(void* records, int64_t records_capacity) {
+  if (!records && records_capacity > 0) { otto_set_error("records is NULL"); return OTTO_EINVAL; }
+  if (records_capacity >= (1ll << 32)) { otto_set_error("a rank is limited to 2^32 - 1 pair records (32 GiB); shard the sessions"); return OTTO_EINVAL; }
+  return OTTO_OK;
+}
+
+extern "C" int otto_covisit_scatter(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                                    int64_t workspace_bytes, void* records, int64_t records_capacity, void* stream) {
+  Layout L;
+  int rc = scatter_args(ev, spec, workspace, workspace_bytes, &L);
+  if (rc) return rc;
+  if ((rc = check_records(records, records_capacity))) return rc;
+  if ((rc = scatter_records(L, spec, workspace, records, nullptr, (cudaStream_t)stream))) return rc;
+  return partition_records(L, workspace, records, (cudaStream_t)stream);
+}
+
+extern "C" int otto_covisit_scatter_owned(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                                          int64_t workspace_bytes, const OttoOwnerPlan* plan, void* stream) {
+  Layout L;
+  int rc = scatter_args(ev, spec, workspace, workspace_bytes, &L);
+  if (rc) return rc;
+  if ((rc = check_plan(plan, spec, true))) return rc;
+  return scatter_records(L, spec, workspace, nullptr, plan, (cudaStream_t)stream);
+}
+
+extern "C" int otto_covisit_partition(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                                      int64_t workspace_bytes, void* records, int64_t records_capacity, void* stream) {
+  Layout L;
+  int rc = scatter_args(ev, spec, workspace, workspace_bytes, &L);
+  if (rc) return rc;
+  if ((rc = check_records(records, records_capacity))) return rc;
+  return partition_records(L, workspace, records, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ reduce
@@ -907,6 +1099,11 @@ extern "C" int otto_covisit_merge_segments(const OttoPairSegment* segments_host,
 
 extern "C" int otto_peer_alloc(int64_t bytes, void** ptr_host) {
   if (bytes <= 0 || !ptr_host) { otto_set_error("bad argument"); return OTTO_EINVAL; }
+  // The size is rounded up to a multiple of 32 MiB.  Measured on this pool's B200s (profiles/r01_microbench_peer.txt):
+  // a peer that maps an IPC-exported cudaMalloc allocation whose size is NOT a multiple of 2 MiB reaches it through
+  // small pages; scattered 64-byte stores over a 6.2 GB buffer then run at 6 GB/s instead of 313 GB/s (TLB misses
+  // on every run), which made the owner-direct scatter 35x slower than the link allows.
+  bytes = (bytes + (32ll << 20) - 1) & ~((32ll << 20) - 1);
   const cudaError_t e = cudaMalloc(ptr_host, (size_t)bytes);
   if (e != cudaSuccess) {
     size_t free_b = 0, total_b = 0;

@@ -48,6 +48,12 @@ struct PairGenParams {
   int32_t weight_mode;
   int32_t ts_min;
   uint32_t type_weight[3];
+  // MODE 2 (owner-direct scatter, multi-GPU): row x belongs to owner o with cuts[o] <= x < cuts[o + 1]; its records
+  // go to owner_rec[o] (the owner's record buffer mapped into this process, NVLink stores) at the slot the cursor
+  // holds, which the host derived from the all-gathered row counts
+  int32_t n_owners;
+  uint32_t cuts[OTTO_MAX_OWNERS + 1];
+  uint2* owner_rec[OTTO_MAX_OWNERS];
 };
 
 constexpr int PAIRGEN_WARPS = 8;
@@ -66,8 +72,10 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x) {
   return x;
 }
 
-template <bool SCATTER>
+// MODE 0: count pass, 1: scatter into p.records, 2: scatter into the owners' buffers
+template <int MODE>
 __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairGenParams p) {
+  constexpr bool SCATTER = MODE != 0;
   const uint32_t lane = lane_id();
   const uint32_t lt = lanemask_lt();
   const int64_t warp = (int64_t)blockIdx.x * PAIRGEN_WARPS + (threadIdx.x >> 5);
@@ -165,6 +173,13 @@ __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairG
       const uint32_t cnt = __popc(mywm);
       uint32_t slot = 0;
       if (active && cnt) slot = atomicAdd(&p.cursor[aid], cnt);
+      uint2* dst = p.records;
+      if (MODE == 2) {
+        dst = p.owner_rec[0];
+#pragma unroll
+        for (int g = 1; g < OTTO_MAX_OWNERS; ++g)
+          if (g < p.n_owners && aid >= p.cuts[g]) dst = p.owner_rec[g];
+      }
       uint32_t v = 1;
       if (p.weight_mode == OTTO_WEIGHT_TYPE) v = ty == 0 ? p.type_weight[0] : (ty == 1 ? p.type_weight[1] : p.type_weight[2]);
       const bool time_mode = p.weight_mode == OTTO_WEIGHT_TIME;
@@ -175,7 +190,9 @@ __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairG
         const uint32_t wmi = __shfl_sync(FULL_MASK, mywm, src);
         const uint32_t sloti = __shfl_sync(FULL_MASK, slot, src);
         const uint32_t val = time_mode ? (uint32_t)__shfl_sync(FULL_MASK, tv, src) : v;
-        if ((wmi >> lane) & 1u) st_stream_u2(p.records + (sloti + __popc(wmi & lt)), make_uint2(aid, val));
+        uint2* dsti = p.records;
+        if (MODE == 2) dsti = (uint2*)__shfl_sync(FULL_MASK, (unsigned long long)dst, src);
+        if ((wmi >> lane) & 1u) st_stream_u2(dsti + (sloti + __popc(wmi & lt)), make_uint2(aid, val));
       }
     }
   }

@@ -12,7 +12,18 @@ exchanged by one all-to-all keyed on aid_x ownership.
     reduce       (accumulate + top-k over the G received segments of my aid range)
                                              broadcast   each owner's rows (gather_table) for candidate-gen
 
-Every rank forms the same bins (the upper bounds are all-reduced before bins exist) and the accumulators are
+Owner-direct variant (default on one NVLink box, `GpuRankBackend(peer=...)`): the exchange is fused into the
+scatter kernel.  The per-row pair counts are all-gathered, so every rank knows the owner of each aid_x row and the
+position of its own run inside the owner's record buffer; the scatter kernel stores each record straight into that
+buffer through the peer mapping (NVLink writes), and everything behind it - partition of the hot rows, accumulate,
+top-k - is local to the owner and identical to a single-GPU build of the owner's rows:
+
+    count_begin                              all-gather  row counts [G, A] uint32 -> totals, counts of lower ranks
+    count_finish_owned (bins, my layout, cursors into the owners' buffers)
+    scatter_owned (records -> owners' HBM)   all-reduce  1 element: "every scatter has landed"
+    partition + reduce (one local segment)
+
+Every rank forms the same bins (the row totals are reduced before bins exist) and the accumulators are
 integers, so the G-GPU table equals the 1-GPU table byte for byte.  The reference has no distributed code
 (SURVEY.md §2.1); its only partitioning is the aid_x-range "part" files, which is what ownership mirrors.
 
@@ -125,6 +136,24 @@ class GpuRankBackend:
         records = self.b.scatter()
         return records, self.b.views()["bin_offsets"]
 
+    # -- owner-direct scatter: records go straight into the owner's peer-mapped buffer -----------
+    @property
+    def owner_direct(self) -> bool:
+        return (self.peer is not None and os.environ.get("OTTO_OWNER_DIRECT", "1") != "0"
+                and dist.is_initialized() and 1 < dist.get_world_size(self.peer.group) <= N.MAX_OWNERS)
+
+    def count_finish_owned(self, aid_cuts, rank, row_before):
+        stats = self.b.count_finish_owned(aid_cuts, rank, row_before)
+        return stats, self.b.views()["bin_base"]
+
+    def scatter_owned(self, aid_cuts, rank) -> None:
+        self.b.records = self.peer.ensure(int(self.b.stats.pairs) + int(self.b.stats.hot_pairs))     # collective
+        self.b.scatter_owned(aid_cuts, rank, self.peer.peers)
+
+    def partition(self):
+        records = self.b.partition()
+        return records, self.b.views()["bin_offsets"]
+
     def reduce(self, segments, bin_lo, bin_hi, aid_lo, aid_hi) -> TopKTable:
         # one run per bin for the reduce kernels once a bin is spread over more than two senders (with two the extra
         # copy of the merge costs more than the second run per bin)
@@ -160,6 +189,55 @@ def plan_owners(bin_counts: torch.Tensor, bin_base: torch.Tensor, world: int) ->
     return OwnerPlan(aid_cuts, bin_cuts)
 
 
+def plan_rows(row_total: torch.Tensor, world: int) -> list:
+    """aid cuts [G + 1] from the pairs per aid_x row (int64): contiguous ranges with (nearly) equal pair counts."""
+    A = row_total.numel()
+    before_aid = torch.zeros(A + 1, dtype=torch.int64, device=row_total.device)
+    torch.cumsum(row_total, 0, out=before_aid[1:])
+    total = int(before_aid[-1].item())
+    targets = torch.tensor([total * g // world for g in range(1, world)], dtype=torch.int64, device=row_total.device)
+    inner = torch.searchsorted(before_aid, targets, right=False).clamp_(0, A).tolist() if world > 1 else []
+    aid_cuts = [0] + [int(x) for x in inner] + [A]
+    for i in range(1, len(aid_cuts)):                              # keep the cuts monotone
+        aid_cuts[i] = max(aid_cuts[i], aid_cuts[i - 1])
+    return aid_cuts
+
+
+def _build_owner_direct(backend, group, mark, world: int, rank: int):
+    """The exchange fused into the scatter: records are stored straight into the owner's buffer (module docstring)."""
+    local = backend.count_begin()                                   # int32 view of this rank's uint32 row counts
+    mark("count_begin")
+    every = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(every, local, group=group)
+    counts = torch.stack(every).to(torch.int64) & 0xFFFFFFFF       # [G, A]
+    total = counts.sum(0)
+    if int(total.max().item()) >= 2 ** 32:
+        raise ValueError("an aid_x row holds 2^32 or more pairs")
+    before = counts[:rank].sum(0).to(torch.int32)                  # wraps into the uint32 bit pattern
+    sent = int(counts[rank].sum().item())
+    local.copy_(total.to(torch.int32))                             # the workspace's row_total: totals over all ranks
+    aid_cuts = plan_rows(total, world)
+    mark("allgather_rows+plan")
+    stats, bin_base = backend.count_finish_owned(aid_cuts, rank, before)
+    mark("count_finish")
+    backend.scatter_owned(aid_cuts, rank)
+    # "every rank's records have landed": a rank's part of this collective is ordered behind its scatter kernel
+    landed = torch.zeros(1, dtype=torch.int32, device=local.device)
+    dist.all_reduce(landed, group=group)
+    mark("scatter")
+    records, bin_off = backend.partition()
+    mark("partition")
+    bin_cuts = [int(v) for v in bin_base.to(torch.int64)[torch.tensor(aid_cuts, device=bin_base.device)].tolist()]
+    plan = OwnerPlan(aid_cuts, bin_cuts)
+    lo, hi = bin_cuts[rank], bin_cuts[rank + 1]
+    table = backend.reduce([(records, bin_off[lo:hi + 1])], lo, hi, aid_cuts[rank], aid_cuts[rank + 1])
+    mark("merge+reduce")
+    out_stats = dict(backend.stats())
+    out_stats["owned_aids"] = aid_cuts[rank + 1] - aid_cuts[rank]
+    out_stats["sent_records"] = sent
+    return table, (aid_cuts[rank], aid_cuts[rank + 1]), out_stats, plan
+
+
 def build_topk_distributed(backend, group=None, timing: dict | None = None):
     """All ranks call this with their own session shard.  Returns (table, (aid_lo, aid_hi), stats, plan): rows
     [aid_lo, aid_hi) of `table` are final on this rank."""
@@ -175,6 +253,8 @@ def build_topk_distributed(backend, group=None, timing: dict | None = None):
             timing[name] = timing.get(name, 0.0) + (now - t_last[0]) * 1e3
             t_last[0] = now
     mark("start")
+    if world > 1 and getattr(backend, "owner_direct", False):
+        return _build_owner_direct(backend, group, mark, world, rank)
     ub = backend.count_begin()
     mark("count_begin")
     if world > 1:

@@ -74,7 +74,75 @@ class NumpyRankBackend:
         return {}
 
 
-def _worker(rank, world, port, split_ub, out):
+class NumpyOwnerBackend(NumpyRankBackend):
+    """Stand-in for the owner-direct scatter: "storing into the owner's buffer" is an object all-gather of
+    (position, record) lists that every owner applies to its own array."""
+    owner_direct = True
+
+    def count_finish_owned(self, aid_cuts, rank, row_before):
+        stats, bin_base = self.count_finish()                       # bins from the totals (self.total was summed in place)
+        tot = self.total.numpy().astype(np.int64)
+        cuts = np.asarray(aid_cuts)
+        self.owner = np.searchsorted(cuts, np.arange(self.n_aids), side="right") - 1
+        self.owner = np.minimum(self.owner, len(aid_cuts) - 2)
+        hot = self.nb > 1
+        E = np.concatenate([[0], np.cumsum(tot)])
+        Hs = np.concatenate([[0], np.cumsum(np.where(hot, tot, 0))])
+        P = E[cuts[1:]] - E[cuts[:-1]]
+        H = Hs[cuts[1:]] - Hs[cuts[:-1]]
+        o = self.owner
+        pos = np.where(hot, P[o] + Hs[:-1] - Hs[cuts[o]], E[:-1] - E[cuts[o]])
+        self.cursor = pos + row_before.numpy().astype(np.int64)
+        self.rank, self.P_mine, self.H_mine = rank, int(P[rank]), int(H[rank])
+        mine = o == rank
+        self.lay = np.where(mine, tot, 0)
+        self.lay_off = np.concatenate([[0], np.cumsum(self.lay)])
+        self.lay_hot = np.concatenate([[0], np.cumsum(np.where(mine & hot, tot, 0))])
+        stats["pairs"], stats["hot_pairs"] = self.P_mine, self.H_mine
+        return stats, bin_base
+
+    def scatter_owned(self, aid_cuts, rank):
+        x, y = self.pairs["aid_x"].to_numpy().astype(np.int64), self.pairs["aid_y"].to_numpy().astype(np.int64)
+        order = np.argsort(x, kind="stable")
+        x, y = x[order], y[order]
+        first = np.concatenate([[0], np.cumsum(np.bincount(x, minlength=self.n_aids))])
+        at = self.cursor[x] + (np.arange(len(x)) - first[x])        # my run of a row is contiguous behind the lower ranks'
+        rec = (y | (np.ones_like(y) << 32)).astype(np.int64)
+        world = len(aid_cuts) - 1
+        outbox = [(at[self.owner[x] == o], rec[self.owner[x] == o]) for o in range(world)]
+        inbox = [None] * world
+        dist.all_gather_object(inbox, outbox)
+        self.buf = np.full(self.P_mine + self.H_mine, -1, dtype=np.int64)
+        for sender in inbox:
+            pos, r = sender[rank]
+            assert (self.buf[pos] == -1).all(), "two ranks wrote the same slot"
+            self.buf[pos] = r
+        # the only empty slots are the final positions of the hot rows (filled from the staging area by partition)
+        assert int((self.buf == -1).sum()) == self.H_mine, "the owners' layout has holes"
+
+    def partition(self):
+        B = int(self.bin_base[-1])
+        cnt = np.zeros(B, dtype=np.int64)
+        parts = {}
+        for xrow in np.nonzero(self.lay)[0]:
+            n, b0, nb = self.lay[xrow], self.bin_base[xrow], self.nb[xrow]
+            if nb == 1:
+                cnt[b0] = n
+                parts[b0] = self.buf[self.lay_off[xrow]:self.lay_off[xrow] + n]
+            else:
+                st = self.P_mine + self.lay_hot[xrow]
+                r = self.buf[st:st + n]
+                sub = _sub_bin(r & 0xFFFFFFFF, np.full(n, nb)).astype(np.int64)
+                for j in range(nb):
+                    parts[b0 + j] = r[sub == j]
+                    cnt[b0 + j] = len(parts[b0 + j])
+        self.bin_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+        self.rec = np.concatenate([parts[b] for b in sorted(parts)]) if parts else np.zeros(0, dtype=np.int64)
+        assert len(self.rec) == self.P_mine
+        return torch.from_numpy(self.rec), torch.from_numpy(self.bin_off)
+
+
+def _worker(rank, world, port, split_ub, out, owner_direct=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from otto_multi_objective_recommender_system_b200 import distributed, synth
@@ -83,7 +151,7 @@ def _worker(rank, world, port, split_ub, out):
     sessions = np.sort(df["session"].unique())
     mine = sessions[rank * len(sessions) // world:(rank + 1) * len(sessions) // world]     # contiguous session chunk
     spec = co.OracleSpec(co.WEIGHT_UNIT, k=7)
-    backend = NumpyRankBackend(df.loc[df["session"].isin(mine)], spec, 80, split_ub)
+    backend = (NumpyOwnerBackend if owner_direct else NumpyRankBackend)(df.loc[df["session"].isin(mine)], spec, 80, split_ub)
     table, (lo, hi), stats, plan = distributed.build_topk_distributed(backend)
     assert table["aid_x"].between(lo, hi - 1).all()
     gathered = [None] * world
@@ -96,22 +164,36 @@ def _worker(rank, world, port, split_ub, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("split_ub", [1 << 30, 40])
-def test_two_rank_exchange_equals_single_process(split_ub):
+@pytest.mark.parametrize("world,split_ub,owner_direct", [(2, 1 << 30, False), (2, 40, False), (2, 1 << 30, True), (2, 40, True),
+                                                        (3, 40, True)])
+def test_multi_rank_exchange_equals_single_process(world, split_ub, owner_direct):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, split_ub, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, split_ub, out, owner_direct)) for r in range(world)]
     for p in procs:
         p.start()
     got, want, cuts = out.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert cuts[0] == cuts[1], "every rank must derive the same ownership plan"
+    assert all(c == cuts[0] for c in cuts), "every rank must derive the same ownership plan"
     assert got["aid_x"] == want["aid_x"] and got["aid_y"] == want["aid_y"] and got["wgt"] == want["wgt"]
+
+
+def test_plan_rows_balances_skewed_rows():
+    from otto_multi_objective_recommender_system_b200 import distributed
+    rows = torch.tensor([1000, 1, 1, 1, 500, 500, 1, 1], dtype=torch.int64)
+    assert distributed.plan_rows(rows, 1) == [0, 8]
+    cuts = distributed.plan_rows(rows, 2)
+    assert cuts[0] == 0 and cuts[-1] == 8 and cuts == sorted(cuts)
+    left = int(rows[:cuts[1]].sum())
+    assert abs(left - 1002) <= 1000                                  # a cut never splits a row
+    c8 = distributed.plan_rows(rows, 8)
+    assert len(c8) == 9 and c8 == sorted(c8) and c8[0] == 0 and c8[-1] == 8
+    assert distributed.plan_rows(torch.zeros(5, dtype=torch.int64), 3) == [0, 0, 0, 5]
 
 
 def test_plan_owners_balances_skewed_rows():

@@ -8,8 +8,11 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, variant, split_ub, n_sessions, n_aids, use_peer):
+def _worker(rank, world, port, variant, split_ub, n_sessions, n_aids, transport):
     import torch.distributed as dist
+    # owner_direct: NVLink stores from the scatter kernel; peer_read: owners read the senders' slabs; nccl: all-to-all
+    use_peer = transport != "nccl"
+    os.environ["OTTO_OWNER_DIRECT"] = "1" if transport == "owner_direct" else "0"
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -23,6 +26,7 @@ def _worker(rank, world, port, variant, split_ub, n_sessions, n_aids, use_peer):
     shard = csr.slice_sessions(rank * S // world, (rank + 1) * S // world)
     peer = distributed.PeerRecords(dev) if use_peer else None     # NVLink peer memory vs NCCL all-to-all
     backend = distributed.GpuRankBackend(shard, spec, exact=True, peer=peer)
+    assert backend.owner_direct == (transport == "owner_direct")
     table, (lo, hi), stats, plan = distributed.build_topk_distributed(backend)
     distributed.gather_table(table, plan)
     single, sstats = covisit.build_topk(csr, spec, exact=True)
@@ -38,13 +42,13 @@ def _worker(rank, world, port, variant, split_ub, n_sessions, n_aids, use_peer):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("use_peer", [True, False])
+@pytest.mark.parametrize("transport", ["owner_direct", "peer_read", "nccl"])
 @pytest.mark.parametrize("variant,split_ub", [("CLICKS", 0), ("CARTS_ORDERS", 64), ("BUY2BUY", 0)])
-def test_multi_gpu_equals_single_gpu(native_lib, variant, split_ub, use_peer):
+def test_multi_gpu_equals_single_gpu(native_lib, variant, split_ub, transport):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    torch.multiprocessing.spawn(_worker, args=(world, port, variant, split_ub, 20000, 2500, use_peer), nprocs=world, join=True)
+    torch.multiprocessing.spawn(_worker, args=(world, port, variant, split_ub, 20000, 2500, transport), nprocs=world, join=True)
