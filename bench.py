@@ -373,8 +373,11 @@ def run_b200(args):
         roofline = {"bound": "hbm", "kernel": "whole build (phases interleave with collectives)", "achieved":
                     whole["achieved_per_gpu"], "peak": peak, "unit": "GB/s", "frac": whole["frac"], "traffic": None,
                     "peak_source": peak_src, "algorithmic_bytes": bytes_all,
-                    "exchange": {"all_to_all_bytes_total": sent, "per_gpu_per_step": sent / world,
-                                 "note": "upper bound: includes the slab a rank keeps for itself"}}
+                    "exchange": {"transport": ("nccl all_to_all" if args.nccl_exchange else "peer read (owners read the senders' slabs over NVLink)"
+                                               if not backend.owner_direct else
+                                               "owner-direct scatter (records stored into the owner's buffer over NVLink)"),
+                                 "record_bytes_total": sent, "per_gpu_per_step": sent / world,
+                                 "note": "upper bound: includes the records a rank keeps for itself"}}
 
     # ---- end to end from pinned host columns ----
     e2e = None
