@@ -43,6 +43,46 @@ class CovisitSpec:
                                  self.tail_n, self.k, self.ts_min, self.ts_max, self.split_ub, self.global_events)
 
 
+    _MODES = {"time": N.WEIGHT_TIME, "type": N.WEIGHT_TYPE, "unit": N.WEIGHT_UNIT}
+
+    @classmethod
+    def from_dict(cls, d: dict) -> "CovisitSpec":
+        """Recipe from a plain mapping (configs/*.json): weight = time | type | unit plus any field of the spec."""
+        d = dict(d)
+        mode = d.pop("weight", "time")
+        if mode not in cls._MODES:
+            raise ValueError(f"weight must be one of {sorted(cls._MODES)}, got {mode!r}")
+        allowed = {"type_weight", "event_types", "x_types", "y_types", "window_s", "tail_n", "k", "ts_min", "ts_max", "split_ub"}
+        unknown = set(d) - allowed
+        if unknown:
+            raise ValueError(f"unknown recipe keys: {sorted(unknown)}")
+        for key in ("type_weight", "event_types", "x_types", "y_types"):
+            if key in d:
+                d[key] = tuple(int(v) for v in d[key])
+                if key != "type_weight" and not set(d[key]) <= {0, 1, 2}:
+                    raise ValueError(f"{key} must be a subset of [0, 1, 2]")
+        if "type_weight" in d and len(d["type_weight"]) != 3:
+            raise ValueError("type_weight needs three entries: clicks, carts, orders")
+        return cls(weight_mode=cls._MODES[mode], **d)
+
+
+def load_stem_recipes(path) -> dict:
+    """{stem: CovisitSpec} from a JSON file (configs/unpinned_stems.example.json); keys starting with '_' are comments.
+    Stems must be file stems the readers know (covisitation/inference.py:87-111)."""
+    import json
+    from .candidates import STEMS
+    with open(path) as f:
+        raw = json.load(f)
+    out = {}
+    for stem, recipe in raw.items():
+        if stem.startswith("_"):
+            continue
+        if stem not in STEMS:
+            raise ValueError(f"unknown matrix stem {stem!r}; the readers load {STEMS}")
+        out[stem] = CovisitSpec.from_dict(recipe)
+    return out
+
+
 CLICKS = CovisitSpec(N.WEIGHT_TIME, k=20)                                  # stem "time_weighted"
 CARTS_ORDERS = CovisitSpec(N.WEIGHT_TYPE, type_weight=(1, 6, 3), k=15)     # stem "cart_weighted"
 BUY2BUY = CovisitSpec(N.WEIGHT_UNIT, event_types=(1, 2), window_s=14 * 86400, k=15)   # stem "cart_order"

@@ -1,6 +1,6 @@
 """CLI twin of src/covisitation/inference.py for the covisitation branch, on one B200.
 
-    python -m otto_multi_objective_recommender_system_b200.inference {validation|submission} --data DIR [--build]
+    python -m otto_multi_objective_recommender_system_b200.inference {validation|submission} --data DIR [--build [--stems FILE.json]]
 
 Mirrors the reference script's file contract (covisitation/inference.py:44-52,76-131,251-267,437-447):
   validation  reads  DIR/splits/val.parquet (+ val_labels.parquet), DIR/aid_frequencies/train_20_most_frequent_*,
@@ -11,7 +11,9 @@ Mirrors the reference script's file contract (covisitation/inference.py:44-52,76
               writes DIR/submissions/covisitation_submission.csv.gz
   any other mode raises ValueError('Invalid mode'), like the reference.
 --build first builds the three graded matrices (the builder the reference ships without) from
-train ∪ val (validation) or train ∪ test (submission) and writes the part files.
+train ∪ val (validation) or train ∪ test (submission) and writes the part files; --stems adds the stems whose
+recipes the reference does not reveal (click_weighted, order_weighted, click_cart, click_order) from a recipe file, so
+that all seven tables the reference script loads (:87-111) exist.
 Difference, stated: the fastText / Annoy neighbour terms (:165-170, :223-224) are not on this path (no model
 offline).  Sessions with >= 20 unique aids take the recency-weight branch (:128-131, :142-199) like the reference.
 """
@@ -34,7 +36,7 @@ def _first_existing(*paths):
     raise FileNotFoundError(" | ".join(str(p) for p in paths))
 
 
-def build_matrices(data: pathlib.Path, mode: str, n_aids: int | None, device) -> dict:
+def build_matrices(data: pathlib.Path, mode: str, n_aids: int | None, device, extra_stems: dict | None = None) -> dict:
     if mode == "validation":
         frame = io.read_event_frame(data / "splits" / "train.parquet", data / "splits" / "val.parquet", n_aids=n_aids)
     else:
@@ -42,7 +44,7 @@ def build_matrices(data: pathlib.Path, mode: str, n_aids: int | None, device) ->
                                     _first_existing(data / "test.pkl", data / "splits" / "test.parquet"), n_aids=n_aids)
     csr = covisit.ingest(frame, "desc", device=device)
     tables = {}
-    for stem, spec in covisit.VARIANTS.items():
+    for stem, spec in {**covisit.VARIANTS, **(extra_stems or {})}.items():
         tables[stem], stats = covisit.build_topk(csr, spec)
         io.write_topk_parts(tables[stem], data / "covisitation" / mode, stem, io.n_parts_for(stem, mode), 15, k=15)
         logging.info(f"built {stem}: {stats}")
@@ -82,6 +84,8 @@ def main(argv=None) -> dict:
     ap.add_argument("mode", type=str)
     ap.add_argument("--data", type=pathlib.Path, required=True)
     ap.add_argument("--build", action="store_true")
+    ap.add_argument("--stems", type=pathlib.Path, default=None,
+                    help="JSON recipes of further matrix stems to build (configs/unpinned_stems.example.json)")
     ap.add_argument("--n-aids", type=int, default=None)
     ap.add_argument("--device", default="cuda:0")
     args = ap.parse_args(argv)
@@ -96,7 +100,8 @@ def main(argv=None) -> dict:
     else:
         test_frame = io.read_event_frame(_first_existing(data / "test.pkl", data / "splits" / "test.parquet"), n_aids=args.n_aids)
         popular = io.read_popular(data / "aid_frequencies", "all")
-    built = build_matrices(data, mode, args.n_aids, dev) if args.build else None
+    extra = covisit.load_stem_recipes(args.stems) if args.stems else None
+    built = build_matrices(data, mode, args.n_aids, dev, extra) if args.build else None
     n_aids = max([test_frame.n_aids] + ([t.n_aids for t in built.values()] if built else [])) if args.n_aids is None else args.n_aids
     del built
     # always consume the part files (15 rows per aid), exactly what the reference script reads

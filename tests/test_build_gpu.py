@@ -166,6 +166,15 @@ def test_generic_spec_type_masks(cv):
     check_against_oracle(cv, frame, spec, "clicks+carts tail 12 1h")
 
 
+def test_unpinned_stem_recipes_build_like_the_oracle(cv):
+    """configs/unpinned_stems.example.json: the four stems without a known recipe go through the same kernels."""
+    recipes = cv.load_stem_recipes(pathlib.Path(__file__).resolve().parents[1] / "configs" / "unpinned_stems.example.json")
+    assert sorted(recipes) == ["click_cart", "click_order", "click_weighted", "order_weighted"]
+    frame = synth_frame(3000, 200, seed=23)
+    for stem, spec in recipes.items():
+        check_against_oracle(cv, frame, spec, f"recipe {stem}")
+
+
 def test_empty_and_tiny_inputs(cv):
     df = pd.DataFrame({"session": [5], "aid": [3], "ts": [1659304800], "type": [0]})
     got, stats, table = run_build(cv, frame_from_df(df, 8), cv.CLICKS)
