@@ -343,6 +343,16 @@ int64_t otto_recency_scratch_bytes(int32_t max_session_len, int32_t max_table_k)
 int otto_recency_long(const OttoSessions* sessions, const int32_t* session_list, int32_t n_list, int32_t max_session_len,
                       const OttoRecencySpec* spec, void* scratch, int64_t scratch_bytes, int32_t* pred, void* stream);
 
+/* The same ranking with its weights, for the recency-weighted candidate generator
+ * (ranker/recency_weighted_candidate_generator.py:61-105: type coefficients {0: 1, 1: 6, 2: 1}, no covisitation bonus
+ * (all tables NULL), every unique aid of the session kept: n >= the longest session of the list).
+ * rows_by_list != 0: row i of the outputs belongs to session_list[i] (outputs are [3][n_list][n]); else rows are
+ * session indices ([3][n_sessions][n]) and only the listed rows are written.  score (fp64, bit-exact against the
+ * Python Counter) and len ([3][rows]) are optional; entries beyond len are -1 / 0.0. */
+int otto_recency_scored(const OttoSessions* sessions, const int32_t* session_list, int32_t n_list, int32_t max_session_len,
+                        const OttoRecencySpec* spec, void* scratch, int64_t scratch_bytes, int32_t rows_by_list, int32_t* pred,
+                        double* score, int32_t* len, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -118,6 +118,47 @@ def recency_predictions(session_aids, session_event_types, tables, n: int = 20):
     return [sorted_click_aids, sorted_cart_aids, sorted_order_aids]
 
 
+def recency_weighted_candidates(session_aids, session_event_types):
+    """One session of ranker/recency_weighted_candidate_generator.py:61-93 (= :169-201 for the test set), statement
+    for statement: -> [(aids, weights)] for click, cart, order; every unique aid of the session, weight desc."""
+    event_type_coefficient = {0: 1, 1: 6, 2: 1}                                             # :25
+    session_unique_aids = list(dict.fromkeys(session_aids[::-1]))
+    click_recency_weights = np.logspace(0.1, 1, len(session_aids), base=2, endpoint=True) - 1
+    cart_recency_weights = np.logspace(0.5, 1, len(session_aids), base=2, endpoint=True) - 1
+    order_recency_weights = np.logspace(0.5, 1, len(session_aids), base=2, endpoint=True) - 1
+    session_aid_click_weights = Counter()
+    session_aid_cart_weights = Counter()
+    session_aid_order_weights = Counter()
+    for aid, event_type, cw, kw, ow in zip(session_aids, session_event_types, click_recency_weights, cart_recency_weights, order_recency_weights):
+        session_aid_click_weights[aid] += (cw * event_type_coefficient[event_type])
+        session_aid_cart_weights[aid] += (kw * event_type_coefficient[event_type])
+        session_aid_order_weights[aid] += (ow * event_type_coefficient[event_type])
+    out = []
+    for counter in (session_aid_click_weights, session_aid_cart_weights, session_aid_order_weights):
+        ranked = counter.most_common(len(session_unique_aids))
+        out.append(([aid for aid, weight in ranked], [weight for aid, weight in ranked]))
+    return out
+
+
+def recency_weighted_frame(df_events: pd.DataFrame) -> dict:
+    """All sessions -> the exploded frames the script pickles (:117-144): session, candidates uint64,
+    candidate_scores float32."""
+    sess = session_lists(df_events)
+    rows = {"click": [], "cart": [], "order": []}
+    for t in sess.itertuples():
+        res = recency_weighted_candidates(list(t.aid), list(t.type))
+        for name, (aids, weights) in zip(("click", "cart", "order"), res):
+            rows[name].extend((t.session, a, w) for a, w in zip(aids, weights))
+    out = {}
+    for name, r in rows.items():
+        f = pd.DataFrame(r, columns=["session", "candidates", "candidate_scores"])
+        f["candidates"] = f["candidates"].astype(np.uint64)
+        f["candidate_scores_f64"] = f["candidate_scores"].astype(np.float64)
+        f["candidate_scores"] = f["candidate_scores"].astype(np.float32)
+        out[name] = f
+    return out
+
+
 def ranker_frame(df_events: pd.DataFrame, tables: dict, n: int = 100) -> dict:
     """All sessions -> the three exploded candidate frames the ranker script pickles (:177-197 / :290-307):
     columns session, candidates uint64, candidate_scores float32."""

@@ -123,6 +123,7 @@ _SIGNATURES = {
     "otto_candidates": (C.c_int, [P(OttoSessions), i32, P(OttoCandidateSpec), vp, i64, P(OttoCandidates), vp]),
     "otto_recency_scratch_bytes": (i64, [i32, i32]),
     "otto_recency_long": (C.c_int, [P(OttoSessions), vp, i32, i32, P(OttoRecencySpec), vp, i64, vp, vp]),
+    "otto_recency_scored": (C.c_int, [P(OttoSessions), vp, i32, i32, P(OttoRecencySpec), vp, i64, i32, vp, vp, vp, vp]),
     "otto_assemble_predictions": (C.c_int, [P(OttoSessions), P(OttoCandidates), i32, i32, vp, i32, i32, vp, vp, vp]),
 }
 

@@ -36,7 +36,11 @@ struct RecencyParams {
   const double* w_cart;
   const int64_t* w_offset;    // [max_len + 1]
   int32_t n;                  // predictions per target (20)
-  int32_t* pred;              // [3][n_sessions][n]
+  int32_t* pred;              // [3][rows][n]; row = session index, or position in `list` when rows_by_list
+  double* score;              // optional [3][rows][n]: the weights of pred
+  int32_t* out_len;           // optional [3][rows]: entries written (the rest is -1 / 0.0)
+  int64_t rows;
+  int32_t rows_by_list;
   // scratch slab per block
   uint64_t* slab;
   int64_t slab_words;
@@ -215,9 +219,17 @@ __global__ void __launch_bounds__(256) recency_long_kernel(const RecencyParams p
         w.pos[i] = u >= 0 ? (uint32_t)u : (uint32_t)U + w.first[h];
       }
       __syncthreads();
-      // most_common(n): n rounds of (weight desc, insertion asc) selection; weights are positive doubles
-      int32_t* out = p.pred + ((int64_t)tg * p.n_sessions + s) * p.n;
-      for (int r = 0; r < p.n; ++r) {
+      // most_common(n): min(n, entries) rounds of (weight desc, insertion asc) selection; weights are positive doubles
+      const int64_t row = p.rows_by_list ? (int64_t)item : s;
+      int32_t* out = p.pred + ((int64_t)tg * p.rows + row) * p.n;
+      double* out_score = p.score ? p.score + ((int64_t)tg * p.rows + row) * p.n : nullptr;
+      const int rounds = d < p.n ? d : p.n;
+      for (int r = rounds + tid; r < p.n; r += T) {
+        out[r] = -1;
+        if (out_score) out_score[r] = 0.0;
+      }
+      if (tid == 0 && p.out_len) p.out_len[(int64_t)tg * p.rows + row] = rounds;
+      for (int r = 0; r < rounds; ++r) {
         unsigned long long bv = 0;
         uint32_t bp = 0xffffffffu, bi = 0xffffffffu;
         for (int i = tid; i < d; i += T) {
@@ -240,6 +252,7 @@ __global__ void __launch_bounds__(256) recency_long_kernel(const RecencyParams p
               v = s_best_v[k]; ps = s_best_p[k]; ix = s_best_i[k];
             }
           out[r] = ix == 0xffffffffu ? -1 : (int32_t)w.keys[w.occ[ix]];
+          if (out_score) out_score[r] = ix == 0xffffffffu ? 0.0 : __longlong_as_double((long long)v);
           if (ix != 0xffffffffu) w.pos[ix] = 0xffffffffu;     // taken
         }
         __syncthreads();
@@ -276,11 +289,12 @@ extern "C" int64_t otto_recency_scratch_bytes(int32_t max_session_len, int32_t m
   return RECENCY_BLOCKS * recency_slab_words(lcap, hs) * 8 + 256;
 }
 
-extern "C" int otto_recency_long(const OttoSessions* sessions, const int32_t* session_list, int32_t n_list,
-                                 int32_t max_session_len, const OttoRecencySpec* spec, void* scratch, int64_t scratch_bytes,
-                                 int32_t* pred, void* stream) {
+extern "C" int otto_recency_scored(const OttoSessions* sessions, const int32_t* session_list, int32_t n_list,
+                                   int32_t max_session_len, const OttoRecencySpec* spec, void* scratch, int64_t scratch_bytes,
+                                   int32_t rows_by_list, int32_t* pred, double* score, int32_t* len, void* stream) {
   if (!sessions || !spec || !pred) { otto_set_error("NULL argument"); return OTTO_EINVAL; }
   if (n_list <= 0) return OTTO_OK;
+  if (!session_list) { otto_set_error("session_list is NULL"); return OTTO_EINVAL; }
   if (spec->n < 1 || spec->n > 4096) { otto_set_error("n must be in [1, 4096]"); return OTTO_EINVAL; }
   int max_k = 1;
   for (int t = 0; t < 3; ++t) {
@@ -311,6 +325,10 @@ extern "C" int otto_recency_long(const OttoSessions* sessions, const int32_t* se
   p.w_offset = spec->w_offset;
   p.n = spec->n;
   p.pred = pred;
+  p.score = score;
+  p.out_len = len;
+  p.rows_by_list = rows_by_list ? 1 : 0;
+  p.rows = rows_by_list ? (int64_t)n_list : sessions->n_sessions;
   int64_t lcap, hs;
   recency_caps(max_session_len, max_k, &lcap, &hs);
   p.lcap = (int32_t)lcap;
@@ -322,4 +340,11 @@ extern "C" int otto_recency_long(const OttoSessions* sessions, const int32_t* se
   recency_long_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
   LAUNCH_CHECK();
   return OTTO_OK;
+}
+
+extern "C" int otto_recency_long(const OttoSessions* sessions, const int32_t* session_list, int32_t n_list,
+                                 int32_t max_session_len, const OttoRecencySpec* spec, void* scratch, int64_t scratch_bytes,
+                                 int32_t* pred, void* stream) {
+  return otto_recency_scored(sessions, session_list, n_list, max_session_len, spec, scratch, scratch_bytes, 0, pred, nullptr,
+                             nullptr, stream);
 }

@@ -201,3 +201,33 @@ def test_long_session_recency_branch_matches_reference_loop(mods):
             want = oc.recency_predictions(t.aid, t.type, {"time_weighted": otables["time_weighted"]}, 20)
             for ti in range(3):
                 assert got2[ti, i].tolist() == want[ti], (t.session, ti)
+
+
+def test_recency_weighted_candidate_generator_matches_reference_loop(mods):
+    """ranker/recency_weighted_candidate_generator.py:61-144: every unique aid of every session, ranked by fp64
+    recency-weighted scores; aids, order and scores (fp64 before the float32 cast) bit-exact."""
+    cv, cand_mod, synth = mods
+    frame = synth.generate(synth.SynthSpec("test", 2500, 300, seed=5))
+    df = frame.to_pandas()
+    rng = np.random.default_rng(3)
+    extra = []
+    for s, L in enumerate([33, 64, 200, 457, 32, 31]):                 # both length groups and their boundary
+        aids = rng.integers(0, 300 if L != 64 else 4, L)
+        types = rng.choice([0, 1, 2], L, p=[0.7, 0.2, 0.1])
+        extra += [(10_000_000 + s, int(a), 1662000000 + i, int(t)) for i, (a, t) in enumerate(zip(aids, types))]
+    df = pd.concat([df, pd.DataFrame(extra, columns=["session", "aid", "ts", "type"])], ignore_index=True)
+    sess = cv.ingest(synth.EventFrame.from_pandas(df, 300), "asc", device="cuda:0")
+    labels = {"click": {int(df["session"].iloc[0]): {int(df["aid"].iloc[0])}}, "cart": {}, "order": {}}
+    got = cand_mod.recency_weighted_candidates(sess, labels=labels, keep_f64=True)
+    want = oc.recency_weighted_frame(df)
+    for event in ("click", "cart", "order"):
+        g, w = got[event], want[event]
+        assert len(g) == len(w), event
+        assert np.array_equal(g["session"].to_numpy(), w["session"].to_numpy()), event
+        assert np.array_equal(g["candidates"].to_numpy(), w["candidates"].to_numpy()), event
+        assert np.array_equal(g["candidate_scores_f64"].to_numpy(), w["candidate_scores_f64"].to_numpy()), event
+        assert g["candidates"].dtype == np.uint64 and g["candidate_scores"].dtype == np.float32
+        assert g["candidate_labels"].dtype == np.uint8
+    assert int(got["click"]["candidate_labels"].sum()) == 1 and int(got["cart"]["candidate_labels"].sum()) == 0
+    # carts and orders share weights and coefficients in the script: identical frames
+    assert got["cart"].drop(columns="candidate_labels").equals(got["order"].drop(columns="candidate_labels"))

@@ -121,3 +121,35 @@ def test_cli_submission_and_invalid_mode(mods, tmp_path):
     assert len(list((tmp_path / "covisitation" / "submission").glob("top_15_time_weighted_*.pqt"))) == 6
     with pytest.raises(ValueError, match="Invalid mode"):
         inference.main(["train", "--data", str(tmp_path)])
+
+
+def test_recency_weighted_generator_cli_writes_the_reference_files(mods, tmp_path):
+    """ranker/recency_weighted_candidate_generator.py: file names, columns, dtypes, labels and max recalls."""
+    cv, _, inference, io, synth = mods
+    from otto_multi_objective_recommender_system_b200 import recency_weighted_candidate_generator as rw
+    train, val, labels, _ = _make_data_dir(tmp_path, synth, io)
+    res = rw.main(["validation", "--data", str(tmp_path), "--n-aids", "300"])
+    want = oc.recency_weighted_frame(val)
+    lab = {e: {int(r.session): set(int(a) for a in np.atleast_1d(r.ground_truth)) for r in labels.loc[labels["type"] == t].itertuples()}
+           for e, t in (("click", "clicks"), ("cart", "carts"), ("order", "orders"))}
+    for event in ("click", "cart", "order"):
+        path = tmp_path / "candidate" / f"{event}_recency_weighted_validation.pkl"
+        assert path in res["paths"]
+        got = pd.read_pickle(path)
+        assert list(got.columns) == ["session", "candidates", "candidate_scores", "candidate_labels"]
+        assert got.dtypes.astype(str).to_dict()["candidates"] == "uint64" and got["candidate_scores"].dtype == np.float32
+        w = want[event]
+        assert np.array_equal(got["session"].to_numpy(), w["session"].to_numpy())
+        assert np.array_equal(got["candidates"].to_numpy(), w["candidates"].to_numpy())
+        assert np.array_equal(got["candidate_scores"].to_numpy(), w["candidate_scores"].to_numpy())
+        want_lab = [int(int(a) in lab[event].get(int(s), ())) for s, a in zip(w["session"], w["candidates"])]
+        assert got["candidate_labels"].tolist() == want_lab
+        hits = sum(want_lab)
+        denom = sum(min(len(l), 20) for l in lab[event].values())
+        assert res["recall"][event] == pytest.approx(hits / denom if denom else 0.0)
+    (tmp_path / "splits" / "val.parquet").rename(tmp_path / "splits" / "test.parquet")
+    res = rw.main(["submission", "--data", str(tmp_path), "--n-aids", "300"])
+    got = pd.read_pickle(tmp_path / "candidate" / "order_recency_weighted_test.pkl")
+    assert list(got.columns) == ["session", "candidates", "candidate_scores"]
+    with pytest.raises(ValueError, match="Invalid mode"):
+        rw.main(["train", "--data", str(tmp_path)])

@@ -152,3 +152,19 @@ def test_recency_branch_restatement_properties():
     tables = {"time_weighted": {24: [7, 7]}}             # two +0.05 bonuses for aid 7 in the click ranking only
     c3, k3, _ = oc.recency_predictions(aids, types, tables, 20)
     assert c3.index(7) < clicks.index(7) and k3 == carts
+
+
+def test_recency_weighted_generator_restatement():
+    """ranker/recency_weighted_candidate_generator.py:61-93 on a hand-checkable session."""
+    from oracle import candidates_oracle as oc
+    w = 2.0 ** np.linspace(0.1, 1, 3) - 1
+    (c_aids, c_w), (k_aids, k_w), (o_aids, o_w) = oc.recency_weighted_candidates([1, 2, 1], [0, 1, 0])
+    assert c_aids == [2, 1]                               # the cart counts 6x: 6 * w[1] > w[0] + w[2]
+    assert c_w == [w[1] * 6, w[0] * 1 + w[2] * 1]
+    assert (k_aids, k_w) == (o_aids, o_w)                 # same weights and coefficients for carts and orders
+    # every unique aid is kept, ties fall to the first inserted
+    aids, _ = oc.recency_weighted_candidates([5, 6, 7], [0, 0, 0])[0]
+    assert aids == [7, 6, 5]
+    f = oc.recency_weighted_frame(pd.DataFrame({"session": [3, 3, 3, 9], "aid": [1, 2, 1, 4], "ts": [1, 2, 3, 4], "type": [0, 1, 0, 2]}))
+    assert f["click"]["session"].tolist() == [3, 3, 9] and f["click"]["candidates"].tolist() == [2, 1, 4]
+    assert f["click"]["candidate_scores"].dtype == np.float32 and f["click"]["candidates"].dtype == np.uint64
