@@ -72,6 +72,35 @@ def ranker_candidates(session_aids, session_event_types, tables, n: int = 100):
     return out
 
 
+def regular_candidates(session_aids, session_event_types, tables, n: int = 100):
+    """One session of ranker/regular_candidate_generation.py:139-180 (fastText term dropped): the session's unique
+    aids (most recent first, scores |H| .. 1) followed by the ranker-form votes -> [(aids, scores)] per target."""
+    unique, *lists = _gather(session_aids, session_event_types, tables)
+    out = []
+    for concat in lists:
+        kept = [(aid, weight) for aid, weight in Counter(concat).most_common(n) if aid not in unique]
+        weights = np.arange(1, len(unique) + 1).tolist()[::-1] + [weight for _, weight in kept]     # :163
+        out.append((unique + [aid for aid, _ in kept], weights))
+    return out
+
+
+def regular_frame(df_events: pd.DataFrame, tables: dict, n: int = 100) -> dict:
+    """All sessions -> the exploded frames of ranker/regular_candidate_generation.py:225-257."""
+    sess = session_lists(df_events)
+    rows = {"click": [], "cart": [], "order": []}
+    for t in sess.itertuples():
+        res = regular_candidates(t.aid, t.type, tables, n)
+        for name, (aids, weights) in zip(("click", "cart", "order"), res):
+            rows[name].extend((t.session, a, w) for a, w in zip(aids, weights))
+    out = {}
+    for name, r in rows.items():
+        f = pd.DataFrame(r, columns=["session", "candidates", "candidate_scores"])
+        f["candidates"] = f["candidates"].astype(np.uint64)
+        f["candidate_scores"] = f["candidate_scores"].astype(np.float32)
+        out[name] = f
+    return out
+
+
 def standalone_predictions(session_aids, session_event_types, tables, popular, n: int = 20):
     """One session of covisitation/inference.py:227-243 (covisitation branch; fastText term dropped).
 

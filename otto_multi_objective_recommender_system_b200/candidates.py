@@ -175,6 +175,57 @@ def assemble_predictions(sessions: EventCSR, cand: Candidates, popular: dict, n:
     return pred, long_session.bool()
 
 
+def regular_candidates(sessions: EventCSR, tables: dict, n: int = 100, labels: dict | None = None, n_chunks: int = 15) -> dict:
+    """ranker/regular_candidate_generation.py:139-180,225-257: per session its unique aids (most recent first, scores
+    |H| .. 1, :163) followed by the ranker-form votes (most_common(n), history dropped) -> the exploded frames the
+    script pickles as candidate/{event}_{validation,test}.pkl.  Like the script, sessions are processed in chunks
+    (:218: 15) so the dense [target, session, |H| + n] device rows stay small.  The fastText / Annoy term (:155-156)
+    is not on this path."""
+    import pandas as pd
+    lib = N.lib()
+    dev = sessions.aid.device
+    cand = generate_candidates(sessions, tables, reference_spec(tables.keys(), n))
+    T, S = len(cand.targets), sessions.n_sessions
+    sid_all = sessions.session_ids.cpu().numpy()
+    parts = {t: [] for t in cand.targets}
+    dummy = torch.zeros(1, dtype=torch.int32, device=dev)
+    n_chunks = max(1, min(n_chunks, S))
+    for c in range(n_chunks):
+        lo, hi = c * S // n_chunks, (c + 1) * S // n_chunks
+        if hi <= lo:
+            continue
+        sub = sessions.slice_sessions(lo, hi)
+        W = max_session_len(sub) + n
+        c_aid, c_score, c_len = (x[:, lo:hi].contiguous() for x in (cand.aid, cand.score, cand.len))
+        pred = torch.empty((T, hi - lo, W), dtype=torch.int32, device=dev)
+        ss = _sessions_struct(sub)
+        oc = N.OttoCandidates(c_aid.data_ptr(), c_score.data_ptr(), c_len.data_ptr())
+        with torch.cuda.device(dev):
+            # no popular fill, rows wide enough for the whole history: row = history + votes
+            N.check(lib.otto_assemble_predictions(C.byref(ss), C.byref(oc), T, n, dummy.data_ptr(), 0, W, pred.data_ptr(), None,
+                                                  _stream_ptr(dev)))
+        row_len = (pred >= 0).sum(dim=2)
+        hist_len = row_len - c_len
+        j = torch.arange(W, device=dev)[None, None, :]
+        vote = torch.gather(c_score, 2, (j - hist_len[:, :, None]).clamp_(0, n - 1).expand(T, hi - lo, W))
+        score = torch.where(j < hist_len[:, :, None], hist_len[:, :, None] - j, vote)
+        mask = j < row_len[:, :, None]
+        for ti, t in enumerate(cand.targets):
+            m = mask[ti]
+            parts[t].append((np.repeat(sid_all[lo:hi], row_len[ti].cpu().numpy()), pred[ti][m].cpu().numpy(), score[ti][m].cpu().numpy()))
+    out = {}
+    for t, chunks in parts.items():
+        f = pd.DataFrame({"session": np.concatenate([c[0] for c in chunks]) if chunks else np.zeros(0, sid_all.dtype),
+                          "candidates": (np.concatenate([c[1] for c in chunks]) if chunks else np.zeros(0, np.int32)).astype(np.uint64),
+                          "candidate_scores": (np.concatenate([c[2] for c in chunks]) if chunks else np.zeros(0, np.int32)).astype(np.float32)})
+        if labels is not None:
+            lab = labels.get(t, {})
+            f["candidate_labels"] = np.fromiter((int(int(a) in lab.get(int(s), ())) for s, a in zip(f["session"], f["candidates"])),
+                                                dtype=np.uint8, count=len(f))
+        out[t] = f
+    return out
+
+
 _WEIGHT_CACHE: dict = {}
 
 

@@ -116,7 +116,7 @@ def read_topk_parts(directory, stem: str, n_aids: int, k: int, n_parts: int | No
     return TopKTable.from_rows(ax, ay, w, n_aids, k)
 
 
-def write_candidate_frames(frames: dict, directory, mode: str, family: str = "covisitation") -> list:
+def write_candidate_frames(frames: dict, directory, mode: str, family: str | None = "covisitation") -> list:
     """frames = Candidates.to_frames(); names as ranker/covisitation_candidate_generation.py:177-197,290-307."""
     if mode not in ("validation", "submission"):
         raise ValueError("Invalid mode")
@@ -125,7 +125,8 @@ def write_candidate_frames(frames: dict, directory, mode: str, family: str = "co
     tag = "validation" if mode == "validation" else "test"
     out = []
     for event, f in frames.items():
-        path = directory / f"{event}_{family}_{tag}.pkl"
+        # family None: the names of ranker/regular_candidate_generation.py:225-257 ({event}_validation.pkl)
+        path = directory / (f"{event}_{family}_{tag}.pkl" if family else f"{event}_{tag}.pkl")
         f.to_pickle(path)
         out.append(path)
     return out

@@ -231,3 +231,27 @@ def test_recency_weighted_candidate_generator_matches_reference_loop(mods):
     assert int(got["click"]["candidate_labels"].sum()) == 1 and int(got["cart"]["candidate_labels"].sum()) == 0
     # carts and orders share weights and coefficients in the script: identical frames
     assert got["cart"].drop(columns="candidate_labels").equals(got["order"].drop(columns="candidate_labels"))
+
+
+def test_regular_candidate_form_matches_reference_loop(mods):
+    """ranker/regular_candidate_generation.py:139-180: history (scores |H| .. 1) + ranker-form votes, all seven stems."""
+    cv, cand_mod, synth = mods
+    rng = np.random.default_rng(17)
+    n_aids = 300
+    tables, otables = {}, {}
+    for stem in oc.STEMS:
+        tables[stem], otables[stem] = random_table(cv, rng, n_aids, 15)
+    frame, df = make_test_frame(synth, 1200, n_aids, seed=8, extra_lengths=(33, 90, 257))
+    sess = cv.ingest(frame, "asc", device="cuda:0")
+    labels = {"click": {}, "cart": {int(df["session"].iloc[0]): {int(df["aid"].iloc[0])}}, "order": {}}
+    for n, n_chunks in ((100, 15), (5, 1)):
+        got = cand_mod.regular_candidates(sess, tables, n, labels=labels, n_chunks=n_chunks)
+        want = oc.regular_frame(df, otables, n)
+        for event in ("click", "cart", "order"):
+            g, w = got[event], want[event]
+            assert len(g) == len(w), (event, n)
+            for col in ("session", "candidates", "candidate_scores"):
+                assert np.array_equal(g[col].to_numpy(), w[col].to_numpy()), (event, n, col)
+            assert g["candidates"].dtype == np.uint64 and g["candidate_scores"].dtype == np.float32
+        # the history aid of the labelled session is a candidate of that session exactly once
+        assert int(got["cart"]["candidate_labels"].sum()) == 1

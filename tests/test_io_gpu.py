@@ -153,3 +153,29 @@ def test_recency_weighted_generator_cli_writes_the_reference_files(mods, tmp_pat
     assert list(got.columns) == ["session", "candidates", "candidate_scores"]
     with pytest.raises(ValueError, match="Invalid mode"):
         rw.main(["train", "--data", str(tmp_path)])
+
+
+def test_regular_candidate_generation_cli(mods, tmp_path):
+    """ranker/regular_candidate_generation.py: table names without "_15", 6 (+2) parts, candidate/{event}_validation.pkl."""
+    cv, _, inference, io, synth = mods
+    from otto_multi_objective_recommender_system_b200 import regular_candidate_generation as reg
+    train, val, labels, _ = _make_data_dir(tmp_path, synth, io)
+    csr = cv.ingest(train, "desc", device="cuda:0")
+    otables = {}
+    for stem, spec in cv.VARIANTS.items():
+        table, _ = cv.build_topk(csr, spec)
+        paths = io.write_topk_parts(table, tmp_path / "covisitation" / "validation", stem, reg.N_PARTS.get(stem, 6), None, k=15)
+        assert paths[0].name == f"top_{stem}_0.pqt"
+        otables[stem] = {}
+        for p in paths:
+            otables[stem].update(oc.covisitation_df_to_dict(pd.read_parquet(p)))
+    res = reg.main(["validation", "--data", str(tmp_path), "--n-aids", "300"])
+    want = oc.regular_frame(val, otables, 100)
+    for event in ("click", "cart", "order"):
+        got = pd.read_pickle(tmp_path / "candidate" / f"{event}_validation.pkl")
+        assert list(got.columns) == ["session", "candidates", "candidate_scores", "candidate_labels"]
+        for col in ("session", "candidates", "candidate_scores"):
+            assert np.array_equal(got[col].to_numpy(), want[event][col].to_numpy()), (event, col)
+    assert 0.0 <= res["recall"]["weighted"] <= 1.0
+    with pytest.raises(ValueError, match="Invalid mode"):
+        reg.main(["test", "--data", str(tmp_path)])

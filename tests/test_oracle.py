@@ -168,3 +168,15 @@ def test_recency_weighted_generator_restatement():
     f = oc.recency_weighted_frame(pd.DataFrame({"session": [3, 3, 3, 9], "aid": [1, 2, 1, 4], "ts": [1, 2, 3, 4], "type": [0, 1, 0, 2]}))
     assert f["click"]["session"].tolist() == [3, 3, 9] and f["click"]["candidates"].tolist() == [2, 1, 4]
     assert f["click"]["candidate_scores"].dtype == np.float32 and f["click"]["candidates"].dtype == np.uint64
+
+
+def test_regular_candidate_form_restatement():
+    """ranker/regular_candidate_generation.py:139-180 on a hand-checkable session."""
+    from oracle import candidates_oracle as oc
+    tables = {"time_weighted": {1: [7, 8], 2: [7, 1]}}
+    (c_aids, c_w), (k_aids, k_w), _ = oc.regular_candidates([1, 2, 1], [0, 0, 1], tables, 100)
+    assert c_aids == [1, 2, 7, 8]                       # history most recent first, then votes without history aids
+    assert c_w == [2, 1, 2, 1]                          # |H| .. 1, then the vote counts (7 twice, 8 once)
+    assert (k_aids, k_w) == (c_aids, c_w)
+    f = oc.regular_frame(pd.DataFrame({"session": [4, 4, 4], "aid": [1, 2, 1], "ts": [1, 2, 3], "type": [0, 0, 1]}), tables, 100)
+    assert f["order"]["candidates"].tolist() == [1, 2, 7, 8] and f["order"]["candidate_scores"].dtype == np.float32
