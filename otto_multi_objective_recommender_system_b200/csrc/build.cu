@@ -623,6 +623,7 @@ extern "C" int otto_covisit_count_finish_owned(const OttoEvents* ev, const OttoC
   int rc = check_spec(spec);
   if (rc) return rc;
   if ((rc = check_plan(plan, spec, false))) return rc;
+  if (!ev) { otto_set_error("events is NULL"); return OTTO_EINVAL; }
   if (!row_before) { otto_set_error("row_before is NULL"); return OTTO_EINVAL; }
   const Layout L = make_layout(ev->n_sessions, ev->n_events, spec);
   if ((rc = check_ws(L, workspace, workspace_bytes))) return rc;

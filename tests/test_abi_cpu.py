@@ -84,6 +84,32 @@ def test_host_only_entry_points(native_lib):
     assert e.value.code == N.OTTO_EINVAL
 
 
+def test_owner_plan_argument_checks(native_lib):
+    """Owner-direct entry points validate the plan on the host before any CUDA call."""
+    from otto_multi_objective_recommender_system_b200 import _native as N
+    from otto_multi_objective_recommender_system_b200 import covisit
+    lib = native_lib
+    spec = covisit.CLICKS.to_c(1000)
+    ev = N.OttoEvents(10, 100, None, None, None, None)
+
+    def plan(n, rank, cuts):
+        p = N.OttoOwnerPlan()
+        p.n_owners, p.rank = n, rank
+        for i in range(N.MAX_OWNERS + 1):
+            p.aid_cuts[i] = cuts[min(i, len(cuts) - 1)]
+        return p
+    for bad, what in ((plan(0, 0, [0, 1000]), b"n_owners"), (plan(9, 0, [0, 1000]), b"n_owners"), (plan(2, 2, [0, 500, 1000]), b"rank"),
+                      (plan(2, 0, [0, 500, 900]), b"aid_cuts"), (plan(2, 0, [0, 1200, 1000]), b"non-decreasing")):
+        assert lib.otto_covisit_count_finish_owned(C.byref(ev), C.byref(spec), None, 0, C.byref(bad), None, None, None) == N.OTTO_EINVAL
+        assert what in lib.otto_last_error(), lib.otto_last_error()
+    ok = plan(2, 1, [0, 500, 1000])
+    assert lib.otto_covisit_count_finish_owned(C.byref(ev), C.byref(spec), None, 0, C.byref(ok), None, None, None) == N.OTTO_EINVAL
+    assert b"row_before" in lib.otto_last_error()
+    # the scatter needs every owner's buffer
+    assert lib.otto_covisit_scatter_owned(C.byref(ev), C.byref(spec), None, 0, C.byref(ok), None) in (N.OTTO_EINVAL, N.OTTO_ENOSPC)
+    assert lib.otto_covisit_count_finish_owned(None, C.byref(spec), None, 0, C.byref(ok), None, None, None) == N.OTTO_EINVAL
+
+
 def test_product_path_has_no_cpu_fallback():
     """CPU tensors are rejected before any work: there is no host implementation to fall back to."""
     import torch
