@@ -23,7 +23,7 @@ __global__ void store_runs(uint2* a, uint2* b, int mixed, uint64_t buf_elems, ui
   const uint32_t groups = run_elems >= 32 ? 1 : 32 / run_elems, g = run_elems >= 32 ? 0 : lane / run_elems;
   for (uint64_t r = warp; r * groups < n_runs; r += n_warps) {
     const uint64_t id = r * groups + g;
-    const uint64_t at = ((uint64_t)mix((uint32_t)id) * 2654435761ull) % (buf_elems - run_elems);
+    const uint64_t at = __umulhi(mix((uint32_t)id), (uint32_t)(buf_elems - run_elems));
     uint2* buf = (mixed && (id & 1)) ? b : a;
     for (uint32_t i = run_elems >= 32 ? lane : lane % run_elems; i < run_elems; i += 32) buf[at + i] = make_uint2((uint32_t)id, i);
   }
