@@ -53,3 +53,64 @@ def assert_time_table_close(got: pd.DataFrame, acc: pd.DataFrame, k: int, what: 
         w_got = w_or[diff]
         np.testing.assert_allclose(w_got, w_want, rtol=2 * RTOL_TIME, atol=0,
                                    err_msg=f"{what}: top-K differs beyond weight ties")
+
+
+# ---- vectors produced by executing the reference's own loop bodies (tests/golden/make_reference_vectors.py) ----
+
+def reference_vectors():
+    import json
+    import pathlib
+    return json.load(open(pathlib.Path(__file__).resolve().parent / "golden" / "reference_candidates.json"))
+
+
+def reference_vector_inputs(g):
+    """-> (event frame as DataFrame, {stem: {aid_x: [aid_y...]}}, labels {event: {session: set}}, popular lists)."""
+    rows = []
+    for s in g["sessions"]:
+        rows += [(s["session"], a, 1661724000 + i, t) for i, (a, t) in enumerate(zip(s["aid"], s["type"]))]
+    df = pd.DataFrame(rows, columns=["session", "aid", "ts", "type"])
+    tables = {stem: {int(x): ys for x, ys in r.items()} for stem, r in g["tables"].items()}
+    labels = {"click": {}, "cart": {}, "order": {}}
+    for s in g["sessions"]:
+        if s["click_labels"] != []:
+            labels["click"][s["session"]] = {s["click_labels"]}
+        if s["cart_labels"]:
+            labels["cart"][s["session"]] = set(s["cart_labels"])
+        if s["order_labels"]:
+            labels["order"][s["session"]] = set(s["order_labels"])
+    return df, tables, labels, g["popular"]
+
+
+def table_rows(rows: dict) -> pd.DataFrame:
+    """{aid_x: [aid_y best first]} -> the (aid_x, aid_y, wgt) rows of a part file (weights only encode the order)."""
+    out = [(x, y, float(len(ys) - i)) for x, ys in sorted(rows.items()) for i, y in enumerate(ys)]
+    return pd.DataFrame(out, columns=["aid_x", "aid_y", "wgt"])
+
+
+def check_candidate_frames(g, family: str, frames: dict, score_column: str = "candidate_scores", with_labels: bool = True):
+    """frames = {event: exploded frame (session, candidates, candidate_scores[, candidate_labels])} of ALL sessions of the
+    vectors, in session order; family = 'ranker' | 'recency' | 'regular'."""
+    for event in ("click", "cart", "order"):
+        f = frames[event]
+        by_session = {s: grp for s, grp in f.groupby("session", sort=False)}
+        for s, want in zip(g["sessions"], g[family]):
+            aids, scores, labels = want[event]
+            grp = by_session.get(s["session"])
+            got_aids = [] if grp is None else [int(a) for a in grp["candidates"]]
+            assert got_aids == aids, (family, event, s["session"])
+            got_scores = [] if grp is None else grp[score_column].tolist()
+            if score_column == "candidate_scores":       # the pickled column is float32
+                assert got_scores == [float(np.float32(w)) for w in scores], (family, event, s["session"])
+            else:                                        # fp64 Counter values, bit for bit
+                assert got_scores == scores, (family, event, s["session"])
+            if with_labels:
+                got_labels = [] if grp is None else [int(l) for l in grp["candidate_labels"]]
+                assert got_labels == labels, (family, event, s["session"])
+        assert list(dict.fromkeys(f["session"])) == [s["session"] for s, w in zip(g["sessions"], g[family]) if w[event][0]]
+
+
+def check_standalone_predictions(g, preds: dict):
+    """preds = {event: [list of aids per session]} (padding removed)."""
+    for event in ("click", "cart", "order"):
+        for s, want, got in zip(g["sessions"], g["standalone"], preds[event]):
+            assert [int(a) for a in got] == want[event], (event, s["session"])

@@ -180,3 +180,50 @@ def test_regular_candidate_form_restatement():
     assert (k_aids, k_w) == (c_aids, c_w)
     f = oc.regular_frame(pd.DataFrame({"session": [4, 4, 4], "aid": [1, 2, 1], "ts": [1, 2, 3], "type": [0, 0, 1]}), tables, 100)
     assert f["order"]["candidates"].tolist() == [1, 2, 7, 8] and f["order"]["candidate_scores"].dtype == np.float32
+
+
+def _attach_labels(frames, labels):
+    for event, f in frames.items():
+        lab = labels[event]
+        f["candidate_labels"] = [int(int(a) in lab.get(int(s), ())) for s, a in zip(f["session"], f["candidates"])]
+    return frames
+
+
+def test_oracle_matches_vectors_from_the_reference_loop_bodies():
+    """tests/golden/reference_candidates.json was produced by executing the reference's own loop bodies
+    (make_reference_vectors.py): the restatements in oracle/candidates_oracle.py must reproduce it exactly."""
+    import parity_helpers as H
+    from oracle import candidates_oracle as oc
+    g = H.reference_vectors()
+    df, tables, labels, popular = H.reference_vector_inputs(g)
+    H.check_candidate_frames(g, "ranker", _attach_labels(oc.ranker_frame(df, tables, 100), labels))
+    H.check_candidate_frames(g, "regular", _attach_labels(oc.regular_frame(df, tables, 100), labels))
+    rw = _attach_labels(oc.recency_weighted_frame(df), labels)
+    H.check_candidate_frames(g, "recency", rw)
+    H.check_candidate_frames(g, "recency", rw, score_column="candidate_scores_f64")
+    pops = [popular["click"], popular["cart"], popular["order"]]
+    preds = {"click": [], "cart": [], "order": []}
+    n_long = 0
+    for s in g["sessions"]:
+        if len(set(s["aid"])) >= 20:                                        # covisitation/inference.py:127-131
+            res = oc.recency_predictions(s["aid"], s["type"], tables, 20)
+            n_long += 1
+        else:
+            res = oc.standalone_predictions(s["aid"], s["type"], tables, pops, 20)
+        for event, r in zip(("click", "cart", "order"), res):
+            preds[event].append(r)
+    assert n_long >= 5
+    H.check_standalone_predictions(g, preds)
+
+
+@pytest.mark.skipif(not pathlib.Path("/root/reference/src").exists(), reason="the reference tree is not on this machine")
+def test_reference_vectors_are_reproducible(tmp_path, monkeypatch):
+    """Re-running the generator against /root/reference yields the committed file (build container only)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_vectors", GOLDEN / "make_reference_vectors.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr(mod, "OUT", tmp_path)
+    (tmp_path / "popular.json").write_text((GOLDEN / "popular.json").read_text())
+    mod.main()
+    assert json.load(open(tmp_path / "reference_candidates.json")) == json.load(open(GOLDEN / "reference_candidates.json"))
