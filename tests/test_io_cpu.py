@@ -56,3 +56,26 @@ def test_candidate_frame_file_names(tmp_path):
     assert back.dtypes.astype(str).to_dict() == {"session": "int64", "candidates": "uint64", "candidate_scores": "float32"}
     with pytest.raises(ValueError, match="Invalid mode"):
         io.write_candidate_frames({}, tmp_path, "nope")
+
+
+def test_chunk_directory_round_trip(tmp_path):
+    """utilities/split_dataset_writer_parquet.py:21-33: files of consecutive session ids, read back in chunk order."""
+    import pandas as pd
+    from otto_multi_objective_recommender_system_b200 import io, synth
+    frame = synth.generate(synth.SynthSpec("train", 250, 40, seed=3))
+    paths = io.write_event_chunks(frame, tmp_path / "train_truncated_parquet", "train_truncated", session_chunk_size=100)
+    assert [p.name for p in paths] == [f"train_truncated_{i}.parquet" for i in range(3)]       # 250 // 100 + 1
+    first = pd.read_parquet(paths[0])
+    assert first["session"].max() < 100 and pd.read_parquet(paths[1])["session"].between(100, 199).all()
+    # eleven chunks would sort 0, 1, 10, 2 ... by name: the reader orders by chunk index
+    (tmp_path / "many").mkdir()
+    for i in range(11):
+        pd.DataFrame({"session": [i], "aid": [i], "ts": [1659304800 + i], "type": [0]}).to_parquet(tmp_path / "many" / f"c_{i}.parquet")
+    assert io.read_event_frame(tmp_path / "many").to_pandas()["session"].tolist() == list(range(11))
+    back = io.read_event_frame(tmp_path / "train_truncated_parquet", n_aids=40).to_pandas()
+    want = frame.to_pandas().sort_values(["session", "ts"], kind="stable").reset_index(drop=True)
+    assert back.astype("int64").equals(want.astype("int64"))
+    import pytest
+    (tmp_path / "empty").mkdir()
+    with pytest.raises(FileNotFoundError):
+        io.read_event_frame(tmp_path / "empty")
