@@ -13,7 +13,7 @@ session on a small seeded input and stores inputs and outputs in tests/golden/re
 The fastText / Annoy neighbour lookup (no model offline) is neutralised by a stub index that returns only the query
 item, so `fasttext_similar_aids` is empty - exactly the term DESIGN.md states as dropped.  Everything else is the
 reference's code.  tests/test_oracle.py checks the oracle restatements against these vectors (CPU), and
-tests/test_candidates_gpu.py checks the CUDA path against them (GPU).
+tests/test_zz_reference_vectors_gpu.py checks the CUDA path against them (GPU).
 
 Run from the repo root in the build container (needs /root/reference):  python tests/golden/make_reference_vectors.py
 """
