@@ -10,6 +10,8 @@ session on a small seeded input and stores inputs and outputs in tests/golden/re
   recency       ranker/recency_weighted_candidate_generator.py first `for idx, row in tqdm(df_val.iterrows()` loop
   regular       ranker/regular_candidate_generation.py        first `for t in tqdm(df_val.itertuples()` loop
 
+The submission-mode twins of these loops (`df_test`) are executed too and must give identical lists.
+
 The fastText / Annoy neighbour lookup (no model offline) is neutralised by a stub index that returns only the query
 item, so `fasttext_similar_aids` is empty - exactly the term DESIGN.md states as dropped.  Everything else is the
 reference's code.  tests/test_oracle.py checks the oracle restatements against these vectors (CPU), and
@@ -103,16 +105,16 @@ def coefficient_of(path: pathlib.Path) -> dict:
     return eval(m.group(1))           # a dict literal such as {0: 1, 1: 9, 2: 6}
 
 
-def run(body: str, ns: dict, sessions, style: str, only=None):
+def run(body: str, ns: dict, sessions, style: str, only=None, frame_name: str = "df_val"):
     code = compile(body, "<reference loop body>", "exec")
     rec = Recorder()
-    ns = dict(ns, df_val=rec)
-    T = collections.namedtuple("T", ["Index", "aid", "type", "click_labels", "cart_labels", "order_labels"])
+    ns = dict(ns, **{frame_name: rec})
+    T = collections.namedtuple("T", ["Index", "session", "aid", "type", "click_labels", "cart_labels", "order_labels"])
     for i, s in enumerate(sessions):
         if only is not None and not only(s):
             continue
         if style == "itertuples":
-            ns["t"] = T(i, s["aid"], s["type"], s["click_labels"], s["cart_labels"], s["order_labels"])
+            ns["t"] = T(i, s["session"], s["aid"], s["type"], s["click_labels"], s["cart_labels"], s["order_labels"])
         else:
             ns["idx"], ns["row"] = i, s
         exec(code, ns)
@@ -148,6 +150,40 @@ def main():
     cells = run(loop_body(p, "for t in tqdm(df_val.itertuples()"), namespace(tables, popular, None), sessions, "itertuples")
     out["regular"] = [{e: [cells[i][f"{e}_candidates"], cells[i][f"{e}_candidate_scores"], cells[i][f"{e}_candidate_labels"]]
                        for e in ("click", "cart", "order")} for i in range(len(sessions))]
+
+    # the submission-mode loops of the four scripts (df_test: no labels) must give the same lists on the same sessions
+    def same(cells, key, family, pick=lambda v: v):
+        for i in range(len(sessions)):
+            for e in ("click", "cart", "order"):
+                want = out[family][i][e] if family == "standalone" else out[family][i][e][0 if key.endswith("candidates") else 1]
+                assert pick(cells[i][f"{e}_{key}"]) == want, (family, key, i, e)
+    p = REF / "ranker" / "covisitation_candidate_generation.py"
+    cells = run(loop_body(p, "for t in tqdm(df_test.itertuples()"), namespace(tables, popular, None), sessions, "itertuples", frame_name="df_test")
+    same(cells, "candidates", "ranker")
+    same(cells, "candidate_scores", "ranker")
+    p = REF / "covisitation" / "inference.py"
+    ns = namespace(tables, popular, coefficient_of(p))
+    ns["test_predictions"] = []          # the submission loops append {'session_type': '<session>_<event>s', 'labels': 'a b c'} (:387-391, :437-441)
+    run(loop_body(p, "for t in tqdm(df_test.loc[recency_weight_predictions_idx].itertuples()"), ns, sessions, "itertuples", is_long, "df_test")
+    run(loop_body(p, "for t in tqdm(df_test.loc[covisitation_predictions_idx].itertuples()"), ns, sessions, "itertuples",
+        lambda s: not is_long(s), "df_test")
+    index_of = {s["session"]: i for i, s in enumerate(sessions)}
+    cells = collections.defaultdict(dict)
+    for row in ns["test_predictions"]:
+        sid, event = row["session_type"].rsplit("_", 1)
+        cells[index_of[int(sid)]][f"{event[:-1]}_predictions"] = [int(a) for a in row["labels"].split()]
+    assert len(ns["test_predictions"]) == 3 * len(sessions)
+    same(cells, "predictions", "standalone")
+    p = REF / "ranker" / "recency_weighted_candidate_generator.py"
+    cells = run(loop_body(p, "for idx, row in tqdm(df_test.iterrows()"), namespace(tables, popular, coefficient_of(p)), sessions, "iterrows",
+                frame_name="df_test")
+    same(cells, "candidates", "recency")
+    same(cells, "candidate_scores", "recency", lambda v: [float(w) for w in v])
+    p = REF / "ranker" / "regular_candidate_generation.py"
+    cells = run(loop_body(p, "for t in tqdm(df_test.itertuples()"), namespace(tables, popular, None), sessions, "itertuples", frame_name="df_test")
+    same(cells, "candidates", "regular")
+    same(cells, "candidate_scores", "regular")
+    out["submission_loops_identical"] = True
 
     def plain(o):
         if isinstance(o, (np.integer,)):
