@@ -484,7 +484,7 @@ def run_b200(args):
             "config": {"workload": workload_name(args), "sessions_rank0": S, "events_rank0": E, "aids": A,
                        "tail_events_rank0": E30, "pairs_rank0": P, "distinct_pairs_rank0": D, "bins": B,
                        "split_rows": stats["split_rows"], "k": K, "events_all_ranks": events_all,
-                       "parallelism": "1 GPU" if world == 1 else f"sessions sharded over {world} GPUs, aid_x-owner all-to-all",
+                       "parallelism": "1 GPU" if world == 1 else f"sessions sharded over {world} GPUs, rows owned by aid_x range (transport: roofline.exchange)",
                        "l2": "inputs larger than L2 (event CSR and pair records are GBs)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "candidates": cand_info,
             "gpu_launches": int(launches), "clocks": clocks}))
