@@ -356,26 +356,3 @@ def recall_at_20(pred: torch.Tensor, labels: list) -> float:
     hits = sum(len(set(int(a) for a in row if a >= 0).intersection(l)) for row, l in zip(p, labels))
     denom = sum(min(len(l), 20) for l in labels)
     return hits / denom if denom else 0.0
-
-
-def smoke_check() -> None:
-    """Tiny candidate-generation run on cuda:0 against the CPU oracle (called by __graft_entry__.smoke)."""
-    from oracle import candidates_oracle as co_c
-    from oracle import covisit_oracle as co
-    from . import covisit, synth
-    train = synth.generate(synth.SynthSpec("train", 2000, 300, seed=3))
-    test = synth.generate(synth.SynthSpec("test", 500, 300, seed=4, first_session=2000))
-    csr = covisit.ingest(train, "desc", device="cuda:0")
-    tables, otables = {}, {}
-    for stem, spec in covisit.VARIANTS.items():
-        tables[stem], _ = covisit.build_topk(csr, spec)
-        otables[stem] = co_c.covisitation_df_to_dict(tables[stem].to_pandas())
-    sess = covisit.ingest(test, "asc", device="cuda:0")
-    cand = generate_candidates(sess, tables, reference_spec(tables.keys(), 20))
-    want = co_c.ranker_frame(test.to_pandas(), otables, 20)
-    got = cand.to_frames()
-    for t in ("click", "cart", "order"):
-        assert got[t]["session"].tolist() == want[t]["session"].tolist(), t
-        assert got[t]["candidates"].tolist() == want[t]["candidates"].tolist(), t
-        assert got[t]["candidate_scores"].tolist() == want[t]["candidate_scores"].tolist(), t
-    print(f"smoke candidates: {len(got['click'])} click rows ok")

@@ -6,7 +6,7 @@ Mirrors the reference script's file contract (covisitation/inference.py:44-52,76
   validation  reads  DIR/splits/val.parquet (+ val_labels.parquet), DIR/aid_frequencies/train_20_most_frequent_*,
                      DIR/covisitation/validation/top_15_<stem>_<part>.pqt
               logs   recall@20 per type and the 0.1 / 0.3 / 0.6 weighted recall
-  submission  reads  DIR/test.pkl (or splits/test.parquet), DIR/aid_frequencies/all_20_most_frequent_*,
+  submission  reads  DIR/test.pkl (or splits/test.parquet), DIR/aid_frequencies/test_20_most_frequent_* (:271-278),
                      DIR/covisitation/submission/top_15_<stem>_<part>.pqt
               writes DIR/submissions/covisitation_submission.csv.gz
   any other mode raises ValueError('Invalid mode'), like the reference.
@@ -27,6 +27,10 @@ import numpy as np
 import torch
 
 from . import candidates, covisit, io
+
+
+# popular-fill lists per mode: covisitation/inference.py:76-83 (train_20_...) and :271-278 (test_20_...)
+POPULAR_PREFIX = {"validation": "train", "submission": "test"}
 
 
 def _first_existing(*paths):
@@ -96,10 +100,10 @@ def main(argv=None) -> dict:
 
     if mode == "validation":
         test_frame = io.read_event_frame(data / "splits" / "val.parquet", n_aids=args.n_aids)
-        popular = io.read_popular(data / "aid_frequencies", "train")
+        popular = io.read_popular(data / "aid_frequencies", POPULAR_PREFIX[mode])
     else:
         test_frame = io.read_event_frame(_first_existing(data / "test.pkl", data / "splits" / "test.parquet"), n_aids=args.n_aids)
-        popular = io.read_popular(data / "aid_frequencies", "all")
+        popular = io.read_popular(data / "aid_frequencies", POPULAR_PREFIX[mode])
     extra = covisit.load_stem_recipes(args.stems) if args.stems else None
     built = build_matrices(data, mode, args.n_aids, dev, extra) if args.build else None
     n_aids = max([test_frame.n_aids] + ([t.n_aids for t in built.values()] if built else [])) if args.n_aids is None else args.n_aids

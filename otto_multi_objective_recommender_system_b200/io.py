@@ -163,8 +163,9 @@ def write_candidate_frames(frames: dict, directory, mode: str, family: str | Non
 
 
 def read_popular(directory, prefix: str) -> dict:
-    """data/aid_frequencies/{prefix}_20_most_frequent_{click,cart,order}_aids.json (covisitation/inference.py:76-83);
-    prefix is 'train' (validation) or 'all' (submission).  The json keys are the aids, most frequent first."""
+    """data/aid_frequencies/{prefix}_20_most_frequent_{click,cart,order}_aids.json; prefix is 'train' in validation
+    mode (covisitation/inference.py:76-83) and 'test' in submission mode (:271-278).  The json keys are the aids, most
+    frequent first."""
     directory = pathlib.Path(directory)
     out = {}
     for event in ("click", "cart", "order"):

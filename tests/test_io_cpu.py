@@ -79,3 +79,19 @@ def test_chunk_directory_round_trip(tmp_path):
     (tmp_path / "empty").mkdir()
     with pytest.raises(FileNotFoundError):
         io.read_event_frame(tmp_path / "empty")
+
+
+def test_popular_prefix_per_mode_matches_the_reference_text():
+    # covisitation/inference.py:76-83 reads train_20_most_frequent_*, :271-278 reads test_20_most_frequent_*
+    import pathlib
+    import re
+    from otto_multi_objective_recommender_system_b200 import inference
+    assert inference.POPULAR_PREFIX == {"validation": "train", "submission": "test"}
+    ref = pathlib.Path("/root/reference/src/covisitation/inference.py")
+    if not ref.exists():
+        pytest.skip("reference tree not present on this box")
+    text = ref.read_text()
+    val_at, sub_at = text.rindex("if args.mode == 'validation'"), text.rindex("elif args.mode == 'submission'")
+    for mode, (lo, hi) in {"validation": (val_at, sub_at), "submission": (sub_at, len(text))}.items():
+        prefixes = set(re.findall(r"'(\w+)_20_most_frequent_(?:click|cart|order)_aids\.json'", text[lo:hi]))
+        assert prefixes == {inference.POPULAR_PREFIX[mode]}, (mode, prefixes)

@@ -49,19 +49,21 @@ __global__ void runs_kernel(uint2* buf, uint64_t buf_elems, uint32_t run_elems, 
 int main() {
   int n = 0;
   CK(cudaGetDeviceCount(&n));
-  if (n < 2) { printf("needs 2 GPUs\n"); return 0; }
+  const bool have_peer = n >= 2;      // one GPU: local rows only (the scatter ceiling question of DESIGN.md §8)
   int can = 0;
-  CK(cudaDeviceCanAccessPeer(&can, 0, 1));
+  if (have_peer) CK(cudaDeviceCanAccessPeer(&can, 0, 1));
   printf("peer access 0 -> 1: %d\n", can);
   const uint64_t buf_bytes = 2ull << 30, buf_elems = buf_bytes / 8;
   uint2 *local = nullptr, *peer = nullptr;
   uint64_t* sink = nullptr;
-  CK(cudaSetDevice(1));
-  CK(cudaMalloc(&peer, buf_bytes));
-  CK(cudaMemset(peer, 1, buf_bytes));
-  CK(cudaDeviceSynchronize());
-  CK(cudaSetDevice(0));
-  CK(cudaDeviceEnablePeerAccess(1, 0));
+  if (have_peer) {
+    CK(cudaSetDevice(1));
+    CK(cudaMalloc(&peer, buf_bytes));
+    CK(cudaMemset(peer, 1, buf_bytes));
+    CK(cudaDeviceSynchronize());
+    CK(cudaSetDevice(0));
+    CK(cudaDeviceEnablePeerAccess(1, 0));
+  }
   CK(cudaMalloc(&local, buf_bytes));
   CK(cudaMemset(local, 1, buf_bytes));
   CK(cudaMalloc(&sink, 8));
@@ -71,7 +73,7 @@ int main() {
   const uint64_t total_bytes = 4ull << 30;
   const int runs[] = {8, 32, 64, 128, 256, 1024, 8192};
   printf("%-6s %-6s %-9s %8s %10s\n", "where", "op", "align", "run B", "GB/s");
-  for (int where = 0; where < 2; ++where)
+  for (int where = 0; where < (have_peer ? 2 : 1); ++where)
     for (int store = 0; store < 2; ++store)
       for (int aligned = 0; aligned < 2; ++aligned)
         for (int run : runs) {
