@@ -124,8 +124,8 @@ uint64_t otto_launch_count(void);
 
 /* Measurement aid for bench.py: with profiling on, otto_covisit_reduce brackets each of its kernels with CUDA
  * events on the caller's stream; otto_profile_reduce_ms synchronises the last one and returns the five
- * durations of the most recent call (warp kernel, 512-, 256-, 128-thread block kernels, merge_split_rows) in
- * milliseconds.  Profiled calls run the block kernels back to back on the caller's stream; unprofiled calls run
+ * durations of the most recent call (classify + warp tier 0 [bins <= 256 records], block tier 3 [> 3072], block tier 2
+ * [<= 3072], warp tier 1 [<= 1024], merge_split_rows) in milliseconds.  Profiled calls run the block kernels back to back on the caller's stream; unprofiled calls run
  * them concurrently on two internal side streams (forked from and joined to the caller's stream). */
 int otto_profile_enable(int on);
 int otto_profile_reduce_ms(float* ms_host /* [5] */);
@@ -138,6 +138,12 @@ int otto_profile_scatter_ms(float* ms_host /* [3] */);
 /* Checks that (session, ts) is non-decreasing; *sorted_host = 1/0. Synchronises. */
 int otto_frame_is_sorted(const int32_t* session, const int32_t* ts, int64_t n_events, int32_t* flag_dev,
                          int32_t* sorted_host, void* stream);
+
+/* Event contents the kernels index with: counts the rows whose aid is outside [0, n_aids) or whose type is above 2
+ * (the dtypes of utilities/dataset_writer_pickle.py:57-60 allow both).  count_dev: 8 bytes of device scratch.
+ * Returns OTTO_EINVAL (and the count in *n_bad_host) when any row offends.  Synchronises. */
+int otto_frame_check(const int32_t* aid, const uint8_t* type, int64_t n_events, int32_t n_aids, void* count_dev,
+                     int64_t* n_bad_host, void* stream);
 
 /* From a frame sorted by (session, ts) ascending with run-length offsets (ascending CSR), writes the
  * most-recent-first CSR columns: inside each session ts descending, ties in original row order. */
@@ -162,7 +168,10 @@ int otto_covisit_sizes(int64_t n_sessions, int64_t n_events, const OttoCovisitSp
 
 int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
                              int64_t workspace_bytes, void* stream);
-/* Fills stats_host->{tail_events,pairs,bins,split_rows,hot_pairs}; synchronises. */
+/* Fills stats_host->{tail_events,pairs,bins,split_rows,hot_pairs}; synchronises.  OTTO_EINVAL when a tail event carried
+ * an aid outside [0, n_aids), a type above 2 or (time mode) a ts outside [ts_min, ts_max]: count_begin replaces such
+ * events by a harmless one and flags them, so nothing is written out of bounds (in owner-direct mode the pair kernels
+ * store into a peer's memory at positions derived from the aid). */
 int otto_covisit_count_finish(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
                               int64_t workspace_bytes, OttoBuildStats* stats_host, void* stream);
 /* count_begin + count_finish */
@@ -182,8 +191,9 @@ int otto_covisit_views(const OttoEvents* ev, const OttoCovisitSpec* spec, void* 
 int otto_covisit_scatter(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
                          void* records, int64_t records_capacity, void* stream);
 
-/* For bins [bin_lo, bin_hi) = rows [aid_lo, aid_hi): accumulate the records of all segments per
- * (aid_x, aid_y), select the top k per aid_x and write those rows of `out`.  A segment's offsets are
+/* For bins [bin_lo, bin_hi) = rows [aid_lo, aid_hi): accumulate the records of ONE bin-contiguous segment per
+ * (aid_x, aid_y), select the top k per aid_x and write those rows of `out` (n_segments must be 1: a multi-GPU owner
+ * merges what it received with otto_covisit_merge_segments first; OTTO_EINVAL otherwise).  The segment's offsets are
  * indexed by (bin - bin_lo) and may carry any base (offsets[0] is subtracted).  Fills
  * stats_host->{distinct,pair_checksum,table_overflow}; synchronises when stats_host != NULL. */
 int64_t otto_covisit_reduce_scratch_bytes(const OttoCovisitSpec* spec, int64_t n_bins, int64_t n_aids_range);

@@ -93,6 +93,7 @@ _SIGNATURES = {
     "otto_profile_reduce_ms": (C.c_int, [P(C.c_float)]),
     "otto_profile_scatter_ms": (C.c_int, [P(C.c_float)]),
     "otto_frame_is_sorted": (C.c_int, [vp, vp, i64, vp, P(i32), vp]),
+    "otto_frame_check": (C.c_int, [vp, vp, i64, i32, vp, P(i64), vp]),
     "otto_ingest_desc": (C.c_int, [vp, i64, vp, vp, vp, i64, vp, vp, vp, vp]),
     "otto_covisit_sizes": (C.c_int, [i64, i64, P(OttoCovisitSpec), P(OttoBuildSizes)]),
     "otto_covisit_count_begin": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, vp]),

@@ -142,7 +142,10 @@ def ingest(frame: EventFrame, order: str = "desc", device=None) -> EventCSR:
         raise ValueError("frames are limited to 2^31 - 1 events per device")
     with torch.cuda.device(device):
         st = _stream_ptr(device)
-        flag = torch.zeros(1, dtype=torch.int32, device=device)
+        flag = torch.zeros(2, dtype=torch.int64, device=device)
+        # aid in [0, n_aids), type in {0, 1, 2}: every later kernel indexes with them (raises OttoError otherwise)
+        n_bad = C.c_int64(0)
+        N.check(lib.otto_frame_check(aid.data_ptr(), typ.data_ptr(), E, int(frame.n_aids), flag[1:].data_ptr(), C.byref(n_bad), st))
         is_sorted = C.c_int32(0)
         N.check(lib.otto_frame_is_sorted(sess.data_ptr(), ts.data_ptr(), E, flag.data_ptr(), C.byref(is_sorted), st))
         if not is_sorted.value:

@@ -1,5 +1,6 @@
 // C-ABI entry points of the covisitation build (include/otto_covisit.h) and the small kernels around
 // the two hot ones (pairgen.cuh, reduce.cuh): ingest, tail CSR, per-aid pair upper bounds, bins.
+#include <limits.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -46,6 +47,36 @@ extern "C" int otto_frame_is_sorted(const int32_t* session, const int32_t* ts, i
   return OTTO_OK;
 }
 
+// Event contents the kernels index with: aid in [0, n_aids), type in {0, 1, 2}.  Counts the offending rows.
+__global__ void frame_check_kernel(const int32_t* __restrict__ aid, const uint8_t* __restrict__ type, int64_t n, uint32_t n_aids,
+                                   unsigned long long* bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool b = i < n && ((uint32_t)aid[i] >= n_aids || type[i] > 2);
+  const uint32_t m = __ballot_sync(FULL_MASK, b);
+  if (m && lane_id() == 0) atomicAdd(bad, (unsigned long long)__popc(m));
+}
+
+extern "C" int otto_frame_check(const int32_t* aid, const uint8_t* type, int64_t n_events, int32_t n_aids, void* count_dev,
+                                int64_t* n_bad_host, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_aids <= 0 || !count_dev || !n_bad_host) { otto_set_error("bad argument"); return OTTO_EINVAL; }
+  CUDA_TRY(cudaMemsetAsync(count_dev, 0, 8, st));
+  if (n_events > 0) {
+    frame_check_kernel<<<(unsigned)ceil_div(n_events, 256), 256, 0, st>>>(aid, type, n_events, (uint32_t)n_aids,
+                                                                          (unsigned long long*)count_dev);
+    LAUNCH_CHECK();
+  }
+  unsigned long long bad = 0;
+  CUDA_TRY(cudaMemcpyAsync(&bad, count_dev, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *n_bad_host = (int64_t)bad;
+  if (bad) {
+    otto_set_error("%llu events have an aid outside [0, %d) or a type above 2", bad, n_aids);
+    return OTTO_EINVAL;
+  }
+  return OTTO_OK;
+}
+
 // One warp per session: reverse the ascending session so that ts is descending, keeping runs of equal
 // ts in their original order (what the stable ts-descending sort of builder step 2 produces).
 __global__ void __launch_bounds__(256)
@@ -80,6 +111,25 @@ extern "C" int otto_ingest_desc(const int32_t* session_offsets, int64_t n_sessio
 }
 
 // ------------------------------------------------------------------ workspace layout
+
+// What the tail kernels check about every event they copy: the pair kernels index arrays with the aid (row histogram,
+// cursors, owner cuts - in owner-direct mode a PEER's memory), pack the type into two bits and store ts - ts_min as
+// u32.  An offending event is replaced by (aid 0, type 0, ts_lo) so that nothing is written out of bounds, and
+// flagged in stats[STAT_BAD_EVENTS]; count_finish then returns OTTO_EINVAL.
+struct EventLimits {
+  uint32_t n_aids;
+  int32_t ts_lo, ts_hi;   // inclusive range (INT32_MIN .. INT32_MAX outside time mode)
+};
+constexpr int STAT_BAD_EVENTS = 6;
+
+__device__ __forceinline__ void check_event(const EventLimits& lim, int32_t& a, uint32_t& ty, int32_t& t, unsigned long long* stats) {
+  if ((uint32_t)a >= lim.n_aids || ty > 2u || t < lim.ts_lo || t > lim.ts_hi) {
+    a = 0;
+    ty = 0;
+    t = lim.ts_lo;
+    atomicAdd(&stats[STAT_BAD_EVENTS], 1ull);
+  }
+}
 
 struct Layout {
   int64_t S, E, Ecap, A, Bmax, Hmax;
@@ -173,8 +223,8 @@ static int g_profile = 0;
 static cudaEvent_t g_prof_sc[4];
 static bool g_prof_sc_valid = false;
 static int side_streams_init();
-extern cudaStream_t g_side[2];
-extern cudaEvent_t g_fork, g_join[2];
+extern cudaStream_t g_side[3];
+extern cudaEvent_t g_fork, g_join[3];
 
 // ------------------------------------------------------------------ tail CSR + upper bounds
 
@@ -188,7 +238,7 @@ __global__ void tail_count_kernel(const int32_t* __restrict__ off, const uint8_t
   if ((mask & 7u) == 7u) {
     n = min(end - beg, tail_n);
   } else {
-    for (int32_t p = beg; p < end && n < tail_n; ++p) n += (mask >> type[p]) & 1u;
+    for (int32_t p = beg; p < end && n < tail_n; ++p) n += type[p] < 32 ? (mask >> type[p]) & 1u : 0u;
   }
   cnt[s] = (uint32_t)n;
 }
@@ -200,7 +250,8 @@ __global__ void tail_count_kernel(const int32_t* __restrict__ off, const uint8_t
 __global__ void __launch_bounds__(256)
     tail_copy_filtered_kernel(const int32_t* __restrict__ off, const int32_t* __restrict__ aid, const int32_t* __restrict__ ts,
                               const uint8_t* __restrict__ type, int64_t S, uint32_t mask, const uint32_t* __restrict__ tail_off,
-                              uint32_t* __restrict__ tail_aw, int32_t* __restrict__ tail_ts) {
+                              uint32_t* __restrict__ tail_aw, int32_t* __restrict__ tail_ts, const EventLimits lim,
+                              unsigned long long* stats) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
   const uint32_t tb = tail_off[s];
@@ -209,11 +260,12 @@ __global__ void __launch_bounds__(256)
   const int32_t end = off[s + 1];
   uint32_t taken = 0;
   for (int32_t p = off[s]; p < end && taken < n; ++p) {
-    const uint32_t ty = type[p];
-    if ((mask >> ty) & 1u) {
-      const int32_t a = aid[p];
+    uint32_t ty = type[p];
+    if (ty < 32u && ((mask >> ty) & 1u)) {
+      int32_t a = aid[p], t = ts[p];
+      check_event(lim, a, ty, t, stats);
       tail_aw[tb + taken] = (uint32_t)a | (ty << 30);
-      tail_ts[tb + taken] = ts[p];
+      tail_ts[tb + taken] = t;
       ++taken;
     }
   }
@@ -227,7 +279,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     tail_copy_all_kernel(const int32_t* __restrict__ off, const int32_t* __restrict__ aid, const int32_t* __restrict__ ts,
                          const uint8_t* __restrict__ type, int64_t S, const uint32_t* __restrict__ tail_off,
-                         uint32_t* __restrict__ tail_aw, int32_t* __restrict__ tail_ts) {
+                         uint32_t* __restrict__ tail_aw, int32_t* __restrict__ tail_ts, const EventLimits lim,
+                         unsigned long long* stats) {
   const int64_t s0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
   if (s0 >= S) return;
   const int lane = (int)lane_id();
@@ -249,8 +302,11 @@ __global__ void __launch_bounds__(256)
     const uint32_t tu = __shfl_sync(FULL_MASK, to, u);
     const int32_t src = __shfl_sync(FULL_MASK, src0, u) + (int32_t)(q - (tu - T0));
     if (q < total) {
-      tail_aw[T0 + q] = (uint32_t)aid[src] | ((uint32_t)type[src] << 30);
-      tail_ts[T0 + q] = ts[src];
+      int32_t a = aid[src], t = ts[src];
+      uint32_t ty = type[src];
+      check_event(lim, a, ty, t, stats);
+      tail_aw[T0 + q] = (uint32_t)a | (ty << 30);
+      tail_ts[T0 + q] = t;
     }
   }
 }
@@ -507,15 +563,21 @@ extern "C" int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitS
   }
   if ((rc = exclusive_scan<uint32_t, uint32_t>(WS(uint32_t, tail_off), S, WS(uint32_t, tail_off), WS(uint32_t, scan), st)))
     return rc;
+  EventLimits lim;
+  lim.n_aids = (uint32_t)spec->n_aids;
+  const bool time_mode = spec->weight_mode == OTTO_WEIGHT_TIME;
+  lim.ts_lo = time_mode ? spec->ts_min : INT32_MIN;
+  lim.ts_hi = time_mode ? spec->ts_max : INT32_MAX;
   if (S > 0 && (spec->event_type_mask & 7u) == 7u) {
     tail_copy_all_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(ev->session_offsets, ev->aid, ev->ts, ev->type, S,
                                                                      WS(uint32_t, tail_off), WS(uint32_t, tail_aw),
-                                                                     WS(int32_t, tail_ts));
+                                                                     WS(int32_t, tail_ts), lim, WS(unsigned long long, stats));
     LAUNCH_CHECK();
   } else if (S > 0) {
     tail_copy_filtered_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(ev->session_offsets, ev->aid, ev->ts, ev->type, S,
                                                                           spec->event_type_mask, WS(uint32_t, tail_off),
-                                                                          WS(uint32_t, tail_aw), WS(int32_t, tail_ts));
+                                                                          WS(uint32_t, tail_aw), WS(int32_t, tail_ts), lim,
+                                                                          WS(unsigned long long, stats));
     LAUNCH_CHECK();
   }
   if (S > 0) {
@@ -527,6 +589,15 @@ extern "C" int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitS
   // the copy that a multi-GPU host all-reduces; the rank's own counts stay in row_count
   CUDA_TRY(cudaMemcpyAsync(WS(uint32_t, row_total), WS(uint32_t, row_count), (L.A + 1) * 4, cudaMemcpyDeviceToDevice, st));
   return OTTO_OK;
+}
+
+static int bad_events_error(const OttoCovisitSpec* spec, unsigned long long n) {
+  if (spec->weight_mode == OTTO_WEIGHT_TIME)
+    otto_set_error("%llu tail events have an aid outside [0, %d), a type above 2 or a ts outside [ts_min, ts_max] = [%d, %d] "
+                   "(seconds expected; the pickles carry milliseconds)", n, spec->n_aids, spec->ts_min, spec->ts_max);
+  else
+    otto_set_error("%llu tail events have an aid outside [0, %d) or a type above 2", n, spec->n_aids);
+  return OTTO_EINVAL;
 }
 
 // bins from the (all-reduced) row totals, record offsets of this rank's rows, scatter cursors
@@ -555,9 +626,10 @@ extern "C" int otto_covisit_count_finish(const OttoEvents* ev, const OttoCovisit
   count_stats_kernel<<<1, 1, 0, st>>>(WS(uint32_t, tail_off), L.S, WS(uint32_t, bin_base), A, WS(unsigned long long, row_off),
                                       WS(unsigned long long, hot_off), WS(unsigned long long, stats));
   LAUNCH_CHECK();
-  unsigned long long h[5];
+  unsigned long long h[8];
   CUDA_TRY(cudaMemcpyAsync(h, WS(char, stats), sizeof(h), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  if (h[STAT_BAD_EVENTS]) return bad_events_error(spec, h[STAT_BAD_EVENTS]);
   // the bin arrays were sized from the event count: refuse before anything is written past them
   if ((int64_t)h[2] > L.Bmax || (int64_t)h[3] > L.Hmax) {
     otto_set_error("%llu bins / %llu hot rows exceed the %lld / %lld the workspace was sized for: set spec.global_events to the "
@@ -665,6 +737,7 @@ extern "C" int otto_covisit_count_finish_owned(const OttoEvents* ev, const OttoC
   unsigned long long h[32];
   CUDA_TRY(cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  if (h[STAT_BAD_EVENTS]) return bad_events_error(spec, h[STAT_BAD_EVENTS]);
   if ((int64_t)h[2] > L.Bmax || (int64_t)h[3] > L.Hmax) {
     otto_set_error("%llu bins / %llu hot rows exceed the %lld / %lld the workspace was sized for: set spec.global_events to the "
                    "event count of all ranks", h[2], h[3], (long long)L.Bmax, (long long)L.Hmax);
@@ -818,7 +891,7 @@ extern "C" int otto_covisit_partition(const OttoEvents* ev, const OttoCovisitSpe
 // ------------------------------------------------------------------ reduce
 
 struct ScratchLayout {
-  int64_t p_key, p_sum, p_cnt, p_len, list_m, list_l, list_x, counters, stats, total;
+  int64_t p_key, p_sum, p_cnt, p_len, list[4], counters, stats, total;
 };
 
 static ScratchLayout make_scratch(int k, int64_t n_bins, int64_t n_aids_range) {
@@ -832,9 +905,7 @@ static ScratchLayout make_scratch(int k, int64_t n_bins, int64_t n_aids_range) {
   s.p_sum = take(slots * k * 8);
   s.p_cnt = take(slots * k * 4);
   s.p_len = take(slots * 4);
-  s.list_m = take((n_bins + 1) * 4);
-  s.list_l = take((n_bins + 1) * 4);
-  s.list_x = take((n_bins + 1) * 4);
+  for (int t = 0; t < 4; ++t) s.list[t] = take((n_bins + 1) * 4);
   s.counters = take(64);
   s.stats = take(64);
   s.total = o;
@@ -881,12 +952,13 @@ static int set_smem(K kernel, size_t bytes) {
   return OTTO_OK;
 }
 
-// The three block kernels work on disjoint bin lists, so they run concurrently on two side streams (forked
-// after the warp kernel has built the lists, joined before the split-row merge): each of them alone leaves SMs
-// idle in its tail and the 512-thread kernel fills only a quarter of the warp slots.  OTTO_REDUCE_SERIAL=1 keeps
-// everything on the caller's stream.
-cudaStream_t g_side[2];
-cudaEvent_t g_fork, g_join[2];
+// The tier kernels work on disjoint bin lists and are persistent (blocks take work until their list is empty), so they
+// run concurrently on three side streams + the caller's stream, launched largest-footprint first: the 512-thread tier
+// leaves half of an SM's shared memory and three quarters of its warp slots unused, which the blocks of the later
+// launches fill; as a tier runs dry the next one's waiting blocks take its place.  OTTO_REDUCE_SERIAL=1 (and profiled
+// calls) keep everything on the caller's stream.
+cudaStream_t g_side[3];
+cudaEvent_t g_fork, g_join[3];
 static bool g_side_ready = false;
 
 static int side_streams_init() {
@@ -898,58 +970,75 @@ static int side_streams_init() {
   return OTTO_OK;
 }
 
+static int occupancy_blocks(const void* kernel, int threads, size_t smem) {
+  int n = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
+  return n;
+}
+
+template <bool TIME, int TIER>
+static int launch_tier(const ReduceParams& p, int n_sm, cudaStream_t st) {
+  int rc;
+  if (TIER == 0) {
+    auto kern = reduce_warp_kernel<TIME, 9, 256, 0>;
+    constexpr size_t smem = (size_t)WARP_TIER_WARPS * warp_tier_bytes<TIME, 9, 256>();
+    if ((rc = set_smem(kern, smem))) return rc;
+    static const int occ = occupancy_blocks((const void*)kern, WARP_TIER_WARPS * 32, smem);
+    kern<<<n_sm * occ, WARP_TIER_WARPS * 32, smem, st>>>(p);
+  } else if (TIER == 1) {
+    auto kern = reduce_block_kernel<TIME, 128, 11, 1, false>;
+    constexpr size_t smem = reduce_block_smem<TIME, 128, 11, false>();
+    if ((rc = set_smem(kern, smem))) return rc;
+    static const int occ = occupancy_blocks((const void*)kern, 128, smem);
+    kern<<<n_sm * occ, 128, smem, st>>>(p);
+  } else if (TIER == 2) {
+    auto kern = reduce_block_kernel<TIME, 256, 12, 2, false>;
+    constexpr size_t smem = reduce_block_smem<TIME, 256, 12, false>();
+    if ((rc = set_smem(kern, smem))) return rc;
+    static const int occ = occupancy_blocks((const void*)kern, 256, smem);
+    kern<<<n_sm * occ, 256, smem, st>>>(p);
+  } else {
+    auto kern = reduce_block_kernel<TIME, 512, 13, 3, true>;
+    constexpr size_t smem = reduce_block_smem<TIME, 512, 13, true>();
+    if ((rc = set_smem(kern, smem))) return rc;
+    static const int occ = occupancy_blocks((const void*)kern, 512, smem);
+    kern<<<n_sm * occ, 512, smem, st>>>(p);
+  }
+  LAUNCH_CHECK();
+  return OTTO_OK;
+}
+
+// profile slots: [0] classify + warp tier 0, [1] block tier 3, [2] block tier 2, [3] block tier 1, [4] split-row merge
 template <bool TIME>
 static int launch_reduce(const ReduceParams& p, int n_sm, cudaStream_t st) {
   int rc;
   static const bool serial = getenv("OTTO_REDUCE_SERIAL") != nullptr;
   const bool fork = !serial && !g_profile;
   if (fork && (rc = side_streams_init())) return rc;
-  constexpr size_t small_smem = (size_t)SMALL_WARPS * SMALL_PER_WARP;
-  if ((rc = set_smem(reduce_small_kernel<TIME>, small_smem))) return rc;
   const int64_t n_bins = p.bin_hi - p.bin_lo;
-  int64_t small_blocks = ceil_div(n_bins, SMALL_WARPS);
-  if (small_blocks > (int64_t)n_sm * 64) small_blocks = (int64_t)n_sm * 64;
   PROF_MARK(0);
-  reduce_small_kernel<TIME><<<(unsigned)small_blocks, SMALL_WARPS * 32, small_smem, st>>>(p);
+  reduce_classify_kernel<<<(unsigned)ceil_div(n_bins, 256), 256, 0, st>>>(p);
   LAUNCH_CHECK();
-  PROF_MARK(1);
-  cudaStream_t s_l = st, s_x = st;
   if (fork) {
     CUDA_TRY(cudaEventRecord(g_fork, st));
-    CUDA_TRY(cudaStreamWaitEvent(g_side[0], g_fork, 0));
-    CUDA_TRY(cudaStreamWaitEvent(g_side[1], g_fork, 0));
-    s_l = g_side[0];
-    s_x = g_side[1];
-  }
-  {
-    auto kern = reduce_block_kernel<TIME, 512, 13, 2>;
-    constexpr size_t smem = reduce_block_smem<TIME, 512, 13, 2>();
-    if ((rc = set_smem(kern, smem))) return rc;
-    kern<<<n_sm, 512, smem, s_x>>>(p);
-    LAUNCH_CHECK();
-    if (!fork) PROF_MARK(2);
-  }
-  {
-    auto kern = reduce_block_kernel<TIME, 256, 12, 1>;
-    constexpr size_t smem = reduce_block_smem<TIME, 256, 12, 1>();
-    if ((rc = set_smem(kern, smem))) return rc;
-    kern<<<n_sm * 3, 256, smem, s_l>>>(p);
-    LAUNCH_CHECK();
-    if (!fork) PROF_MARK(3);
-  }
-  {
-    auto kern = reduce_block_kernel<TIME, 128, 11, 0>;
-    constexpr size_t smem = reduce_block_smem<TIME, 128, 11, 0>();
-    if ((rc = set_smem(kern, smem))) return rc;
-    kern<<<n_sm * 7, 128, smem, st>>>(p);
-    LAUNCH_CHECK();
-    if (!fork) PROF_MARK(4);
-  }
-  if (fork) {
-    CUDA_TRY(cudaEventRecord(g_join[0], g_side[0]));
-    CUDA_TRY(cudaEventRecord(g_join[1], g_side[1]));
-    CUDA_TRY(cudaStreamWaitEvent(st, g_join[0], 0));
-    CUDA_TRY(cudaStreamWaitEvent(st, g_join[1], 0));
+    for (auto& s : g_side) CUDA_TRY(cudaStreamWaitEvent(s, g_fork, 0));
+    if ((rc = launch_tier<TIME, 3>(p, n_sm, g_side[2]))) return rc;
+    if ((rc = launch_tier<TIME, 2>(p, n_sm, g_side[1]))) return rc;
+    if ((rc = launch_tier<TIME, 1>(p, n_sm, g_side[0]))) return rc;
+    if ((rc = launch_tier<TIME, 0>(p, n_sm, st))) return rc;
+    for (int i = 0; i < 3; ++i) {
+      CUDA_TRY(cudaEventRecord(g_join[i], g_side[i]));
+      CUDA_TRY(cudaStreamWaitEvent(st, g_join[i], 0));
+    }
+  } else {
+    if ((rc = launch_tier<TIME, 0>(p, n_sm, st))) return rc;
+    PROF_MARK(1);
+    if ((rc = launch_tier<TIME, 3>(p, n_sm, st))) return rc;
+    PROF_MARK(2);
+    if ((rc = launch_tier<TIME, 2>(p, n_sm, st))) return rc;
+    PROF_MARK(3);
+    if ((rc = launch_tier<TIME, 1>(p, n_sm, st))) return rc;
+    PROF_MARK(4);
   }
   merge_split_rows_kernel<<<n_sm * 4, 256, 0, st>>>(p);
   LAUNCH_CHECK();
@@ -965,7 +1054,10 @@ extern "C" int otto_covisit_reduce(const OttoCovisitSpec* spec, const uint32_t* 
                                    void* stream) {
   int rc = check_spec(spec);
   if (rc) return rc;
-  if (n_segments < 1 || n_segments > OTTO_MAX_SEGMENTS) { otto_set_error("n_segments must be in [1, 8]"); return OTTO_EINVAL; }
+  if (n_segments != 1 || !segments_host) {
+    otto_set_error("otto_covisit_reduce takes ONE bin-contiguous segment: merge received segments first (otto_covisit_merge_segments)");
+    return OTTO_EINVAL;
+  }
   if (!out || out->k != spec->k || out->n_aids != spec->n_aids) { otto_set_error("output table shape does not match the spec"); return OTTO_EINVAL; }
   if (bin_hi < bin_lo || aid_hi < aid_lo) { otto_set_error("empty or inverted range"); return OTTO_EINVAL; }
   const ScratchLayout SL = make_scratch(spec->k, bin_hi - bin_lo, aid_hi - aid_lo);
@@ -976,8 +1068,8 @@ extern "C" int otto_covisit_reduce(const OttoCovisitSpec* spec, const uint32_t* 
   cudaStream_t st = (cudaStream_t)stream;
   ReduceParams p;
   memset(&p, 0, sizeof(p));
-  for (int s = 0; s < n_segments; ++s) p.seg[s] = segments_host[s];
-  p.n_seg = n_segments;
+  p.records = (const uint2*)segments_host[0].records;
+  p.offsets = segments_host[0].offsets;
   p.bin_x = bin_x;
   p.bin_base = bin_base;
   p.bin_lo = bin_lo;
@@ -988,6 +1080,12 @@ extern "C" int otto_covisit_reduce(const OttoCovisitSpec* spec, const uint32_t* 
   p.time_mode = spec->weight_mode == OTTO_WEIGHT_TIME;
   p.w_scale = p.time_mode ? 3.0 / (double)(spec->ts_max - spec->ts_min) : 0.0;
   p.range = p.time_mode ? (uint32_t)(spec->ts_max - spec->ts_min) : 0u;
+  p.y_bits = 0;
+  while (p.y_bits < 31 && (1ll << p.y_bits) < (int64_t)spec->n_aids) ++p.y_bits;
+  p.max_v = 1;
+  if (spec->weight_mode == OTTO_WEIGHT_TYPE)
+    for (int i = 0; i < 3; ++i)
+      if ((uint32_t)spec->type_weight[i] > p.max_v) p.max_v = (uint32_t)spec->type_weight[i];
   p.out_y = out->aid_y;
   p.out_w = out->wgt;
   p.out_len = out->len;
@@ -998,9 +1096,7 @@ extern "C" int otto_covisit_reduce(const OttoCovisitSpec* spec, const uint32_t* 
   p.p_sum = (uint64_t*)(sc + SL.p_sum);
   p.p_cnt = (uint32_t*)(sc + SL.p_cnt);
   p.p_len = (int32_t*)(sc + SL.p_len);
-  p.list_m = (uint32_t*)(sc + SL.list_m);
-  p.list_l = (uint32_t*)(sc + SL.list_l);
-  p.list_x = (uint32_t*)(sc + SL.list_x);
+  for (int t = 0; t < 4; ++t) p.list[t] = (uint32_t*)(sc + SL.list[t]);
   p.counters = (uint32_t*)(sc + SL.counters);
   p.stats = (unsigned long long*)(sc + SL.stats);
   CUDA_TRY(cudaMemsetAsync(p.counters, 0, 64, st));

@@ -12,28 +12,31 @@
 //   type / unit  wgt = float(sum)                               (exact below 2^24)
 // Final order key = (float bits of wgt) << 32 | ~aid_y, so a plain max implements (wgt desc, aid_y asc).
 //
-// What the round-1 profiles taught (profiles/r01_*): the kernels are instruction-issue bound, not HBM
-// bound, so the work per record is what matters:
-//   * claimed slots are appended to an "occupied" list, so the sweeps and the clearing touch the d
-//     distinct entries instead of all table slots;
-//   * 64-bit shared atomicAdd compiles to a CAS spin loop (ATOMS.CAST.SPIN.64); the time sum is kept as a
-//     32-bit low word plus a packed word (count in bits 0-23, carries of the low word in bits 24-31);
-//   * top-K: sweep 1 takes, per lane, the max of an integer order key I = count * R + 3 * tsum (exactly
-//     proportional to the weight; no fp64); the K-th largest of the 32 lane-group maxima is a lower bound
-//     T on the K-th largest entry; sweep 2 pushes the entries with I >= T - T * 2^-22 (about 1.5 K of
-//     them; the margin covers entries that tie with T after fp32 rounding) into a candidate list, for
-//     which the exact float keys are formed and rank-sorted by one warp.  If an adversarial layout
-//     overflows the list, an exact K-round selection over the table runs instead.
-// Three size classes share the code: a warp with a 512-slot table per bin, a 128-thread block (2048
-// slots) and a 256-thread block (4096 slots) that falls back to several aid_y-hash passes when a bin
-// exceeds its table.  Slices of split rows write partial top-K lists; merge_split_rows() picks the final
-// K (slices hold disjoint aid_y, so the merge is a pure selection).
+// Round-2 design (v5).  The round-1 kernels issued 9.6 warp-instructions per record where the insert itself
+// needs about one; the rest was paid per bin and per warp (profiles/README.md).  What changed:
+//   * selection works on a 32-bit order key: time mode the top 32 bits of count * R + 3 * tsum (shift from the
+//     bin's record count), type / unit mode (sum << s) | top bits of ~aid_y, i.e. the final order itself as far as
+//     32 bits reach.  The K-th largest of the 32 lane-group maxima (a 32-bit bitonic network, ~75 instructions
+//     instead of ~530 for 64-bit keys) is a lower bound of the K-th largest entry; entries at or above it
+//     (minus the fp32 rounding margin in time mode) are the ~25-35 candidates whose exact keys one warp ranks;
+//   * sweep 1 keeps every entry's key in registers, so sweep 2 is a compare per entry plus the reset of the entry's
+//     slot; only candidates read their payload again.  Nothing else touches the table, so one pass resets it;
+//   * bins of up to 1024 records are processed by ONE warp each (no block barriers at all, the occupied-list
+//     counter lives in a register), in two table sizes; larger bins by a block with three barriers per bin:
+//     the ranking of bin b's candidates by warp 0 overlaps the inserts of bin b + 1 (candidate lists and the
+//     block's counters are double buffered, record chunks are handed out dynamically);
+//   * a classify kernel builds one work list per tier; bin metadata is fetched 32 (warp tiers) or 8 (block tiers)
+//     bins at a time, for the block tiers one batch ahead;
+//   * if the candidate list overflows (adversarial ties), the bin is re-inserted and an exact K-round selection
+//     runs instead.
+// Slices of split rows write partial top-K lists; merge_split_rows() picks the final K (slices hold disjoint
+// aid_y, so the merge is a pure selection).
 #pragma once
 #include "common.cuh"
 
 struct ReduceParams {
-  OttoPairSegment seg[OTTO_MAX_SEGMENTS];
-  int32_t n_seg;
+  const uint2* records;      // the one segment of this call
+  const uint64_t* offsets;   // offsets[b - bin_lo] .. offsets[b - bin_lo + 1] bound bin b; offsets[0] is subtracted
   const uint32_t* bin_x;     // [B] bin -> aid_x (global bin ids)
   const uint32_t* bin_base;  // [A + 1]
   int64_t bin_lo, bin_hi;    // this call's bins
@@ -42,6 +45,8 @@ struct ReduceParams {
   int32_t time_mode;
   uint32_t range;            // ts_max - ts_min (time mode)
   double w_scale;            // 3 / (ts_max - ts_min)
+  uint32_t y_bits;           // bits of n_aids - 1
+  uint32_t max_v;            // largest record value outside time mode (largest type weight, or 1)
   int32_t* out_y;
   float* out_w;
   int32_t* out_len;
@@ -52,165 +57,236 @@ struct ReduceParams {
   uint64_t* p_sum;
   uint32_t* p_cnt;
   int32_t* p_len;
-  // work lists for the block kernels
-  uint32_t* list_m;
-  uint32_t* list_l;
-  uint32_t* list_x;
-  uint32_t* counters;        // [0] n_m  [1] n_l  [2] next_m  [3] next_l  [4] n_x  [5] next_x
+  uint32_t* list[4];         // work list of every tier: bin - bin_lo
+  uint32_t* counters;        // [0..3] items per tier, [4..7] next item per tier
   unsigned long long* stats; // [0] distinct  [1] checksum  [2] overflow  [3] slow-path selections  [4..7] records per tier
 };
 
-constexpr uint32_t TINY_MAX = 32;      // records: one step of one warp, no table at all
-constexpr uint32_t SMALL_MAX = 256;    // records: warp kernel, 512-slot table
-constexpr uint32_t MEDIUM_MAX = 1024;  // records: 128-thread kernel, 2048-slot table
-constexpr uint32_t LARGE_MAX = 3072;   // records: 256-thread kernel, 4096-slot table
-// beyond: 512-thread kernel, 8192-slot table; single pass up to 3/4 of the slots, else aid_y-hash passes
+constexpr uint32_t TINY_MAX = 32;     // records: one step of one warp, no table at all
+constexpr uint32_t TIER0_MAX = 256, TIER1_MAX = 1024, TIER2_MAX = 3072;   // records per bin of tiers 0, 1, 2; tier 3 takes the rest
+constexpr int N_CAND = 64;            // candidates a fast selection may produce
+constexpr int N_CAND_BUF = N_CAND + OTTO_MAX_K;   // block tiers: + the best list carried between hash passes
+constexpr uint32_t KEY_NONE = 0u;     // table keys are aid_y + 1
 
 __device__ __forceinline__ int64_t partial_slot(const ReduceParams& p, uint32_t x, uint32_t j) {
   const int64_t extra = ((int64_t)p.bin_base[x] - x) - (p.bin_lo - p.aid_lo);
   return 2 * extra + j;
 }
 
-__device__ __forceinline__ uint32_t bin_records(const ReduceParams& p, int64_t b) {
-  uint32_t n = 0;
-  for (int s = 0; s < p.n_seg; ++s) n += (uint32_t)(p.seg[s].offsets[b - p.bin_lo + 1] - p.seg[s].offsets[b - p.bin_lo]);
-  return n;
-}
+__device__ __forceinline__ uint64_t bin_start(const ReduceParams& p, int64_t b) { return p.offsets[b - p.bin_lo] - p.offsets[0]; }
 
-// single-segment fast path: the bin's run (NULL when the bin is spread over several segments)
-__device__ __forceinline__ const uint2* bin_run(const ReduceParams& p, int64_t b) {
-  if (p.n_seg != 1) return nullptr;
-  return (const uint2*)p.seg[0].records + (p.seg[0].offsets[b - p.bin_lo] - p.seg[0].offsets[0]);
-}
-
-// record i of bin b in the concatenation of the segments' runs (i < bin_records)
-__device__ __forceinline__ uint2 bin_record(const ReduceParams& p, int64_t b, uint32_t i) {
-  for (int s = 0; s < p.n_seg; ++s) {
-    const uint64_t beg = p.seg[s].offsets[b - p.bin_lo], end = p.seg[s].offsets[b - p.bin_lo + 1];
-    const uint32_t len = (uint32_t)(end - beg);
-    if (i < len) return ld_stream_u2((const uint2*)p.seg[s].records + (beg - p.seg[s].offsets[0]) + i);
-    i -= len;
+// ---- work lists: one thread per bin ----
+__global__ void __launch_bounds__(256) reduce_classify_kernel(const ReduceParams p) {
+  const int64_t b = p.bin_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int tier = -1;
+  if (b < p.bin_hi) {
+    const uint64_t n = p.offsets[b - p.bin_lo + 1] - p.offsets[b - p.bin_lo];
+    tier = n <= TIER0_MAX ? 0 : n <= TIER1_MAX ? 1 : n <= TIER2_MAX ? 2 : 3;
   }
-  return make_uint2(KEY_EMPTY, 0);
+  const uint32_t lt = lanemask_lt();
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const uint32_t m = __ballot_sync(FULL_MASK, tier == t);
+    if (m == 0) continue;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(&p.counters[t], (uint32_t)__popc(m));
+    base = __shfl_sync(FULL_MASK, base, leader);
+    if (tier == t) p.list[t][base + __popc(m & lt)] = (uint32_t)(b - p.bin_lo);
+  }
 }
 
-// Open-addressing table over SLOTS = 2^LOG slots.  TIME: hc = count | carries << 24, lo = low 32 bits of
-// the time sum.  !TIME: lo = integer weight sum (hc unused).
+// Shared memory is addressed through 32-bit shared-space addresses and inline PTX: with generic pointers carved from
+// the dynamic allocation the compiler rebuilt the shared window base (S2UR SR_CgaCtaId + 3 uniform ops) in front of
+// every access and wrapped single-lane atomics into its own aggregation sequence - the insert path of v5a issued 380
+// instructions per 64 records (profiles/r02_reduce_v5a_*), three quarters of the kernel.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t atoms_cas(uint32_t addr, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(addr), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void reds_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
+}
+__device__ __forceinline__ void sts_zero16(uint32_t addr) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+}
+
+// Open-addressing table over SLOTS = 2^LOG slots, keys = aid_y + 1 (0 = free), double hashing.
+// Payload of slot h: TIME an 8-byte pair {lo, hc} - lo = low 32 bits of the time sum, hc = (count - 1) | carries of
+// lo << 24, so that the record that claims a slot (three records in four here) only adds to lo; !TIME a 4-byte integer
+// weight sum.  Keys and payloads are contiguous, so a full reset is one run of 16-byte stores.
 template <bool TIME, int LOG>
 struct Table {
   static constexpr uint32_t SLOTS = 1u << LOG;
-  uint32_t* keys;
-  uint32_t* lo;
-  uint32_t* hc;
-  uint16_t* occ;     // claimed slots, in claim order
-  uint32_t* n_occ;
+  static constexpr uint32_t BYTES = SLOTS * (TIME ? 12u : 8u);
+  static constexpr uint32_t PSHIFT = TIME ? 3 : 2;   // log2 of the payload stride
+  uint32_t keys_s, pay_s;        // shared-space byte addresses
+  uint32_t occ_s;                // claimed slots (u16), in claim order
 
+  __device__ __forceinline__ void carve(const void* base, const void* occ) {
+    keys_s = smem_u32(base);
+    pay_s = keys_s + SLOTS * 4;
+    occ_s = smem_u32(occ);
+  }
+  __device__ __forceinline__ uint32_t occ(uint32_t i) const { return lds_u16(occ_s + i * 2); }
+  __device__ __forceinline__ uint32_t key(uint32_t h) const { return lds_u32(keys_s + h * 4); }
+  // {lo, hc} of slot h (hc = 0 outside time mode)
+  __device__ __forceinline__ uint2 payload(uint32_t h) const {
+    return TIME ? lds_u64(pay_s + (h << 3)) : make_uint2(lds_u32(pay_s + (h << 2)), 0u);
+  }
+  __device__ __forceinline__ void set_key(uint32_t h, uint32_t k) { sts_u32(keys_s + h * 4, k); }
   __device__ __forceinline__ void clear_all(uint32_t tid, uint32_t nthreads) {
-    for (uint32_t h = tid; h < SLOTS; h += nthreads) {
-      keys[h] = KEY_EMPTY;
-      lo[h] = 0;
-      if (TIME) hc[h] = 0;
-    }
-    if (tid == 0) *n_occ = 0;
+    for (uint32_t i = tid; i < BYTES / 16; i += nthreads) sts_zero16(keys_s + i * 16);
   }
-  // resets exactly the claimed slots (n = *n_occ read by the caller after a barrier)
-  __device__ __forceinline__ void clear_dirty(uint32_t tid, uint32_t nthreads, uint32_t n) {
-    for (uint32_t i = tid; i < n; i += nthreads) {
-      const uint32_t h = occ[i];
-      keys[h] = KEY_EMPTY;
-      lo[h] = 0;
-      if (TIME) hc[h] = 0;
-    }
+  __device__ __forceinline__ void clear_slot(uint32_t h) {
+    sts_u32(keys_s + h * 4, KEY_NONE);
+    if (TIME) sts_u64(pay_s + (h << 3), 0u, 0u);
+    else sts_u32(pay_s + (h << 2), 0u);
   }
-  // One record per lane (has = this lane holds one); EVERY lane of the warp must call.  Returns false on
-  // overflow.  The probe loop only finds / claims the slot.  Lanes leave it after different numbers of
-  // probes, and without the __syncwarp() below the compiler keeps them diverged: profile r01_reduce_v3b
-  // shows the payload atomics and the occupied-list append executing with 6.7 of 32 lanes per issue
-  // (45 % of all instructions of the kernel).  After reconvergence the append is one atomic per warp.
-  __device__ __forceinline__ bool insert(bool has, uint32_t y, uint32_t v) {
-    // double hashing: slot from the top bits of a Fibonacci hash, odd stride from a second multiplier.  The
-    // profile of the linear-probing version (r01_reduce_v3c) showed ~14 probe iterations per 32-record step
-    // (the slowest lane decides), at 16 SASS instructions each: the probe loop was 3/4 of the kernel.
-    const uint32_t hm = y * 0x9E3779B1u;
-    uint32_t h = hm >> (32 - LOG);
-    const uint32_t step = ((y * 0x85EBCA6Bu) >> (32 - LOG)) | 1u;
-    uint32_t prev = 0x80000000u;   // neither EMPTY nor an aid (aids are < 2^30)
-    if (has) {
-#pragma unroll 1
-      for (uint32_t probe = SLOTS; probe; --probe) {
-        prev = atomicCAS(&keys[h], KEY_EMPTY, y);
-        if (prev == KEY_EMPTY || prev == y) break;
-        h = (h + step) & (SLOTS - 1);
-      }
+  // Two records per lane: both first probes are in flight together (at the load factors here most records settle on
+  // the first probe); the few that collide walk their double-hashing sequence in a short divergent loop each.  EVERY
+  // lane of the warp must call.  A lane's two records may carry the same aid_y: the second CAS then finds the first
+  // one's claim.  The __syncwarp() reconverges the lanes before the warp-wide append to the occupied list.
+  // LOCAL: n_occ_reg is a warp-uniform register counter (one warp owns the table); else n_occ_s is the shared-space
+  // address of the block's counter.  Returns false when the table is full.
+  template <bool LOCAL>
+  __device__ __forceinline__ bool insert2(bool has0, uint32_t y0, uint32_t v0, bool has1, uint32_t y1, uint32_t v1,
+                                          uint32_t& n_occ_reg, uint32_t n_occ_s) {
+    const uint32_t k0 = y0 + 1u, k1 = y1 + 1u;
+    uint32_t a0 = keys_s + (((y0 * 0x9E3779B1u) >> (32 - LOG)) << 2), a1 = keys_s + (((y1 * 0x9E3779B1u) >> (32 - LOG)) << 2);
+    uint32_t prev0 = k0, prev1 = k1;
+    if (has0) prev0 = atoms_cas(a0, KEY_NONE, k0);
+    if (has1) prev1 = atoms_cas(a1, KEY_NONE, k1);
+    if (prev0 != KEY_NONE && prev0 != k0) {
+      const uint32_t step = (((y0 * 0x85EBCA6Bu) >> (32 - LOG)) | 1u) << 2;
+      uint32_t left = SLOTS;
+      do {
+        a0 = keys_s + ((a0 - keys_s + step) & (SLOTS * 4 - 1));
+        prev0 = atoms_cas(a0, KEY_NONE, k0);
+      } while (prev0 != KEY_NONE && prev0 != k0 && --left);
     }
-    const int state = !has ? 0 : prev == KEY_EMPTY ? 2 : (prev == y ? 1 : 0);  // 2 = claimed a fresh slot, 1 = found
+    if (prev1 != KEY_NONE && prev1 != k1) {
+      const uint32_t step = (((y1 * 0x85EBCA6Bu) >> (32 - LOG)) | 1u) << 2;
+      uint32_t left = SLOTS;
+      do {
+        a1 = keys_s + ((a1 - keys_s + step) & (SLOTS * 4 - 1));
+        prev1 = atoms_cas(a1, KEY_NONE, k1);
+      } while (prev1 != KEY_NONE && prev1 != k1 && --left);
+    }
     __syncwarp();
-    const uint32_t fresh = __ballot_sync(FULL_MASK, state == 2);
-    if (fresh) {
-      const int leader = __ffs(fresh) - 1;
-      uint32_t base = 0;
-      if ((int)lane_id() == leader) base = atomicAdd(n_occ, (uint32_t)__popc(fresh));
-      base = __shfl_sync(FULL_MASK, base, leader);
-      if (state == 2) occ[base + __popc(fresh & lanemask_lt())] = (uint16_t)h;
-    }
-    if (state != 0) {
-      const uint32_t old = atomicAdd(&lo[h], v);
-      if (TIME) atomicAdd(&hc[h], 1u + ((old + v < old) ? (1u << 24) : 0u));
-    }
-    return state != 0 || !has;
-  }
-  // Two records per lane with their probe sequences interleaved: both CAS are in flight together, and the loop
-  // control, the reconvergence, the occupied-list append (one atomic for both) are paid once per 64 records.
-  // A lane's two records may carry the same aid_y: the second CAS then finds the first one's claim.
-  __device__ __forceinline__ bool insert2(bool has0, uint32_t y0, uint32_t v0, bool has1, uint32_t y1, uint32_t v1) {
-    uint32_t h0 = (y0 * 0x9E3779B1u) >> (32 - LOG), h1 = (y1 * 0x9E3779B1u) >> (32 - LOG);
-    const uint32_t step0 = ((y0 * 0x85EBCA6Bu) >> (32 - LOG)) | 1u, step1 = ((y1 * 0x85EBCA6Bu) >> (32 - LOG)) | 1u;
-    uint32_t prev0 = 0x80000000u, prev1 = 0x80000000u;
-    bool p0 = has0, p1 = has1;
-#pragma unroll 1
-    for (uint32_t probe = SLOTS; probe && (p0 || p1); --probe) {
-      if (p0) prev0 = atomicCAS(&keys[h0], KEY_EMPTY, y0);
-      if (p1) prev1 = atomicCAS(&keys[h1], KEY_EMPTY, y1);
-      if (p0) {
-        if (prev0 == KEY_EMPTY || prev0 == y0) p0 = false;
-        else h0 = (h0 + step0) & (SLOTS - 1);
-      }
-      if (p1) {
-        if (prev1 == KEY_EMPTY || prev1 == y1) p1 = false;
-        else h1 = (h1 + step1) & (SLOTS - 1);
-      }
-    }
-    const int state0 = (!has0 || p0) ? 0 : prev0 == KEY_EMPTY ? 2 : 1;
-    const int state1 = (!has1 || p1) ? 0 : prev1 == KEY_EMPTY ? 2 : 1;
-    __syncwarp();
-    const uint32_t fresh0 = __ballot_sync(FULL_MASK, state0 == 2), fresh1 = __ballot_sync(FULL_MASK, state1 == 2);
+    const bool ok0 = prev0 == KEY_NONE || prev0 == k0, ok1 = prev1 == KEY_NONE || prev1 == k1;
+    const uint32_t fresh0 = __ballot_sync(FULL_MASK, has0 && prev0 == KEY_NONE);
+    const uint32_t fresh1 = __ballot_sync(FULL_MASK, has1 && prev1 == KEY_NONE);
     if (fresh0 | fresh1) {
-      uint32_t base = 0;
-      if (lane_id() == 0) base = atomicAdd(n_occ, (uint32_t)(__popc(fresh0) + __popc(fresh1)));
-      base = __shfl_sync(FULL_MASK, base, 0);
+      const uint32_t n0 = (uint32_t)__popc(fresh0), add = n0 + (uint32_t)__popc(fresh1);
+      uint32_t base;
+      if (LOCAL) {
+        base = n_occ_reg;
+        n_occ_reg = base + add;
+      } else {
+        base = 0;
+        if (lane_id() == 0) base = atoms_add(n_occ_s, add);
+        base = __shfl_sync(FULL_MASK, base, 0);
+      }
       const uint32_t lt = lanemask_lt();
-      if (state0 == 2) occ[base + __popc(fresh0 & lt)] = (uint16_t)h0;
-      if (state1 == 2) occ[base + __popc(fresh0) + __popc(fresh1 & lt)] = (uint16_t)h1;
+      if (has0 && prev0 == KEY_NONE) sts_u16(occ_s + (base + __popc(fresh0 & lt)) * 2, (a0 - keys_s) >> 2);
+      if (has1 && prev1 == KEY_NONE) sts_u16(occ_s + (base + n0 + __popc(fresh1 & lt)) * 2, (a1 - keys_s) >> 2);
     }
-    if (state0 != 0) {
-      const uint32_t old = atomicAdd(&lo[h0], v0);
-      if (TIME) atomicAdd(&hc[h0], 1u + ((old + v0 < old) ? (1u << 24) : 0u));
+    if (has0 && ok0) {
+      const uint32_t pa = pay_s + ((a0 - keys_s) << (PSHIFT - 2));
+      const uint32_t old = atoms_add(pa, v0);
+      if (TIME) {
+        const uint32_t inc = (prev0 == k0 ? 1u : 0u) + ((old + v0 < old) ? (1u << 24) : 0u);
+        if (inc) reds_add(pa + 4, inc);
+      }
     }
-    if (state1 != 0) {
-      const uint32_t old = atomicAdd(&lo[h1], v1);
-      if (TIME) atomicAdd(&hc[h1], 1u + ((old + v1 < old) ? (1u << 24) : 0u));
+    if (has1 && ok1) {
+      const uint32_t pa = pay_s + ((a1 - keys_s) << (PSHIFT - 2));
+      const uint32_t old = atoms_add(pa, v1);
+      if (TIME) {
+        const uint32_t inc = (prev1 == k1 ? 1u : 0u) + ((old + v1 < old) ? (1u << 24) : 0u);
+        if (inc) reds_add(pa + 4, inc);
+      }
     }
-    return (state0 != 0 || !has0) && (state1 != 0 || !has1);
+    return ok0 && ok1;
   }
-  __device__ __forceinline__ uint32_t count(uint32_t h) const { return TIME ? (hc[h] & 0xffffffu) : 0u; }
-  __device__ __forceinline__ uint64_t sum(uint32_t h) const {
-    return TIME ? (((uint64_t)(hc[h] >> 24) << 32) | lo[h]) : (uint64_t)lo[h];
-  }
-  // integer order key, exactly proportional to the weight
-  __device__ __forceinline__ uint64_t ikey(uint32_t h, uint32_t range) const {
-    return TIME ? (uint64_t)count(h) * range + 3ull * sum(h) : (uint64_t)lo[h];
-  }
+  static __device__ __forceinline__ uint32_t count_of(uint2 pl) { return TIME ? (pl.y & 0xffffffu) + 1u : 0u; }
+  static __device__ __forceinline__ uint64_t sum_of(uint2 pl) { return TIME ? (((uint64_t)(pl.y >> 24) << 32) | pl.x) : (uint64_t)pl.x; }
+  __device__ __forceinline__ uint32_t count(uint32_t h) const { return count_of(payload(h)); }
+  __device__ __forceinline__ uint64_t sum(uint32_t h) const { return sum_of(payload(h)); }
 };
+
+// 32-bit order key of an entry, monotone (non-strictly) in the final order of the bin
+struct KeyCfg {
+  uint32_t shift;    // time: key = (count * R + 3 * tsum) >> shift
+  uint32_t s;        // type / unit: key = (sum << s) | ((~y & ymask) >> yshift)
+  uint32_t yshift, ymask;
+  uint32_t range;
+};
+template <bool TIME>
+__device__ __forceinline__ KeyCfg make_cfg(const ReduceParams& p, uint32_t n) {
+  KeyCfg c;
+  c.range = p.range;
+  c.shift = c.s = c.yshift = c.ymask = 0;
+  if (TIME) {
+    const int bits = 64 - __clzll((long long)(4ull * n * p.range));   // count * R + 3 * tsum <= 4 n R
+    c.shift = bits > 32 ? (uint32_t)(bits - 32) : 0u;
+  } else {
+    const unsigned long long top = (unsigned long long)n * p.max_v;
+    const int wbits = top ? 64 - __clzll((long long)top) : 1;
+    int s = wbits >= 32 ? 0 : 32 - wbits;
+    if (s > (int)p.y_bits) s = (int)p.y_bits;
+    c.s = (uint32_t)s;
+    c.yshift = p.y_bits - (uint32_t)s;
+    c.ymask = p.y_bits >= 32 ? 0xffffffffu : ((1u << p.y_bits) - 1u);
+  }
+  return c;
+}
+template <bool TIME>
+__device__ __forceinline__ uint32_t key32(const KeyCfg& c, uint32_t key, uint32_t lo, uint32_t hc) {
+  if (TIME) {
+    const uint64_t ik = (uint64_t)((hc & 0xffffffu) + 1u) * c.range + 3ull * (((uint64_t)(hc >> 24) << 32) | lo);
+    return (uint32_t)(ik >> c.shift);
+  }
+  const uint32_t y = key - 1u;
+  return c.s ? ((lo << c.s) | ((~y & c.ymask) >> c.yshift)) : lo;
+}
+// time mode: entries whose fp32 weight can tie with the threshold entry's lie within 2^-23 of it
+template <bool TIME>
+__device__ __forceinline__ uint32_t cand_threshold(uint32_t thr) {
+  if (!TIME) return thr;
+  const uint32_t m = (thr >> 22) + 1u;
+  return thr > m ? thr - m : 0u;
+}
 
 __device__ __forceinline__ uint64_t float_key(bool time_mode, uint32_t y, uint32_t cnt, uint64_t sum, double w_scale) {
   const float w = time_mode ? (float)((double)cnt + w_scale * (double)sum) : (float)sum;
@@ -224,27 +300,20 @@ struct Cands {
   uint32_t* cnt;
 };
 
-// Bitonic sort of one u64 per lane, descending (lane 0 ends with the largest).
-__device__ __forceinline__ uint64_t warp_sort_desc(uint64_t v) {
+// K-th largest of the 32 lane values (0 if fewer than k lanes are non-zero): descending bitonic network
+__device__ __forceinline__ uint32_t warp_kth_largest32(uint32_t v, int k) {
   const uint32_t lane = lane_id();
 #pragma unroll
-  for (int k = 2; k <= 32; k <<= 1) {
+  for (int kk = 2; kk <= 32; kk <<= 1) {
 #pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const uint32_t olo = __shfl_xor_sync(FULL_MASK, (uint32_t)v, j);
-      const uint32_t ohi = __shfl_xor_sync(FULL_MASK, (uint32_t)(v >> 32), j);
-      const uint64_t o = ((uint64_t)ohi << 32) | olo;
-      const bool keep_max = ((lane & j) == 0) == ((lane & k) == 0);
-      v = keep_max ? (o > v ? o : v) : (o < v ? o : v);
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      const uint32_t o = __shfl_xor_sync(FULL_MASK, v, j);
+      const bool keep_max = ((lane & j) == 0) == ((lane & kk) == 0);
+      v = keep_max ? max(v, o) : min(v, o);
     }
   }
-  return v;
+  return __shfl_sync(FULL_MASK, v, k - 1);
 }
-// K-th largest of the 32 lane values (0 if fewer than k lanes are non-zero).
-__device__ __forceinline__ uint64_t warp_kth_largest(uint64_t v, int k) { return shfl_u64(warp_sort_desc(v), k - 1); }
-
-// candidates must reach T minus the fp32 tie margin
-__device__ __forceinline__ uint64_t with_margin(uint64_t thr) { return thr > (thr >> 22) + 1 ? thr - (thr >> 22) - 1 : 0; }
 
 // One warp: ranks the n_c candidates (distinct non-zero keys, unordered) and hands every candidate with
 // rank < k to `emit(rank, key, cnt, sum)`.  Returns min(n_c, k).
@@ -260,8 +329,8 @@ __device__ __forceinline__ int warp_rank_emit(const Cands& c, int n_c, int k, Em
   return n_c < k ? n_c : k;
 }
 
-// Exact K-round selection over occupied entries [lo, hi) of the occ list (slow path for candidate-list
-// overflow).  One warp; results (best first) land in dst[dst_base ..); returns how many.
+// Exact K-round selection over occupied entries [lo, hi) of the occ list (slow path: candidate-list overflow).
+// One warp; results (best first) land in dst[dst_base ..); returns how many.  Marks taken keys with bit 31.
 template <bool TIME, int LOG>
 __device__ __forceinline__ int warp_select_slow(Table<TIME, LOG>& t, uint32_t lo, uint32_t hi, int k, double w_scale,
                                                 Cands dst, int dst_base) {
@@ -269,10 +338,10 @@ __device__ __forceinline__ int warp_select_slow(Table<TIME, LOG>& t, uint32_t lo
   auto scan = [&](uint64_t& best, uint32_t& best_h) {
     best = 0;
     for (uint32_t i = lo + lane; i < hi; i += 32) {
-      const uint32_t h = t.occ[i];
-      const uint32_t y = t.keys[h];
-      if (y & KEY_TAKEN) continue;
-      const uint64_t kk = float_key(TIME, y, t.count(h), t.sum(h), w_scale);
+      const uint32_t h = t.occ(i);
+      const uint32_t key = t.key(h);
+      if (key & KEY_TAKEN) continue;
+      const uint64_t kk = float_key(TIME, key - 1u, t.count(h), t.sum(h), w_scale);
       if (kk > best) { best = kk; best_h = h; }
     }
   };
@@ -287,7 +356,7 @@ __device__ __forceinline__ int warp_select_slow(Table<TIME, LOG>& t, uint32_t lo
       dst.key[dst_base + found] = m;
       dst.sum[dst_base + found] = t.sum(best_h);
       dst.cnt[dst_base + found] = t.count(best_h);
-      t.keys[best_h] |= KEY_TAKEN;
+      t.set_key(best_h, t.key(best_h) | KEY_TAKEN);
       scan(best, best_h);
     }
   }
@@ -341,321 +410,366 @@ __device__ __forceinline__ void emit_finish(const ReduceParams& p, const BinOut&
   }
 }
 
-// warp-aggregated append of candidate (y, cnt, sum) with its exact float key; q = this lane has one
-template <int CAP>
-__device__ __forceinline__ void push_candidate(bool q, uint32_t* n_cand, const Cands& c, bool time_mode, uint32_t y,
-                                               uint32_t cnt, uint64_t sum, double w_scale) {
-  const uint32_t m = __ballot_sync(FULL_MASK, q);
-  if (m == 0) return;
-  uint32_t base = 0;
-  if (lane_id() == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(n_cand, (uint32_t)__popc(m));
-  base = __shfl_sync(FULL_MASK, base, __ffs(m) - 1);
-  if (q) {
-    const uint32_t at = base + __popc(m & lanemask_lt());
-    if (at < (uint32_t)CAP) {
-      c.key[at] = float_key(time_mode, y, cnt, sum, w_scale);
-      c.sum[at] = sum;
-      c.cnt[at] = cnt;
-    }
-  }
+struct BinStats {
+  uint64_t occ = 0, pay = 0, rec = 0;
+  uint32_t slow = 0;
+  bool overflow = false;
+};
+
+// =====================================================================================================
+// warp tiers: one warp per bin, no block-level synchronisation
+// =====================================================================================================
+constexpr int WARP_TIER_WARPS = 4;
+
+template <bool TIME, int LOG, int NMAX>
+__host__ __device__ constexpr uint32_t warp_tier_bytes() {   // per warp: cand key / sum (u64) | table | cand cnt | occ (u16)
+  return N_CAND * 16 + Table<TIME, LOG>::BYTES + N_CAND * 4 + NMAX * 2;
 }
 
-// ---- small bins: one warp per bin ----
-constexpr int SMALL_WARPS = 4;
-constexpr int SMALL_LOG = 9;           // 512 slots
-constexpr int SMALL_CANDS = 64;
-constexpr int SMALL_DIRECT = 32;       // up to this many distinct entries: skip the threshold
-// per warp: cand key[64] sum[64] (u64) | keys[512] lo[512] hc[512] cand cnt[64] counters[4] (u32) | occ[256] (u16)
-constexpr uint32_t SMALL_PER_WARP = SMALL_CANDS * 16 + (1u << SMALL_LOG) * 12 + SMALL_CANDS * 4 + 16 + SMALL_MAX * 2;
-
+// the whole bin is one step: fold duplicates with match_any, rank the group leaders
 template <bool TIME>
-__global__ void __launch_bounds__(SMALL_WARPS * 32) reduce_small_kernel(const ReduceParams p) {
+__device__ __forceinline__ void tiny_bin(const ReduceParams& p, const BinOut& o, const uint2* run, uint32_t n, BinStats& st) {
+  const uint32_t lane = lane_id();
+  const bool has = lane < n;
+  uint2 r = make_uint2(0x80000000u | lane, 0);
+  if (has) r = ld_stream_u2(run + lane);
+  const uint32_t lt = lanemask_lt();
+  const uint32_t peers = __match_any_sync(FULL_MASK, r.x);
+  const bool lead = has && (peers & lt) == 0;
+  const uint32_t cnt = TIME ? (uint32_t)__popc(peers) : 0u;
+  uint64_t sum = r.y;
+  uint32_t rest = lead ? (peers & (peers - 1)) : 0u;
+  while (__any_sync(FULL_MASK, rest != 0)) {
+    const int src = rest ? __ffs(rest) - 1 : (int)lane;
+    const uint32_t vv = __shfl_sync(FULL_MASK, r.y, src);
+    if (rest) {
+      sum += vv;
+      rest &= rest - 1;
+    }
+  }
+  const uint64_t key = lead ? float_key(TIME, r.x, cnt, sum, p.w_scale) : 0ull;
+  const uint32_t lm = __ballot_sync(FULL_MASK, lead);
+  int rank = 0;
+  for (uint32_t m = lm; m; m &= m - 1) rank += shfl_u64(key, __ffs(m) - 1) > key;
+  if (lead && rank < p.k) emit_entry(p, o, rank, key, cnt, sum);
+  const int nl = __popc(lm);
+  emit_finish(p, o, nl < p.k ? nl : p.k);
+  if (lane == 0) st.occ += nl;
+  if (lead) st.pay += TIME ? (uint64_t)cnt : sum;
+}
+
+template <bool TIME, int LOG, int NMAX, int TIER>
+__global__ void __launch_bounds__(WARP_TIER_WARPS * 32) reduce_warp_kernel(const ReduceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  unsigned char* base = smem_raw + warp * SMALL_PER_WARP;
-  constexpr uint32_t SLOTS = 1u << SMALL_LOG;
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, lt = lanemask_lt();
+  unsigned char* base = smem_raw + warp * warp_tier_bytes<TIME, LOG, NMAX>();
   Cands c;
   c.key = (uint64_t*)base;
-  c.sum = c.key + SMALL_CANDS;
-  Table<TIME, SMALL_LOG> t;
-  t.keys = (uint32_t*)(c.sum + SMALL_CANDS);
-  t.lo = t.keys + SLOTS;
-  t.hc = t.lo + SLOTS;
-  c.cnt = t.hc + SLOTS;
-  uint32_t* n_cand = c.cnt + SMALL_CANDS;
-  t.n_occ = n_cand + 1;
-  t.occ = (uint16_t*)(n_cand + 4);
+  c.sum = c.key + N_CAND;
+  Table<TIME, LOG> t;
+  unsigned char* tb = (unsigned char*)(c.sum + N_CAND);
+  c.cnt = (uint32_t*)(tb + Table<TIME, LOG>::BYTES);
+  t.carve(tb, c.cnt + N_CAND);
   t.clear_all(lane, 32);
   __syncwarp();
+  constexpr int EPT = NMAX / 32;   // entries per lane: d <= n <= NMAX
 
-  uint64_t st_occ = 0, st_pay = 0, st_rec = 0;
-  uint32_t st_slow = 0;
-  bool overflow = false;
-  const int64_t n_warps = (int64_t)gridDim.x * SMALL_WARPS;
-  // A warp takes 32 consecutive bins at a time: lane l walks the dependent metadata loads of bin c0 + l (record
-  // offsets, bin -> aid_x, first bin of the row), so their latency is paid once per 32 bins instead of once per
-  // bin (r01: with one chain per bin the kernels were bound by exactly these round trips), then the bins are
-  // processed one by one with the metadata coming from registers.
-  for (int64_t c0 = p.bin_lo + ((int64_t)blockIdx.x * SMALL_WARPS + warp) * 32; c0 < p.bin_hi; c0 += n_warps * 32) {
-    const int64_t bl = c0 + lane;
-    const bool inb = bl < p.bin_hi;
-    const uint32_t n_l = inb ? bin_records(p, bl) : 0u;
-    if (inb && n_l > SMALL_MAX) {  // hand over to a block kernel
-      if (n_l <= MEDIUM_MAX) p.list_m[atomicAdd(&p.counters[0], 1u)] = (uint32_t)(bl - p.bin_lo);
-      else if (n_l <= LARGE_MAX) p.list_l[atomicAdd(&p.counters[1], 1u)] = (uint32_t)(bl - p.bin_lo);
-      else p.list_x[atomicAdd(&p.counters[4], 1u)] = (uint32_t)(bl - p.bin_lo);
-    }
+  BinStats st;
+  const uint32_t n_items = p.counters[TIER];
+  const uint32_t* list = p.list[TIER];
+  // A warp takes 32 consecutive list items at a time (one atomic per 32 bins): lane l walks the dependent metadata
+  // loads of item c0 + l (list -> record offsets -> bin -> aid_x -> first bin of the row), so their latency is paid
+  // once per 32 bins.
+  while (true) {
+    uint32_t c0 = 0;
+    if (lane == 0) c0 = atomicAdd(&p.counters[4 + TIER], 32u);
+    c0 = __shfl_sync(FULL_MASK, c0, 0);
+    if (c0 >= n_items) break;
+    const bool inb = c0 + lane < n_items;
+    uint32_t n_l = 0;
     BinOut o_l;
     o_l.whole = true;
     o_l.row = 0;
     o_l.x = 0;
     const uint2* run_l = nullptr;
-    if (inb && n_l <= SMALL_MAX) {
+    if (inb) {
+      const int64_t bl = p.bin_lo + list[c0 + lane];
+      const uint64_t beg = p.offsets[bl - p.bin_lo], end = p.offsets[bl - p.bin_lo + 1];
+      n_l = (uint32_t)(end - beg);
       o_l = bin_out(p, bl);
-      run_l = bin_run(p, bl);
+      run_l = p.records + (beg - p.offsets[0]);
     }
-    uint32_t todo = __ballot_sync(FULL_MASK, inb && n_l <= SMALL_MAX);
-    while (todo) {
-    const int srcl = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const int64_t b = c0 + srcl;
-    const uint32_t n = __shfl_sync(FULL_MASK, n_l, srcl);
-    BinOut o;
-    o.whole = __shfl_sync(FULL_MASK, (int)o_l.whole, srcl) != 0;
-    o.row = (int64_t)shfl_u64((uint64_t)o_l.row, srcl);
-    o.x = __shfl_sync(FULL_MASK, o_l.x, srcl);
-    const uint2* run = (const uint2*)shfl_u64((uint64_t)(uintptr_t)run_l, srcl);
-    if (n == 0) {
-      emit_finish(p, o, 0);
-      continue;
-    }
-    if (lane == 0) st_rec += n;
-    if (n <= TINY_MAX) {
-      // the whole bin is one step: fold duplicates with match_any, rank the group leaders, done
-      const bool has = lane < n;
-      uint2 r = make_uint2(0x80000000u | lane, 0);
-      if (has) r = run ? ld_stream_u2(run + lane) : bin_record(p, b, lane);
-      const uint32_t lt = lanemask_lt();
-      const uint32_t peers = __match_any_sync(FULL_MASK, r.x);
-      const bool lead = has && (peers & lt) == 0;
-      const uint32_t cnt = TIME ? (uint32_t)__popc(peers) : 0u;
-      uint64_t sum = r.y;
-      uint32_t rest = lead ? (peers & (peers - 1)) : 0u;
-      while (__any_sync(FULL_MASK, rest != 0)) {
-        const int src = rest ? __ffs(rest) - 1 : (int)lane;
-        const uint32_t vv = __shfl_sync(FULL_MASK, r.y, src);
-        if (rest) {
-          sum += vv;
-          rest &= rest - 1;
+    const int n_here = min(32u, n_items - c0);
+    for (int srcl = 0; srcl < n_here; ++srcl) {
+      const uint32_t n = __shfl_sync(FULL_MASK, n_l, srcl);
+      BinOut o;
+      o.whole = __shfl_sync(FULL_MASK, (int)o_l.whole, srcl) != 0;
+      o.row = (int64_t)shfl_u64((uint64_t)o_l.row, srcl);
+      o.x = __shfl_sync(FULL_MASK, o_l.x, srcl);
+      const uint2* run = (const uint2*)shfl_u64((uint64_t)(uintptr_t)run_l, srcl);
+      if (n == 0) {
+        emit_finish(p, o, 0);
+        continue;
+      }
+      if (lane == 0) st.rec += n;
+      if (n <= TINY_MAX) {
+        tiny_bin<TIME>(p, o, run, n, st);
+        continue;
+      }
+      const KeyCfg cfg = make_cfg<TIME>(p, n);
+      bool slow = false;
+      while (true) {
+        // ---- insert: two records per lane and step, the next two in flight while the current ones are inserted
+        uint32_t d = 0;
+        {
+          bool h0 = lane < n, h1 = 32 + lane < n;
+          uint2 q0 = make_uint2(0, 0), q1 = make_uint2(0, 0);
+          if (h0) q0 = ld_stream_u2(run + lane);
+          if (h1) q1 = ld_stream_u2(run + 32 + lane);
+          for (uint32_t i0 = 0; i0 < n; i0 += 64) {
+            const bool a0 = h0, a1 = h1;
+            const uint2 r0 = q0, r1 = q1;
+            h0 = i0 + 64 + lane < n;
+            h1 = i0 + 96 + lane < n;
+            if (h0) q0 = ld_stream_u2(run + i0 + 64 + lane);
+            if (h1) q1 = ld_stream_u2(run + i0 + 96 + lane);
+            if (!t.template insert2<true>(a0, r0.x, r0.y, a1, r1.x, r1.y, d, 0u)) st.overflow = true;
+          }
         }
+        __syncwarp();
+        if (slow) {   // exact selection straight from the table (candidate list overflowed on the first attempt)
+          for (uint32_t i = lane; i < d; i += 32) st.pay += TIME ? (uint64_t)t.count(t.occ(i)) : t.sum(t.occ(i));
+          const int n_c = warp_select_slow<TIME, LOG>(t, 0, d, p.k, p.w_scale, c, 0);
+          const int found = warp_rank_emit(c, n_c, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) { emit_entry(p, o, r, kk, cnt, sum); });
+          emit_finish(p, o, found);
+          for (uint32_t i = lane; i < d; i += 32) t.clear_slot(t.occ(i));
+          if (lane == 0) { st.occ += d; ++st.slow; }
+          __syncwarp();
+          break;
+        }
+        // ---- sweep 1: 32-bit keys into registers, lane maxima -> threshold
+        uint32_t k32[EPT];
+        uint32_t best = 0, pay = 0;
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+          k32[j] = 0;
+          if ((uint32_t)j * 32 >= d) break;
+          const uint32_t i = j * 32 + lane;
+          if (i < d) {
+            const uint32_t h = t.occ(i);
+            const uint2 pl = t.payload(h);
+            k32[j] = key32<TIME>(cfg, TIME ? 0u : t.key(h), pl.x, pl.y) + 1u;   // + 1: 0 means "no entry" (saturation is harmless)
+            if (k32[j] == 0) k32[j] = 0xffffffffu;
+            pay += TIME ? (pl.y & 0xffffffu) + 1u : pl.x;
+            best = max(best, k32[j]);
+          }
+        }
+        uint32_t thr = 0;
+        if (d > 32) thr = cand_threshold<TIME>(warp_kth_largest32(best, p.k));
+        // ---- sweep 2: candidates read their payload again; every entry resets its slot
+        uint32_t n_c = 0;
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+          if ((uint32_t)j * 32 >= d) break;
+          const uint32_t i = j * 32 + lane;
+          const bool mine = i < d;
+          const bool q = mine && k32[j] >= thr;
+          const uint32_t m = __ballot_sync(FULL_MASK, q);
+          const uint32_t h = mine ? t.occ(i) : 0u;
+          if (q) {
+            const uint32_t at = n_c + __popc(m & lt);
+            if (at < (uint32_t)N_CAND) {
+              const uint2 pl = t.payload(h);
+              const uint32_t cnt = t.count_of(pl);
+              const uint64_t sum = t.sum_of(pl);
+              c.key[at] = float_key(TIME, t.key(h) - 1u, cnt, sum, p.w_scale);
+              c.sum[at] = sum;
+              c.cnt[at] = cnt;
+            }
+          }
+          n_c += __popc(m);
+          if (mine) t.clear_slot(h);
+        }
+        __syncwarp();
+        if (n_c > (uint32_t)N_CAND) {   // adversarial ties: insert again and select exactly
+          slow = true;
+          continue;
+        }
+        const int found = warp_rank_emit(c, (int)n_c, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) { emit_entry(p, o, r, kk, cnt, sum); });
+        emit_finish(p, o, found);
+        st.pay += pay;
+        if (lane == 0) st.occ += d;
+        __syncwarp();
+        break;
       }
-      const uint64_t key = lead ? float_key(TIME, r.x, cnt, sum, p.w_scale) : 0ull;
-      const uint32_t lm = __ballot_sync(FULL_MASK, lead);
-      int rank = 0;
-      for (uint32_t m = lm; m; m &= m - 1) rank += shfl_u64(key, __ffs(m) - 1) > key;
-      if (lead && rank < p.k) emit_entry(p, o, rank, key, cnt, sum);
-      const int nl = __popc(lm);
-      emit_finish(p, o, nl < p.k ? nl : p.k);
-      if (lane == 0) st_occ += nl;
-      if (lead) st_pay += TIME ? (uint64_t)cnt : sum;
-      continue;
-    }
-    if (lane == 0) *n_cand = 0;
-    for (int s = 0; s < (run ? 1 : p.n_seg); ++s) {
-      uint64_t beg = 0, end = n;
-      const uint2* rec = run;
-      if (!run) {
-        const uint64_t o0 = p.seg[s].offsets[0];
-        beg = p.seg[s].offsets[b - p.bin_lo] - o0;
-        end = p.seg[s].offsets[b - p.bin_lo + 1] - o0;
-        rec = (const uint2*)p.seg[s].records;
-      }
-      for (uint64_t i0 = beg; i0 < end; i0 += 64) {
-        const bool has0 = i0 + lane < end, has1 = i0 + 32 + lane < end;
-        uint2 r0 = make_uint2(0, 0), r1 = make_uint2(0, 0);
-        if (has0) r0 = ld_stream_u2(rec + i0 + lane);
-        if (has1) r1 = ld_stream_u2(rec + i0 + 32 + lane);
-        if (!t.insert2(has0, r0.x, r0.y, has1, r1.x, r1.y)) overflow = true;
-      }
-    }
-    __syncwarp();
-    const uint32_t d = *t.n_occ;
-    // sweep 1: lane maxima of the integer key -> threshold
-    uint64_t thr = 0;
-    if (d > SMALL_DIRECT) {
-      uint64_t best = 0;
-      for (uint32_t i = lane; i < d; i += 32) {
-        const uint64_t ik = t.ikey(t.occ[i], p.range);
-        best = ik > best ? ik : best;
-      }
-      thr = with_margin(warp_kth_largest(best, p.k));
-    }
-    // sweep 2: candidates (+ stats)
-    for (uint32_t i0 = 0; i0 < d; i0 += 32) {
-      const uint32_t i = i0 + lane;
-      bool q = false;
-      uint32_t y = 0, cnt = 0;
-      uint64_t sum = 0;
-      if (i < d) {
-        const uint32_t h = t.occ[i];
-        y = t.keys[h];
-        cnt = t.count(h);
-        sum = t.sum(h);
-        st_pay += TIME ? (uint64_t)cnt : sum;
-        q = t.ikey(h, p.range) >= thr;
-      }
-      push_candidate<SMALL_CANDS>(q, n_cand, c, TIME, y, cnt, sum, p.w_scale);
-    }
-    st_occ += (lane == 0) ? d : 0;
-    __syncwarp();
-    int n_c = (int)*n_cand;
-    if (n_c > SMALL_CANDS) {  // adversarial layout: exact K-round selection straight from the table
-      ++st_slow;
-      n_c = warp_select_slow<TIME, SMALL_LOG>(t, 0, d, p.k, p.w_scale, c, 0);
-    }
-    const int found = warp_rank_emit(c, n_c, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) {
-      emit_entry(p, o, r, kk, cnt, sum);
-    });
-    emit_finish(p, o, found);
-    t.clear_dirty(lane, 32, d);
-    if (lane == 0) *t.n_occ = 0;
-    __syncwarp();
     }
   }
   // one stats update per warp
   for (int off = 16; off > 0; off >>= 1) {
-    st_occ += shfl_u64(st_occ, lane ^ off);
-    st_slow += __shfl_xor_sync(FULL_MASK, st_slow, off);
-    st_pay += shfl_u64(st_pay, lane ^ off);
+    st.occ += shfl_u64(st.occ, lane ^ off);
+    st.slow += __shfl_xor_sync(FULL_MASK, st.slow, off);
+    st.pay += shfl_u64(st.pay, lane ^ off);
+    st.rec += shfl_u64(st.rec, lane ^ off);
   }
-  if (lane == 0 && (st_occ || st_pay)) {
-    atomicAdd(&p.stats[0], (unsigned long long)st_occ);
-    atomicAdd(&p.stats[1], (unsigned long long)st_pay);
-    if (st_slow) atomicAdd(&p.stats[3], (unsigned long long)(st_slow / 32));
+  if (lane == 0 && (st.occ || st.pay)) {
+    atomicAdd(&p.stats[0], (unsigned long long)st.occ);
+    atomicAdd(&p.stats[1], (unsigned long long)st.pay);
+    if (st.slow) atomicAdd(&p.stats[3], (unsigned long long)st.slow);
   }
-  if (lane == 0 && st_rec) atomicAdd(&p.stats[4], (unsigned long long)st_rec);
-  if (overflow) atomicOr(&p.stats[2], 1ull);
+  if (lane == 0 && st.rec) atomicAdd(&p.stats[4 + TIER], (unsigned long long)st.rec);
+  if (st.overflow) atomicOr(&p.stats[2], 1ull);
 }
 
-// ---- medium / large bins: one block per bin, work taken from a list through an atomic cursor ----
-constexpr int BLOCK_CANDS = 128;
+// =====================================================================================================
+// block tiers: one block per bin, three barriers per bin
+// =====================================================================================================
+// MULTI: bins beyond SINGLE_CAP records are accumulated in several aid_y-hash passes (records compacted per warp
+// before inserting so that every insert step runs 32 wide); the best K of every pass are carried into the next.
+template <bool TIME, int THREADS, int LOG, bool MULTI>
+constexpr size_t reduce_block_smem() {
+  // cand key / sum x2 buffers, best key / sum (u64) | table | cand cnt x2, best cnt (u32) | occ (u16) | stage (u64)
+  constexpr size_t SLOTS = (size_t)1 << LOG;
+  constexpr size_t NCB = MULTI ? N_CAND_BUF : N_CAND;
+  return 2 * NCB * 16 + OTTO_MAX_K * 16 + Table<TIME, LOG>::BYTES + 2 * NCB * 4 + OTTO_MAX_K * 4 + SLOTS * 2 +
+         (MULTI ? (size_t)(THREADS / 32) * 64 * 8 : 0);
+}
 
-// TIER 0: medium list, 1: large list, 2: extra-large list (single pass up to 3/4 of the slots, otherwise
-// aid_y-hash passes whose records are first compacted per warp so that every insert step runs 32 wide)
-template <bool TIME, int THREADS, int LOG, int TIER>
-__global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParams p) {
+template <bool TIME, int THREADS, int LOG, int TIER, bool MULTI>
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 7 : THREADS == 256 ? 3 : 1) reduce_block_kernel(const ReduceParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int WARPS = THREADS / 32;
   constexpr uint32_t SLOTS = 1u << LOG;
-  constexpr int NC = BLOCK_CANDS + OTTO_MAX_K;     // candidates + room for the carried best list
-  __shared__ uint32_t s_ncand, s_nocc;
-  __shared__ uint64_t s_gmax[WARPS][32];
-  __shared__ uint64_t s_thr;
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  // carve: cand key[NC'] sum[NC'] | best key[K] sum[K] (u64) | keys lo hc | cand cnt[NC'] best cnt[K] (u32) | occ (u16)
-  constexpr int NCX = (NC > WARPS * OTTO_MAX_K ? NC : WARPS * OTTO_MAX_K) + OTTO_MAX_K;
-  Cands c, best;
-  c.key = (uint64_t*)smem_raw;
-  c.sum = c.key + NCX;
-  best.key = c.sum + NCX;
-  best.sum = best.key + OTTO_MAX_K;
-  Table<TIME, LOG> t;
-  t.keys = (uint32_t*)(best.sum + OTTO_MAX_K);
-  t.lo = t.keys + SLOTS;
-  t.hc = t.lo + SLOTS;
-  c.cnt = t.hc + (TIME ? SLOTS : 0);
-  best.cnt = c.cnt + NCX;
-  t.occ = (uint16_t*)(best.cnt + OTTO_MAX_K);
-  t.n_occ = &s_nocc;
-  uint2* stage = (uint2*)(t.occ + SLOTS) + warp * 64;    // TIER 2 only (see reduce_block_smem)
-  constexpr int CUR = TIER == 0 ? 2 : TIER == 1 ? 3 : 5;
-  constexpr uint32_t SINGLE_CAP = TIER == 2 ? SLOTS / 4 * 3 : 0xffffffffu;
-  const uint32_t lt = lanemask_lt();
-
-  const uint32_t* list = TIER == 0 ? p.list_m : TIER == 1 ? p.list_l : p.list_x;
-  const uint32_t n_items = p.counters[TIER == 0 ? 0 : TIER == 1 ? 1 : 4];
-  uint64_t st_occ = 0, st_pay = 0, st_rec = 0;
-  uint32_t st_slow = 0;
-  bool overflow = false;
-  t.clear_all(threadIdx.x, THREADS);
-  // Work items are taken BATCH at a time and their metadata (dependent loads: list -> record offsets -> bin ->
-  // aid_x -> first bin of the row) is fetched by BATCH threads in parallel into shared memory: one chain of round
-  // trips per batch instead of one per bin (the ablation in profiles/README.md: with empty tables and no inserts
-  // the block kernels still took half their time, all of it in these chains).
+  constexpr int EPT = SLOTS / THREADS;              // entries per thread: d <= SLOTS
+  constexpr uint32_t SINGLE_CAP = SLOTS / 4 * 3;    // records a single pass takes
   constexpr int BATCH = 8;
-  __shared__ uint32_t s_first;
-  __shared__ uint32_t s_mn[BATCH], s_mx[BATCH], s_mwhole[BATCH];
-  __shared__ int64_t s_mb[BATCH], s_mrow[BATCH];
-  __shared__ const uint2* s_mrun[BATCH];
-  if (threadIdx.x == 0) s_first = atomicAdd(&p.counters[CUR], (uint32_t)BATCH);
+  constexpr int NCB = MULTI ? N_CAND_BUF : N_CAND;   // candidate buffer: + the carried best list of hash passes
+  static_assert(WARPS >= 2, "the metadata prefetch runs on warp 1");
+  __shared__ uint32_t s_ncand[2], s_nocc[2], s_chunk[2];
+  __shared__ uint32_t s_gmax[WARPS][32];
+  __shared__ uint32_t s_first[2], s_slow;
+  __shared__ uint32_t s_mn[2][BATCH], s_mx[2][BATCH], s_mwhole[2][BATCH];
+  __shared__ int64_t s_mrow[2][BATCH];
+  __shared__ const uint2* s_mrun[2][BATCH];
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, lt = lanemask_lt();
+  // candidate lists of the two parities are slices of one array each (no pointer arrays: they would live in local memory)
+  Cands c_all, best;
+  c_all.key = (uint64_t*)smem_raw;
+  c_all.sum = c_all.key + 2 * NCB;
+  best.key = c_all.sum + 2 * NCB;
+  best.sum = best.key + OTTO_MAX_K;
+  unsigned char* tb = (unsigned char*)(best.sum + OTTO_MAX_K);
+  c_all.cnt = (uint32_t*)(tb + Table<TIME, LOG>::BYTES);
+  best.cnt = c_all.cnt + 2 * NCB;
+  auto cands = [&](int parity) {
+    Cands r;
+    r.key = c_all.key + parity * NCB;
+    r.sum = c_all.sum + parity * NCB;
+    r.cnt = c_all.cnt + parity * NCB;
+    return r;
+  };
+  Table<TIME, LOG> t;
+  t.carve(tb, best.cnt + OTTO_MAX_K);
+  uint2* stage = (uint2*)((uint16_t*)(best.cnt + OTTO_MAX_K) + SLOTS) + warp * 64;    // MULTI only
+
+  const uint32_t* list = p.list[TIER];
+  const uint32_t n_items = p.counters[TIER];
+  BinStats st;
+  t.clear_all(threadIdx.x, THREADS);
+  if (threadIdx.x < 2) {
+    s_ncand[threadIdx.x] = 0;
+    s_nocc[threadIdx.x] = 0;
+    s_chunk[threadIdx.x] = 0;
+  }
+  if (threadIdx.x == 0) s_slow = 0;
+  // metadata of a batch of work items: dependent loads list -> record offsets -> bin -> aid_x -> first bin of the row,
+  // fetched by BATCH lanes of warp 1 into buffer `buf`; one chain of round trips per batch
+  auto fetch_batch = [&](int buf) {   // called by warp 1 only
+    uint32_t first = 0;
+    if (lane == 0) first = atomicAdd(&p.counters[4 + TIER], (uint32_t)BATCH);
+    first = __shfl_sync(FULL_MASK, first, 0);
+    if (lane == 0) s_first[buf] = first;
+    if (lane < BATCH && first + lane < n_items) {
+      const int64_t bb = p.bin_lo + list[first + lane];
+      const uint64_t beg = p.offsets[bb - p.bin_lo], end = p.offsets[bb - p.bin_lo + 1];
+      const BinOut ob = bin_out(p, bb);
+      s_mn[buf][lane] = (uint32_t)(end - beg);
+      s_mx[buf][lane] = ob.x;
+      s_mwhole[buf][lane] = ob.whole ? 1u : 0u;
+      s_mrow[buf][lane] = ob.row;
+      s_mrun[buf][lane] = p.records + (beg - p.offsets[0]);
+    }
+  };
+  if (warp == 1) fetch_batch(0);
   __syncthreads();
-  while (true) {
-    const uint32_t first = s_first;
+  int par = 0;      // parity of the running bin: candidate list / counters in use
+  // what warp 0 still owes for the previous bin (ranking of its candidates overlaps this bin's inserts)
+  bool owe = false;
+  BinOut owe_o;
+  int owe_par = 0;
+  auto settle = [&]() {   // warp 0 only
+    if (!owe) return;
+    const int n_c = (int)s_ncand[owe_par];
+    const int found = warp_rank_emit(cands(owe_par), n_c, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) { emit_entry(p, owe_o, r, kk, cnt, sum); });
+    emit_finish(p, owe_o, found);
+    __syncwarp();
+    owe = false;
+  };
+  for (int buf = 0;; buf ^= 1) {
+    const uint32_t first = s_first[buf];
     if (first >= n_items) break;
     const uint32_t n_batch = min((uint32_t)BATCH, n_items - first);
-    if (threadIdx.x < n_batch) {
-      const int64_t bb = p.bin_lo + list[first + threadIdx.x];
-      const BinOut ob = bin_out(p, bb);
-      s_mb[threadIdx.x] = bb;
-      s_mn[threadIdx.x] = bin_records(p, bb);
-      s_mx[threadIdx.x] = ob.x;
-      s_mwhole[threadIdx.x] = ob.whole ? 1u : 0u;
-      s_mrow[threadIdx.x] = ob.row;
-      s_mrun[threadIdx.x] = bin_run(p, bb);
-    }
-    __syncthreads();
-    for (uint32_t k = 0; k < n_batch; ++k) {
-    const int64_t b = s_mb[k];
-    const uint32_t n = s_mn[k];
-    const uint32_t n_pass = n > SINGLE_CAP ? (n + SLOTS / 2 - 1) / (SLOTS / 2) : 1;
-    BinOut o;
-    o.x = s_mx[k];
-    o.whole = s_mwhole[k] != 0;
-    o.row = s_mrow[k];
-    const uint2* run = s_mrun[k];
-    if (threadIdx.x == 0) st_rec += n;
-    int n_best = 0;  // meaningful in warp 0
-    for (uint32_t pass = 0; pass < n_pass; ++pass) {
-      const bool last = pass + 1 == n_pass;
-      if (threadIdx.x == 0) s_ncand = 0;
-      uint32_t n_st = 0;   // records staged by this warp (multi-pass only)
-      for (int s = 0; s < (run ? 1 : p.n_seg); ++s) {
-        uint64_t beg = 0, end = n;
-        const uint2* rec = run;
-        if (!run) {
-          const uint64_t o0 = p.seg[s].offsets[0];
-          beg = p.seg[s].offsets[b - p.bin_lo] - o0;
-          end = p.seg[s].offsets[b - p.bin_lo + 1] - o0;
-          rec = (const uint2*)p.seg[s].records;
-        }
+    bool fetched = false;
+    for (uint32_t kb = 0; kb < n_batch; ++kb) {
+      const uint32_t n = s_mn[buf][kb];
+      BinOut o;
+      o.x = s_mx[buf][kb];
+      o.whole = s_mwhole[buf][kb] != 0;
+      o.row = s_mrow[buf][kb];
+      const uint2* run = s_mrun[buf][kb];
+      const uint32_t n_pass = (MULTI && n > SINGLE_CAP) ? (n + SLOTS / 2 - 1) / (SLOTS / 2) : 1;
+      const KeyCfg cfg = make_cfg<TIME>(p, n);
+      if (threadIdx.x == 0) st.rec += n;
+      int n_best = 0;   // meaningful in warp 0 (multi-pass)
+      bool slow = false;
+      for (uint32_t pass = 0; pass < n_pass; ++pass) {
+        const bool last = pass + 1 == n_pass;
+        const Cands cp = cands(par);
+        const uint32_t nocc_s = smem_u32(&s_nocc[par]), chunk_s = smem_u32(&s_chunk[par]);
+        uint32_t dummy = 0;
+        // ---- insert: 64-record chunks handed out dynamically (warp 0 joins late while it ranks the previous bin)
+        if (warp == 0) settle();
         if (n_pass == 1) {
-          // two records per thread and step, the next two in flight while the current ones are inserted
-          auto fetch = [&](uint64_t i0, bool& h0, uint2& q0, bool& h1, uint2& q1) {
-            h0 = i0 + threadIdx.x < end;
-            h1 = i0 + THREADS + threadIdx.x < end;
-            q0 = q1 = make_uint2(0, 0);
-            if (h0) q0 = ld_stream_u2(rec + i0 + threadIdx.x);
-            if (h1) q1 = ld_stream_u2(rec + i0 + THREADS + threadIdx.x);
+          auto grab = [&]() {
+            uint32_t cidx = 0;
+            if (lane == 0) cidx = atoms_add(chunk_s, 1u);
+            return __shfl_sync(FULL_MASK, cidx, 0);
           };
-          bool n0, n1;
-          uint2 q0, q1;
-          fetch(beg, n0, q0, n1, q1);
-          for (uint64_t i0 = beg; i0 < end; i0 += 2 * THREADS) {
-            const bool h0 = n0, h1 = n1;
+          uint32_t i0 = grab() * 64;
+          bool h0 = i0 + lane < n, h1 = i0 + 32 + lane < n;
+          uint2 q0 = make_uint2(0, 0), q1 = make_uint2(0, 0);
+          if (h0) q0 = ld_stream_u2(run + i0 + lane);
+          if (h1) q1 = ld_stream_u2(run + i0 + 32 + lane);
+          while (i0 < n) {
+            const bool a0 = h0, a1 = h1;
             const uint2 r0 = q0, r1 = q1;
-            fetch(i0 + 2 * THREADS, n0, q0, n1, q1);
-            if (!t.insert2(h0, r0.x, r0.y, h1, r1.x, r1.y)) overflow = true;
+            i0 = grab() * 64;
+            h0 = i0 + lane < n;
+            h1 = i0 + 32 + lane < n;
+            if (h0) q0 = ld_stream_u2(run + i0 + lane);
+            if (h1) q1 = ld_stream_u2(run + i0 + 32 + lane);
+            if (!t.template insert2<false>(a0, r0.x, r0.y, a1, r1.x, r1.y, dummy, nocc_s)) st.overflow = true;
           }
         } else {
-          // hash passes: a pass takes 1 / n_pass of the records; compact them per warp so that every insert is 32 wide
-          bool has_n = beg + threadIdx.x < end;
+          // hash passes: a pass takes 1 / n_pass of the records
+          uint32_t n_st = 0;
+          bool has_n = threadIdx.x < n;
           uint2 r_n = make_uint2(0, 0);
-          if (has_n) r_n = ld_stream_u2(rec + beg + threadIdx.x);
-          for (uint64_t i0 = beg; i0 < end; i0 += THREADS) {
+          if (has_n) r_n = ld_stream_u2(run + threadIdx.x);
+          for (uint32_t i0 = 0; i0 < n; i0 += THREADS) {
             bool has = has_n;
             const uint2 r = r_n;
-            has_n = i0 + THREADS + threadIdx.x < end;
-            if (has_n) r_n = ld_stream_u2(rec + i0 + THREADS + threadIdx.x);
+            has_n = i0 + THREADS + threadIdx.x < n;
+            if (has_n) r_n = ld_stream_u2(run + i0 + THREADS + threadIdx.x);
             has = has && __umulhi(hash32b(r.x), n_pass) == pass;
             const uint32_t m = __ballot_sync(FULL_MASK, has);
             if (has) stage[n_st + __popc(m & lt)] = r;
@@ -665,138 +779,176 @@ __global__ void __launch_bounds__(THREADS) reduce_block_kernel(const ReduceParam
               n_st -= 32;
               const uint2 q = stage[n_st + lane];
               __syncwarp();
-              if (!t.insert(true, q.x, q.y)) overflow = true;
+              if (!t.template insert2<false>(true, q.x, q.y, false, 0, 0, dummy, nocc_s)) st.overflow = true;
             }
           }
+          if (n_st) {
+            uint2 q = make_uint2(0, 0);
+            if (lane < n_st) q = stage[lane];
+            __syncwarp();
+            if (!t.template insert2<false>(lane < n_st, q.x, q.y, false, 0, 0, dummy, nocc_s)) st.overflow = true;
+          }
         }
-      }
-      if (n_pass > 1 && n_st) {
-        uint2 q = make_uint2(0, 0);
-        if (lane < n_st) q = stage[lane];
-        __syncwarp();
-        if (!t.insert(lane < n_st, q.x, q.y)) overflow = true;
-        n_st = 0;
-      }
-      __syncthreads();
-      const uint32_t d = s_nocc;
-      // sweep 1: lane-group maxima of the integer key (group = lane index, across warps)
-      uint64_t tbest = 0;
-      for (uint32_t i = threadIdx.x; i < d; i += THREADS) {
-        const uint64_t ik = t.ikey(t.occ[i], p.range);
-        tbest = ik > tbest ? ik : tbest;
-      }
-      s_gmax[warp][lane] = tbest;
-      __syncthreads();
-      if (warp == 0) {
-        uint64_t g = 0;
+        __syncthreads();   // #1: all records of the pass are in the table
+        const uint32_t d = s_nocc[par];
+        if (threadIdx.x == 0) {   // the other parity's counters are idle now (warp 0 has settled what it owed)
+          s_nocc[par ^ 1] = 0;
+          s_chunk[par ^ 1] = 0;
+          s_ncand[par ^ 1] = 0;
+        }
+        if (!fetched && warp == 1) fetch_batch(buf ^ 1);   // next batch's metadata, one batch ahead
+        fetched = true;
+        if (slow) {
+          // exact K-round selection per warp slice of the occ list, lists land at warp * K of the candidate buffer
+          // (N_CAND >= WARPS * K is not guaranteed: only warps 0 and 1 select, over half of the list each)
+          for (uint32_t i = threadIdx.x; i < d; i += THREADS) st.pay += TIME ? (uint64_t)t.count(t.occ(i)) : t.sum(t.occ(i));
+          __syncthreads();
+          if (warp < 2) {
+            const uint32_t half = (d + 1) / 2;
+            const uint32_t lo = warp == 0 ? 0 : half, hi = warp == 0 ? half : d;
+            const int f = warp_select_slow<TIME, LOG>(t, lo, hi, p.k, p.w_scale, cp, warp * OTTO_MAX_K);
+            for (int r = f + (int)lane; r < OTTO_MAX_K; r += 32) cp.key[warp * OTTO_MAX_K + r] = 0;
+          }
+          __syncthreads();
+          if (warp == 0) {
+            // compact the non-zero keys of the two lists (+ the carried best) to the front
+            int w = 0;
+            for (int i0 = 0; i0 < 2 * OTTO_MAX_K; i0 += 32) {
+              const int i = i0 + lane;
+              const uint64_t kk = cp.key[i];
+              const uint64_t ss = cp.sum[i];
+              const uint32_t cc = cp.cnt[i];
+              const uint32_t m = __ballot_sync(FULL_MASK, kk != 0);
+              __syncwarp();
+              if (kk != 0) {
+                const int at = w + __popc(m & lt);
+                cp.key[at] = kk; cp.sum[at] = ss; cp.cnt[at] = cc;
+              }
+              w += __popc(m);
+              __syncwarp();
+            }
+            for (int r = lane; r < n_best; r += 32) {
+              cp.key[w + r] = best.key[r]; cp.sum[w + r] = best.sum[r]; cp.cnt[w + r] = best.cnt[r];
+            }
+            __syncwarp();
+            w += n_best;
+            if (last) {
+              const int found = warp_rank_emit(cp, w, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) { emit_entry(p, o, r, kk, cnt, sum); });
+              emit_finish(p, o, found);
+            } else {
+              n_best = warp_rank_emit(cp, w, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) { best.key[r] = kk; best.sum[r] = sum; best.cnt[r] = cnt; });
+            }
+            __syncwarp();
+            if (lane == 0) { st.occ += d; ++st.slow; }
+          }
+          for (uint32_t i = threadIdx.x; i < d; i += THREADS) t.clear_slot(t.occ(i));
+          __syncthreads();
+          slow = false;
+          par ^= 1;
+          continue;
+        }
+        // ---- sweep 1: 32-bit keys into registers, lane-group maxima (group = lane index, across warps)
+        uint32_t k32[EPT];
+        uint32_t tbest = 0, pay = 0;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) g = s_gmax[w][lane] > g ? s_gmax[w][lane] : g;
-        const uint64_t thr = with_margin(warp_kth_largest(g, p.k));
-        if (lane == 0) s_thr = thr;
-      }
-      __syncthreads();
-      const uint64_t thr = s_thr;
-      // sweep 2: candidates (+ stats)
-      for (uint32_t i0 = 0; i0 < d; i0 += THREADS) {
-        const uint32_t i = i0 + threadIdx.x;
-        bool q = false;
-        uint32_t y = 0, cnt = 0;
-        uint64_t sum = 0;
-        if (i < d) {
-          const uint32_t h = t.occ[i];
-          y = t.keys[h];
-          cnt = t.count(h);
-          sum = t.sum(h);
-          st_pay += TIME ? (uint64_t)cnt : sum;
-          q = t.ikey(h, p.range) >= thr;
+        for (int j = 0; j < EPT; ++j) {
+          k32[j] = 0;
+          if ((uint32_t)j * THREADS >= d) break;
+          const uint32_t i = j * THREADS + threadIdx.x;
+          if (i < d) {
+            const uint32_t h = t.occ(i);
+            const uint2 pl = t.payload(h);
+            k32[j] = key32<TIME>(cfg, TIME ? 0u : t.key(h), pl.x, pl.y) + 1u;
+            if (k32[j] == 0) k32[j] = 0xffffffffu;
+            pay += TIME ? (pl.y & 0xffffffu) + 1u : pl.x;
+            tbest = max(tbest, k32[j]);
+          }
         }
-        push_candidate<BLOCK_CANDS>(q, &s_ncand, c, TIME, y, cnt, sum, p.w_scale);
-      }
-      if (threadIdx.x == 0) st_occ += d;
-      __syncthreads();
-      int n_c = (int)s_ncand;
-      if (n_c > BLOCK_CANDS) {
-        // adversarial layout: exact K-round selection per warp slice of the occ list, lists land at warp * K
-        if (threadIdx.x == 0) ++st_slow;
-        const uint32_t per = (d + WARPS - 1) / WARPS;
-        const uint32_t lo = min(d, warp * per), hi = min(d, (warp + 1) * per);
-        const int f = warp_select_slow<TIME, LOG>(t, lo, hi, p.k, p.w_scale, c, warp * OTTO_MAX_K);
-        for (int r = f + (int)lane; r < OTTO_MAX_K; r += 32) c.key[warp * OTTO_MAX_K + r] = 0;
-        __syncthreads();
-        // compact the non-zero keys to the front (one warp)
-        if (warp == 0) {
-          int w = 0;
-          for (int i0 = 0; i0 < WARPS * OTTO_MAX_K; i0 += 32) {
-            const int i = i0 + lane;
-            const uint64_t kk = c.key[i];
-            const uint64_t ss = c.sum[i];
-            const uint32_t cc = c.cnt[i];
-            const uint32_t m = __ballot_sync(FULL_MASK, kk != 0);
-            __syncwarp();
-            if (kk != 0) {
-              const int at = w + __popc(m & lanemask_lt());
-              c.key[at] = kk; c.sum[at] = ss; c.cnt[at] = cc;
+        s_gmax[warp][lane] = tbest;
+        __syncthreads();   // #2
+        uint32_t g = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) g = max(g, s_gmax[w][lane]);
+        const uint32_t thr = cand_threshold<TIME>(warp_kth_largest32(g, p.k));
+        // ---- sweep 2: candidates read their payload again; every entry resets its slot
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+          if ((uint32_t)j * THREADS >= d) break;
+          const uint32_t i = j * THREADS + threadIdx.x;
+          const bool mine = i < d;
+          const bool q = mine && k32[j] >= thr;
+          const uint32_t m = __ballot_sync(FULL_MASK, q);
+          const uint32_t h = mine ? t.occ(i) : 0u;
+          if (m) {
+            const int leader = __ffs(m) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(&s_ncand[par], (uint32_t)__popc(m));
+            base = __shfl_sync(FULL_MASK, base, leader);
+            if (q) {
+              const uint32_t at = base + __popc(m & lt);
+              if (at < (uint32_t)N_CAND) {   // the carried best list goes behind them
+                const uint2 pl = t.payload(h);
+                const uint32_t cnt = t.count_of(pl);
+                const uint64_t sum = t.sum_of(pl);
+                cp.key[at] = float_key(TIME, t.key(h) - 1u, cnt, sum, p.w_scale);
+                cp.sum[at] = sum;
+                cp.cnt[at] = cnt;
+              }
             }
-            w += __popc(m);
+          }
+          if (mine) t.clear_slot(h);
+        }
+        __syncthreads();   // #3: candidate list complete, table clean
+        const uint32_t n_c = s_ncand[par];
+        if (n_c > (uint32_t)N_CAND) {   // adversarial ties: this pass again, selected exactly
+          slow = true;
+          --pass;
+          par ^= 1;      // fresh counters (the other parity was reset behind barrier #1)
+          continue;
+        }
+        st.pay += pay;
+        if (threadIdx.x == 0) st.occ += d;
+        if (warp == 0) {
+          if (n_pass == 1) {
+            // ranking is deferred: it runs while the other warps insert the next bin
+            owe = true;
+            owe_o = o;
+            owe_par = par;
+          } else {
+            // entries carried from earlier passes join the candidates
+            for (int r = lane; r < n_best; r += 32) {
+              cp.key[n_c + r] = best.key[r]; cp.sum[n_c + r] = best.sum[r]; cp.cnt[n_c + r] = best.cnt[r];
+            }
+            __syncwarp();
+            const int n_all = (int)n_c + n_best;
+            if (last) {
+              const int found = warp_rank_emit(cp, n_all, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) { emit_entry(p, o, r, kk, cnt, sum); });
+              emit_finish(p, o, found);
+            } else {
+              n_best = warp_rank_emit(cp, n_all, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) { best.key[r] = kk; best.sum[r] = sum; best.cnt[r] = cnt; });
+            }
             __syncwarp();
           }
-          n_c = w;
         }
-        // the slow path marks taken keys: restore them so that clear_dirty sees plain keys (it only stores)
+        par ^= 1;
       }
-      // all warps: reset the table for the next pass / bin while warp 0 ranks the candidates
-      t.clear_dirty(threadIdx.x, THREADS, d);
-      if (warp == 0) {
-        n_c = __shfl_sync(FULL_MASK, n_c, 0);
-        // entries carried from earlier passes join the candidates (n_c + n_best <= NCX by construction)
-        for (int r = lane; r < n_best; r += 32) {
-          c.key[n_c + r] = best.key[r];
-          c.sum[n_c + r] = best.sum[r];
-          c.cnt[n_c + r] = best.cnt[r];
-        }
-        __syncwarp();
-        n_c += n_best;
-        if (last) {
-          const int found = warp_rank_emit(c, n_c, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) {
-            emit_entry(p, o, r, kk, cnt, sum);
-          });
-          emit_finish(p, o, found);
-        } else {
-          n_best = warp_rank_emit(c, n_c, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) {
-            best.key[r] = kk; best.sum[r] = sum; best.cnt[r] = cnt;
-          });
-          __syncwarp();
-        }
-      }
-      if (threadIdx.x == THREADS - 1) s_nocc = 0;
-      __syncthreads();
     }
-    }
-    if (threadIdx.x == 0) s_first = atomicAdd(&p.counters[CUR], (uint32_t)BATCH);
-    __syncthreads();
+    // the next batch's metadata was written by warp 1 behind barrier #1 of this batch's first bin; every later
+    // barrier orders it.  A batch always has at least one bin, so at least three barriers have passed.
   }
+  if (warp == 0) settle();
   for (int off = 16; off > 0; off >>= 1) {
-    st_occ += shfl_u64(st_occ, lane ^ off);
-    st_slow += __shfl_xor_sync(FULL_MASK, st_slow, off);
-    st_pay += shfl_u64(st_pay, lane ^ off);
+    st.occ += shfl_u64(st.occ, lane ^ off);
+    st.slow += __shfl_xor_sync(FULL_MASK, st.slow, off);
+    st.pay += shfl_u64(st.pay, lane ^ off);
   }
-  if (lane == 0 && (st_occ || st_pay)) {
-    atomicAdd(&p.stats[0], (unsigned long long)st_occ);
-    atomicAdd(&p.stats[1], (unsigned long long)st_pay);
-    if (st_slow) atomicAdd(&p.stats[3], (unsigned long long)st_slow);
+  if (lane == 0 && (st.occ || st.pay)) {
+    atomicAdd(&p.stats[0], (unsigned long long)st.occ);
+    atomicAdd(&p.stats[1], (unsigned long long)st.pay);
+    if (st.slow) atomicAdd(&p.stats[3], (unsigned long long)st.slow);
   }
-  if (threadIdx.x == 0 && st_rec) atomicAdd(&p.stats[5 + TIER], (unsigned long long)st_rec);
-  if (overflow) atomicOr(&p.stats[2], 1ull);
-}
-
-template <bool TIME, int THREADS, int LOG, int TIER>
-constexpr size_t reduce_block_smem() {
-  constexpr int NC = BLOCK_CANDS + OTTO_MAX_K;
-  constexpr int WARPS = THREADS / 32;
-  constexpr int NCX = (NC > WARPS * OTTO_MAX_K ? NC : WARPS * OTTO_MAX_K) + OTTO_MAX_K;
-  constexpr size_t SLOTS = (size_t)1 << LOG;
-  return (size_t)NCX * 16 + OTTO_MAX_K * 16 + SLOTS * 8 + (TIME ? SLOTS * 4 : 0) + NCX * 4 + OTTO_MAX_K * 4 + SLOTS * 2 +
-         (TIER == 2 ? (size_t)WARPS * 64 * 8 : 0);
+  if (threadIdx.x == 0 && st.rec) atomicAdd(&p.stats[4 + TIER], (unsigned long long)st.rec);
+  if (st.overflow) atomicOr(&p.stats[2], 1ull);
 }
 
 // ---- split rows: merge the slices' partial lists (disjoint aid_y) into the final row ----

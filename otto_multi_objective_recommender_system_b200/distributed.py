@@ -155,9 +155,9 @@ class GpuRankBackend:
         return records, self.b.views()["bin_offsets"]
 
     def reduce(self, segments, bin_lo, bin_hi, aid_lo, aid_hi) -> TopKTable:
-        # one run per bin for the reduce kernels once a bin is spread over more than two senders (with two the extra
-        # copy of the merge costs more than the second run per bin)
-        if len(segments) >= int(os.environ.get("OTTO_MERGE_MIN_SEGMENTS", "3")):
+        # the reduce kernels stream each bin as ONE run: received segments are merged first (the owner-direct scatter
+        # never gets here with more than one)
+        if len(segments) >= 2:
             segments = [self.b.merge_segments(segments, bin_hi - bin_lo)]
         return self.b.reduce(segments, bin_lo, bin_hi, aid_lo, aid_hi)
 

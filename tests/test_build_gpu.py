@@ -277,10 +277,56 @@ def test_one_shot_c_entry_point_with_workspace_retry(cv):
     ws = torch.empty(sizes.workspace_bytes, dtype=torch.uint8, device="cuda:0")
     rc = lib.otto_covisit_build(C.byref(ev), C.byref(cspec), ws.data_ptr(), ws.numel(), C.byref(tc), C.byref(stats), st)
     assert rc == N.OTTO_ENOSPC and stats.pairs > 0 and b"workspace too small" in lib.otto_last_error()
-    need = lib.otto_covisit_build_bytes(csr.n_sessions, csr.n_events, C.byref(cspec), stats.pairs, stats.bins)
+    assert stats.hot_pairs == 0
+    need = lib.otto_covisit_build_bytes(csr.n_sessions, csr.n_events, C.byref(cspec), stats.pairs + stats.hot_pairs, stats.bins)
     ws = torch.empty(need, dtype=torch.uint8, device="cuda:0")
     N.check(lib.otto_covisit_build(C.byref(ev), C.byref(cspec), ws.data_ptr(), ws.numel(), C.byref(tc), C.byref(stats), st))
     torch.cuda.synchronize()
     want = co.build(frame.to_pandas(), H.oracle_spec(spec))
     H.assert_int_table_equal(table.to_pandas(), want, "one-shot build")
     assert stats.distinct > 0 and stats.table_overflow == 0 and sum(stats.tier_records) == stats.pairs
+    # the same with hot (split) rows: their records pass through the staging area behind the final ones, so the retry
+    # has to be sized with pairs + hot_pairs; a workspace sized with pairs alone is refused again, not overrun
+    from dataclasses import replace
+    cspec = replace(spec, split_ub=64).to_c(csr.n_aids)
+    N.check(lib.otto_covisit_sizes(csr.n_sessions, csr.n_events, C.byref(cspec), C.byref(sizes)))   # more bins: larger fixed part
+    ws = torch.empty(sizes.workspace_bytes, dtype=torch.uint8, device="cuda:0")
+    rc = lib.otto_covisit_build(C.byref(ev), C.byref(cspec), ws.data_ptr(), ws.numel(), C.byref(tc), C.byref(stats), st)
+    assert rc == N.OTTO_ENOSPC and stats.hot_pairs > 0 and stats.split_rows > 0
+    short = lib.otto_covisit_build_bytes(csr.n_sessions, csr.n_events, C.byref(cspec), stats.pairs, stats.bins)
+    ws = torch.empty(short, dtype=torch.uint8, device="cuda:0")
+    assert lib.otto_covisit_build(C.byref(ev), C.byref(cspec), ws.data_ptr(), ws.numel(), C.byref(tc), C.byref(stats), st) == N.OTTO_ENOSPC
+    need = lib.otto_covisit_build_bytes(csr.n_sessions, csr.n_events, C.byref(cspec), stats.pairs + stats.hot_pairs, stats.bins)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda:0")
+    N.check(lib.otto_covisit_build(C.byref(ev), C.byref(cspec), ws.data_ptr(), ws.numel(), C.byref(tc), C.byref(stats), st))
+    torch.cuda.synchronize()
+    H.assert_int_table_equal(table.to_pandas(), want, "one-shot build with split rows")
+
+
+def test_event_contents_are_validated(cv):
+    """aids index device arrays (in owner-direct mode a peer's), types are packed into two bits, ts - ts_min is stored as
+    u32: out-of-range events must be refused, not scattered."""
+    N = cv.N
+    good = pd.DataFrame({"session": [1, 1, 2, 2], "aid": [1, 2, 3, 4], "ts": [1659304800 + i for i in range(4)], "type": [0, 1, 2, 0]})
+    for col, val in (("aid", 8), ("aid", -1), ("type", 3)):
+        bad = good.copy()
+        bad.loc[2, col] = val
+        frame = cv.EventFrame(*(torch.from_numpy(bad[c].to_numpy().astype(np.int64)) for c in ("session", "aid", "ts", "type")), n_aids=8)
+        with pytest.raises(N.OttoError, match="outside"):
+            cv.ingest(frame, "desc", device="cuda:0")
+    # millisecond timestamps (the pickles' unit) in time mode: refused at count_finish, nothing written out of bounds
+    ms = good.assign(ts=good["ts"].astype(np.int64) % 2_000_000 + 1_700_000_000)
+    csr = cv.ingest(frame_from_df(ms, 8), "desc", device="cuda:0")
+    b = cv.CovisitBuilder(csr, cv.CLICKS)
+    b.count_begin()
+    with pytest.raises(N.OttoError, match="ts outside"):
+        b.count_finish()
+    # the same frame is fine for the variants that do not weight by time
+    table, stats = cv.build_topk(csr, cv.CARTS_ORDERS)
+    assert stats["pairs"] == 4
+    # a CSR whose aids were valid at ingest but exceed the spec's n_aids (caller passes a smaller n_aids to the builder)
+    csr_small = cv.EventCSR(csr.session_ids, csr.offsets, csr.aid, csr.ts, csr.type, 3, "desc")
+    b = cv.CovisitBuilder(csr_small, cv.CARTS_ORDERS)
+    b.count_begin()
+    with pytest.raises(N.OttoError, match="aid outside"):
+        b.count_finish()

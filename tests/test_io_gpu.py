@@ -41,6 +41,22 @@ def test_topk_part_files_round_trip_and_reference_reader(mods, tmp_path):
     assert torch.equal(back.aid_y, table.aid_y) and torch.equal(back.len, table.len) and torch.equal(back.wgt, table.wgt)
 
 
+def test_table_k_comes_from_the_files_and_is_checked(mods, tmp_path):
+    # the reference consumes every row of a part file (covisitation_df_to_dict: groupby('aid_x')['aid_y'].apply(list)),
+    # so a 20-row table written without "_15" in its name must come back with 20 rows per aid, not cut to 15
+    cv, _, _, io, synth = mods
+    frame = synth.generate(synth.SynthSpec("train", 3000, 400, seed=12))
+    table, _ = cv.build_topk(cv.ingest(frame, "desc", device="cuda:0"), cv.CLICKS)      # k = 20
+    io.write_topk_parts(table, tmp_path, "time_weighted", 6, None)
+    back = io.read_topk_parts(tmp_path, "time_weighted", 400, None, 6, None, "cuda:0")
+    assert back.k == int(table.len.max()) and back.k > 15
+    assert torch.equal(back.aid_y, table.aid_y[:, :back.k]) and torch.equal(back.len, table.len)
+    with pytest.raises(ValueError, match="sized for k = 15"):
+        io.read_topk_parts(tmp_path, "time_weighted", 400, 15, 6, None, "cuda:0")
+    with pytest.raises(ValueError, match="outside"):
+        io.read_topk_parts(tmp_path, "time_weighted", 100, None, 6, None, "cuda:0")
+
+
 def _make_data_dir(tmp_path, synth, io, n_aids=300):
     train = synth.generate(synth.SynthSpec("train", 2500, n_aids, seed=21))
     val_full = synth.generate(synth.SynthSpec("test", 600, n_aids, seed=22, first_session=2500)).to_pandas()
@@ -64,7 +80,7 @@ def _make_data_dir(tmp_path, synth, io, n_aids=300):
     for e, ty in (("click", 0), ("cart", 1), ("order", 2)):
         top = train.to_pandas().query("type == @ty")["aid"].value_counts().head(20)
         popular[e] = [int(a) for a in top.index]
-        for prefix in ("train", "all"):
+        for prefix in ("train", "test", "all"):
             json.dump({str(a): int(c) for a, c in top.items()}, open(tmp_path / "aid_frequencies" / f"{prefix}_20_most_frequent_{e}_aids.json", "w"))
     return train, val, pd.DataFrame(labels), popular
 
