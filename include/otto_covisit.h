@@ -326,6 +326,42 @@ int otto_assemble_predictions(const OttoSessions* sessions, const OttoCandidates
                               const int32_t* popular, int32_t n_popular, int32_t n, int32_t* pred /* [n_targets][n_sessions][n] */,
                               uint8_t* long_session /* [n_sessions] or NULL */, void* stream);
 
+/* ---- candidate frames on the device (ranker/covisitation_candidate_generation.py:151-165,177-197;
+ *      ranker/regular_candidate_generation.py:160-180,225-257; covisitation/inference.py:251-257) ---- */
+
+/* Ground truth of a frame's sessions as a CSR: the aids of session s are aid[offsets[s] .. offsets[s + 1]), unique and
+ * sorted ascending (splits/val_labels.parquet rows of one event type, covisitation/inference.py:116-122). */
+typedef struct {
+  const int64_t* offsets;   /* [n_sessions + 1] */
+  const int32_t* aid;
+} OttoLabels;
+
+/* Exclusive scan of int32 lengths (negative = 0) into int64 offsets [n + 1]; *total_host (optional) synchronises. */
+int64_t otto_row_offsets_scratch_bytes(int64_t n);
+int otto_row_offsets(const int32_t* len, int64_t n, int64_t* offsets, int64_t* total_host, void* scratch, int64_t scratch_bytes,
+                     void* stream);
+
+/* df.explode of one target's lists (aid / score [n_sessions][top_n], len [n_sessions]) into the flat columns the ranker
+ * scripts pickle: session (repeated), candidates uint64, candidate_scores float32 and, when labels != NULL,
+ * candidate_labels uint8 = int(aid in labels of the session).  Session s fills rows row_offsets[s] .. + len[s]. */
+int otto_explode_candidates(const int32_t* aid, const int32_t* score, const int32_t* len, int64_t n_sessions, int32_t top_n,
+                            const int64_t* row_offsets, const int32_t* session_ids, const OttoLabels* labels,
+                            int32_t* session_out, uint64_t* candidates_out, float* scores_out, uint8_t* labels_out, void* stream);
+
+/* recall@k parts of pred [n_sessions][n] (-1 = empty): out_dev[0] = sum over sessions of |set(pred) & set(labels)|,
+ * out_dev[1] = sum of min(|labels|, k_clip); recall = out[0] / out[1] (covisitation/inference.py:251-252). */
+int otto_recall_counts(const int32_t* pred, int64_t n_sessions, int32_t n, const OttoLabels* labels, int32_t k_clip,
+                       uint64_t* out_dev /* [2] */, void* stream);
+
+/* Regular candidate form (ranker/regular_candidate_generation.py:139-180): per session its unique aids, most recent
+ * first, with scores |H| .. 1 (:163), followed by one target's ranker-form votes (aid, count).  row_counts gives the rows
+ * per session (-> otto_row_offsets), regular_rows writes the flat columns (labels optional, as above). */
+int otto_regular_row_counts(const OttoSessions* sessions, const int32_t* aid, const int32_t* score, const int32_t* len,
+                            int32_t top_n, int32_t* rows_out, void* stream);
+int otto_regular_rows(const OttoSessions* sessions, const int32_t* aid, const int32_t* score, const int32_t* len, int32_t top_n,
+                      const int64_t* row_offsets, const int32_t* session_ids, const OttoLabels* labels, int32_t* session_out,
+                      uint64_t* candidates_out, float* scores_out, uint8_t* labels_out, void* stream);
+
 /* ---- long-session branch of the standalone model (covisitation/inference.py:142-199, :336-392) ----
  * Sessions with >= n unique aids (flagged by otto_assemble_predictions) are ranked by recency-weighted event
  * scores plus covisitation bonuses instead of votes.  Targets are clicks, carts, orders (index 0, 1, 2):

@@ -49,6 +49,60 @@ def reference_spec(stems_available, top_n: int = 100) -> CandidateSpec:
 
 
 @dataclass
+class LabelCSR:
+    """Ground truth of a frame's sessions on the device (OttoLabels): aids of session i (row order of the CSR's
+    session_ids) at aid[offsets[i] : offsets[i + 1]], unique and ascending."""
+    offsets: torch.Tensor   # int64 [S + 1]
+    aid: torch.Tensor       # int32
+
+    def to_c(self) -> N.OttoLabels:
+        return N.OttoLabels(self.offsets.data_ptr(), self.aid.data_ptr())
+
+    @staticmethod
+    def build(session_ids, labels, device) -> "LabelCSR":
+        """labels: {session id: iterable of aids} (sessions without an entry have no labels) or a sequence of
+        iterables aligned with session_ids.  One pass over the labelled sessions on the host, then a lexsort."""
+        sid = np.asarray(session_ids.cpu() if hasattr(session_ids, "cpu") else session_ids)
+        S = int(sid.size)
+        if isinstance(labels, dict):
+            index = {int(x): i for i, x in enumerate(sid.tolist())}
+            items = [(index[int(k)], v) for k, v in labels.items() if int(k) in index]
+        else:
+            items = list(enumerate(labels))
+        rows = np.fromiter((i for i, v in items for _ in v), dtype=np.int64)
+        aids = np.fromiter((int(a) for _, v in items for a in v), dtype=np.int64)
+        if rows.size:
+            key = np.unique(rows << 32 | aids)                     # unique + ascending (row, aid)
+            rows, aids = key >> 32, key & 0xFFFFFFFF
+        offsets = np.zeros(S + 1, dtype=np.int64)
+        np.cumsum(np.bincount(rows, minlength=S), out=offsets[1:])
+        return LabelCSR(torch.from_numpy(offsets).to(device), torch.from_numpy(aids.astype(np.int32)).to(device))
+
+
+def _row_offsets(lib, length: torch.Tensor):
+    """Exclusive scan of int32 lengths on the device -> (int64 offsets [n + 1], total)."""
+    dev = length.device
+    n = int(length.numel())
+    off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    need = int(lib.otto_row_offsets_scratch_bytes(n))
+    scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+    total = C.c_int64(0)
+    with torch.cuda.device(dev):
+        N.check(lib.otto_row_offsets(length.data_ptr(), n, off.data_ptr(), C.byref(total), scratch.data_ptr(), need, _stream_ptr(dev)))
+    return off, int(total.value)
+
+
+def _frame_from_device(session, cand, score, label=None):
+    """Flat device columns -> the pickled frame layout (one D2H copy per column, no per-row host work)."""
+    import pandas as pd
+    cols = {"session": session.cpu().numpy(), "candidates": cand.cpu().numpy().view(np.uint64),
+            "candidate_scores": score.cpu().numpy()}
+    if label is not None:
+        cols["candidate_labels"] = label.cpu().numpy()
+    return pd.DataFrame(cols)
+
+
+@dataclass
 class Candidates:
     """Fixed-stride candidate lists on the device: [target, session, rank]."""
     targets: tuple
@@ -57,25 +111,38 @@ class Candidates:
     len: torch.Tensor     # int32 [T, S]
     session_ids: torch.Tensor
 
+    def to_device_columns(self, ti: int, labels: "LabelCSR | None" = None):
+        """One target exploded on the device (otto_explode_candidates): session int32, candidates uint64 (int64
+        storage), candidate_scores float32 [, candidate_labels uint8]."""
+        lib = N.lib()
+        dev = self.aid.device
+        S, n = int(self.aid.shape[1]), int(self.aid.shape[2])
+        off, total = _row_offsets(lib, self.len[ti])
+        session = torch.empty(total, dtype=torch.int32, device=dev)
+        cand = torch.empty(total, dtype=torch.int64, device=dev)
+        score = torch.empty(total, dtype=torch.float32, device=dev)
+        label = torch.empty(total, dtype=torch.uint8, device=dev) if labels is not None else None
+        lc = labels.to_c() if labels is not None else None
+        sid = self.session_ids.to(torch.int32)
+        with torch.cuda.device(dev):
+            N.check(lib.otto_explode_candidates(self.aid[ti].data_ptr(), self.score[ti].data_ptr(), self.len[ti].data_ptr(), S, n,
+                                                off.data_ptr(), sid.data_ptr(), C.byref(lc) if lc is not None else None,
+                                                session.data_ptr(), cand.data_ptr(), score.data_ptr(),
+                                                label.data_ptr() if label is not None else None, _stream_ptr(dev)))
+        return session, cand, score, label
+
     def to_frames(self, labels: dict | None = None) -> dict:
         """The exploded frames the ranker script pickles (:177-197): session, candidates uint64,
-        candidate_scores float32 (+ candidate_labels uint8 when labels = {target: {session: set}})."""
-        import pandas as pd
+        candidate_scores float32 (+ candidate_labels uint8 when labels = {target: {session: set}} or
+        {target: LabelCSR}).  Explode, casts and label marking run on the device."""
         out = {}
-        n = self.aid.shape[2]
-        sid = self.session_ids.cpu().numpy()
         for ti, t in enumerate(self.targets):
-            ln = self.len[ti].cpu().numpy()
-            mask = np.arange(n)[None, :] < ln[:, None]
-            f = pd.DataFrame({"session": np.repeat(sid, ln),
-                              "candidates": self.aid[ti].cpu().numpy()[mask].astype(np.uint64),
-                              "candidate_scores": self.score[ti].cpu().numpy()[mask].astype(np.float32)})
+            lab = None
             if labels is not None:
                 lab = labels.get(t, {})
-                f["candidate_labels"] = np.fromiter(
-                    (int(int(a) in lab.get(int(s), ())) for s, a in zip(f["session"], f["candidates"])),
-                    dtype=np.uint8, count=len(f))
-            out[t] = f
+                if not isinstance(lab, LabelCSR):
+                    lab = LabelCSR.build(self.session_ids, lab, self.aid.device)
+            out[t] = _frame_from_device(*self.to_device_columns(ti, lab))
         return out
 
 
@@ -175,54 +242,41 @@ def assemble_predictions(sessions: EventCSR, cand: Candidates, popular: dict, n:
     return pred, long_session.bool()
 
 
-def regular_candidates(sessions: EventCSR, tables: dict, n: int = 100, labels: dict | None = None, n_chunks: int = 15) -> dict:
+def regular_candidates(sessions: EventCSR, tables: dict, n: int = 100, labels: dict | None = None) -> dict:
     """ranker/regular_candidate_generation.py:139-180,225-257: per session its unique aids (most recent first, scores
     |H| .. 1, :163) followed by the ranker-form votes (most_common(n), history dropped) -> the exploded frames the
-    script pickles as candidate/{event}_{validation,test}.pkl.  Like the script, sessions are processed in chunks
-    (:218: 15) so the dense [target, session, |H| + n] device rows stay small.  The fastText / Annoy term (:155-156)
-    is not on this path."""
-    import pandas as pd
+    script pickles as candidate/{event}_{validation,test}.pkl.  Rows, scores and labels are written by
+    otto_regular_rows; the reference's 15 session chunks (:218) only bound its host memory and are not reproduced.
+    The fastText / Annoy term (:155-156) is not on this path."""
     lib = N.lib()
     dev = sessions.aid.device
     cand = generate_candidates(sessions, tables, reference_spec(tables.keys(), n))
-    T, S = len(cand.targets), sessions.n_sessions
-    sid_all = sessions.session_ids.cpu().numpy()
-    parts = {t: [] for t in cand.targets}
-    dummy = torch.zeros(1, dtype=torch.int32, device=dev)
-    n_chunks = max(1, min(n_chunks, S))
-    for c in range(n_chunks):
-        lo, hi = c * S // n_chunks, (c + 1) * S // n_chunks
-        if hi <= lo:
-            continue
-        sub = sessions.slice_sessions(lo, hi)
-        W = max_session_len(sub) + n
-        c_aid, c_score, c_len = (x[:, lo:hi].contiguous() for x in (cand.aid, cand.score, cand.len))
-        pred = torch.empty((T, hi - lo, W), dtype=torch.int32, device=dev)
-        ss = _sessions_struct(sub)
-        oc = N.OttoCandidates(c_aid.data_ptr(), c_score.data_ptr(), c_len.data_ptr())
-        with torch.cuda.device(dev):
-            # no popular fill, rows wide enough for the whole history: row = history + votes
-            N.check(lib.otto_assemble_predictions(C.byref(ss), C.byref(oc), T, n, dummy.data_ptr(), 0, W, pred.data_ptr(), None,
-                                                  _stream_ptr(dev)))
-        row_len = (pred >= 0).sum(dim=2)
-        hist_len = row_len - c_len
-        j = torch.arange(W, device=dev)[None, None, :]
-        vote = torch.gather(c_score, 2, (j - hist_len[:, :, None]).clamp_(0, n - 1).expand(T, hi - lo, W))
-        score = torch.where(j < hist_len[:, :, None], hist_len[:, :, None] - j, vote)
-        mask = j < row_len[:, :, None]
-        for ti, t in enumerate(cand.targets):
-            m = mask[ti]
-            parts[t].append((np.repeat(sid_all[lo:hi], row_len[ti].cpu().numpy()), pred[ti][m].cpu().numpy(), score[ti][m].cpu().numpy()))
+    S = sessions.n_sessions
+    ss = _sessions_struct(sessions)
+    sid = sessions.session_ids.to(torch.int32)
     out = {}
-    for t, chunks in parts.items():
-        f = pd.DataFrame({"session": np.concatenate([c[0] for c in chunks]) if chunks else np.zeros(0, sid_all.dtype),
-                          "candidates": (np.concatenate([c[1] for c in chunks]) if chunks else np.zeros(0, np.int32)).astype(np.uint64),
-                          "candidate_scores": (np.concatenate([c[2] for c in chunks]) if chunks else np.zeros(0, np.int32)).astype(np.float32)})
+    for ti, t in enumerate(cand.targets):
+        lab = None
         if labels is not None:
             lab = labels.get(t, {})
-            f["candidate_labels"] = np.fromiter((int(int(a) in lab.get(int(s), ())) for s, a in zip(f["session"], f["candidates"])),
-                                                dtype=np.uint8, count=len(f))
-        out[t] = f
+            if not isinstance(lab, LabelCSR):
+                lab = LabelCSR.build(sessions.session_ids, lab, dev)
+        rows = torch.empty(S, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            N.check(lib.otto_regular_row_counts(C.byref(ss), cand.aid[ti].data_ptr(), cand.score[ti].data_ptr(),
+                                                cand.len[ti].data_ptr(), n, rows.data_ptr(), _stream_ptr(dev)))
+        off, total = _row_offsets(lib, rows)
+        session = torch.empty(total, dtype=torch.int32, device=dev)
+        cnd = torch.empty(total, dtype=torch.int64, device=dev)
+        score = torch.empty(total, dtype=torch.float32, device=dev)
+        label = torch.empty(total, dtype=torch.uint8, device=dev) if lab is not None else None
+        lc = lab.to_c() if lab is not None else None
+        with torch.cuda.device(dev):
+            N.check(lib.otto_regular_rows(C.byref(ss), cand.aid[ti].data_ptr(), cand.score[ti].data_ptr(), cand.len[ti].data_ptr(), n,
+                                          off.data_ptr(), sid.data_ptr(), C.byref(lc) if lc is not None else None,
+                                          session.data_ptr(), cnd.data_ptr(), score.data_ptr(),
+                                          label.data_ptr() if label is not None else None, _stream_ptr(dev)))
+        out[t] = _frame_from_device(session, cnd, score, label)
     return out
 
 
@@ -343,16 +397,38 @@ def recency_weighted_candidates(sessions: EventCSR, labels: dict | None = None, 
         if keep_f64:
             f["candidate_scores_f64"] = sc
         if labels is not None:
+            # membership of (row, aid) in the sorted label keys: one vectorised np.isin, no per-row Python
             lab = labels.get(t, {})
-            f["candidate_labels"] = np.fromiter((int(int(x) in lab.get(int(s), ())) for s, x in zip(f["session"], f["candidates"])),
-                                                dtype=np.uint8, count=len(f))
+            if not isinstance(lab, LabelCSR):
+                lab = LabelCSR.build(sessions.session_ids, lab, "cpu")
+            lo = lab.offsets.cpu().numpy()
+            lkey = (np.repeat(np.arange(lo.size - 1, dtype=np.int64), np.diff(lo)) << 32) | lab.aid.cpu().numpy().astype(np.int64)
+            f["candidate_labels"] = np.isin((row.astype(np.int64) << 32) | a.astype(np.int64), lkey).astype(np.uint8)
         out[t] = f
     return out
 
 
-def recall_at_20(pred: torch.Tensor, labels: list) -> float:
-    """covisitation/inference.py:251-257 on device predictions: sum |pred ∩ label| / sum min(|label|, 20)."""
-    p = pred.cpu().numpy()
-    hits = sum(len(set(int(a) for a in row if a >= 0).intersection(l)) for row, l in zip(p, labels))
-    denom = sum(min(len(l), 20) for l in labels)
+def recall_counts(pred: torch.Tensor, labels: "LabelCSR", k: int = 20):
+    """(hits, denominator) of covisitation/inference.py:251-252 on the device (otto_recall_counts)."""
+    lib = N.lib()
+    dev = pred.device
+    _require_cuda(pred, "pred")
+    out = torch.zeros(2, dtype=torch.int64, device=dev)
+    p = pred.contiguous()
+    lc = labels.to_c()
+    with torch.cuda.device(dev):
+        N.check(lib.otto_recall_counts(p.data_ptr(), int(p.shape[0]), int(p.shape[1]), C.byref(lc), k, out.data_ptr(), _stream_ptr(dev)))
+    h, d = out.tolist()
+    return int(h), int(d)
+
+
+def recall_at_20(pred: torch.Tensor, labels) -> float:
+    """covisitation/inference.py:251-257 on device predictions [S, n]: sum |set(pred) ∩ label| / sum min(|label|, 20).
+    labels: LabelCSR, or a sequence of label collections aligned with the rows of pred."""
+    if not pred.is_cuda:
+        pred = pred.to("cuda")           # the counting runs on the device; there is no host implementation
+    pred = pred.to(torch.int32)
+    if not isinstance(labels, LabelCSR):
+        labels = LabelCSR.build(np.arange(int(pred.shape[0])), list(labels), pred.device)
+    hits, denom = recall_counts(pred, labels, 20)
     return hits / denom if denom else 0.0

@@ -34,7 +34,8 @@ struct CandParams {
   uint32_t* list_block;   // sessions for the 128-thread shared-memory tier
   uint32_t* list_large;   // sessions for the 256-thread shared-memory tier
   uint32_t* list_global;  // sessions for the block-global tier
-  uint32_t* counters;     // [0] n_block [1] n_global [2] next_block [3] next_global [4] n_large [5] next_large
+  uint32_t* list_mid;     // sessions for the 128-thread 4096-slot tier
+  uint32_t* counters;     // [0] n_block [1] n_global [2] next_block [3] next_global [4] n_large [5] next_large [6] n_mid [7] next_mid
   uint64_t* slab;         // global tier: per-block slab
   int64_t slab_words;     // u64 words per block
   int32_t max_k_sum;      // max over targets of the sum of table_k over its sources
@@ -43,7 +44,7 @@ struct CandParams {
   int32_t run_target[OTTO_MAX_TARGETS];
 };
 
-constexpr int W_LCAP = 32, W_MCAP = 256;        // warp tier: events, gathered items
+
 constexpr int B_LCAP = 64, B_MCAP = 1024;       // 128-thread shared-memory tier (5 CTAs per SM)
 constexpr int X_LCAP = 256, X_MCAP = 4096;      // 256-thread shared-memory tier (1 CTA per SM)
 constexpr int CAND_WARPS = 4;
@@ -397,25 +398,673 @@ __device__ __forceinline__ void clear_table(const Work& w, int tid) {
 
 __device__ __forceinline__ int64_t item_bound(const CandParams& p, int L) { return (int64_t)L * p.max_k_sum; }
 
-// tier 1: one warp per session; larger sessions are appended to the block tiers' lists
-__global__ void __launch_bounds__(CAND_WARPS * 32) candidates_warp_kernel(const CandParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const Work w = carve_rt(smem_raw + warp * work_bytes<W_LCAP, W_MCAP>(), W_LCAP, W_MCAP, nullptr);
-  clear_table<32>(w, lane);
-  const int64_t n_warps = (int64_t)gridDim.x * CAND_WARPS;
-  for (int64_t s = (int64_t)blockIdx.x * CAND_WARPS + warp; s < p.n_sessions; s += n_warps) {
-    const int L = p.off[s + 1] - p.off[s];
-    const int64_t bound = item_bound(p, L);
-    if (L > W_LCAP || bound > W_MCAP) {
-      if (lane == 0) {
-        if (L <= B_LCAP && bound <= B_MCAP) p.list_block[atomicAdd(&p.counters[0], 1u)] = (uint32_t)s;
-        else if (L <= X_LCAP && bound <= X_MCAP) p.list_large[atomicAdd(&p.counters[4], 1u)] = (uint32_t)s;
-        else p.list_global[atomicAdd(&p.counters[1], 1u)] = (uint32_t)s;
-      }
-      continue;
+// =====================================================================================================
+// fast warp tiers (round 2): sessions of up to 32 events, one event per lane, everything in registers / shuffles
+// =====================================================================================================
+// The round-1 warp kernel spent 1840 warp-instructions on a session of <= 5 events (profiles/r01_final_ncu_candidates):
+// generic group loops, a 64-bit bitonic network per selection, a shared-memory bitonic sort per ascending history set.
+// Here the history sets come from one MATCH.ANY (unique aids) and three ballots (types per aid); a source's rows
+// become SEGMENTS of the concatenation (start position, aid, table), every vote finds its segment by a binary search
+// over the starts; the vote table is addressed through 32-bit shared addresses (see reduce.cuh); the most_common
+// order is a 32-bit key count << 16 | (0xffff - first position), unique per entry, so the N-th largest of the lane
+// maxima is an exact threshold and the ~N..2N survivors are sorted in registers.
+// Two table sizes: 512 slots (<= 256 votes: sessions of <= 5 events with the three graded tables, 80 % of the test
+// sessions) and 2048 slots (<= 1024 votes).  Longer sessions go to the block tiers below.
+__device__ __forceinline__ uint32_t c_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t c_lds(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t c_lds16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t c_lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void c_sts(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void c_sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+__device__ __forceinline__ void c_sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t c_cas(uint32_t a, uint32_t cmp, uint32_t v) {
+  uint32_t o;
+  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(o) : "r"(a), "r"(cmp), "r"(v) : "memory");
+  return o;
+}
+__device__ __forceinline__ void c_red_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void c_red_min(uint32_t a, uint32_t v) { asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+template <int LOGHS, int LMAX>
+struct FastCfg {
+  static constexpr int HS = 1 << LOGHS;
+  static constexpr int VCAP = HS / 2;                       // votes (= upper bound of distinct entries)
+  static constexpr int NSEG = LMAX * OTTO_MAX_SOURCES;      // non-empty (source, history aid) rows of one target
+  // keys | cnt | first (u32 [HS]) | seg_start, seg_aid (u32 [NSEG]) | occ (u16 [VCAP]) | seg_tab (u8 [NSEG]) | ent (u64 [VCAP], top_n > 32)
+  __host__ __device__ static constexpr size_t bytes(bool with_ent) {
+    return ((size_t)HS * 12 + (size_t)NSEG * 8 + (size_t)VCAP * 2 + (size_t)NSEG + 15) / 16 * 16 + (with_ent ? (size_t)VCAP * 8 : 0);
+  }
+};
+
+// descending bitonic network over (key, payload) pairs, one per lane
+__device__ __forceinline__ void warp_sort_desc_kv(uint32_t& k, uint32_t& v) {
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      const uint32_t ok = __shfl_xor_sync(FULL_MASK, k, j);
+      const uint32_t ov = __shfl_xor_sync(FULL_MASK, v, j);
+      const bool keep_max = ((lane & j) == 0) == ((lane & kk) == 0);
+      const bool take = keep_max ? (ok > k) : (ok < k);
+      k = take ? ok : k;
+      v = take ? ov : v;
     }
-    process_session<32>(p, s, lane, w, nullptr);
+  }
+}
+__device__ __forceinline__ uint32_t warp_kth_largest_u32(uint32_t v, int k) {
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      const uint32_t o = __shfl_xor_sync(FULL_MASK, v, j);
+      const bool keep_max = ((lane & j) == 0) == ((lane & kk) == 0);
+      v = keep_max ? max(v, o) : min(v, o);
+    }
+  }
+  return __shfl_sync(FULL_MASK, v, k - 1);
+}
+
+constexpr int MID_LCAP = 64, MID_MCAP = 2048;
+
+// tier of every session by its length: <= lmax0 events fast warp kernel (no list), <= lmax1 list_block, then list_mid,
+// list_large, list_global
+__global__ void candidates_classify_kernel(const CandParams p, int lmax0, int lmax1) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= p.n_sessions) return;
+  const int L = p.off[s + 1] - p.off[s];
+  if (L <= lmax0) return;
+  if (L <= lmax1) p.list_block[atomicAdd(&p.counters[0], 1u)] = (uint32_t)s;
+  else if (L <= MID_LCAP && item_bound(p, L) <= MID_MCAP) p.list_mid[atomicAdd(&p.counters[6], 1u)] = (uint32_t)s;
+  else if (L <= X_LCAP && item_bound(p, L) <= X_MCAP) p.list_large[atomicAdd(&p.counters[4], 1u)] = (uint32_t)s;
+  else p.list_global[atomicAdd(&p.counters[1], 1u)] = (uint32_t)s;
+}
+
+// TIER 0: scans all sessions and takes those of <= lmax0 events; TIER 1: list_block
+template <int LOGHS, int LMAX, int TIER>
+__global__ void __launch_bounds__(CAND_WARPS * 32) candidates_fast_kernel(const CandParams p, int lmax0, int lmax1, int with_ent) {
+  using Cfg = FastCfg<LOGHS, LMAX>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id(), lt = lanemask_lt();
+  unsigned char* base = smem_raw + (size_t)warp * Cfg::bytes(with_ent != 0);
+  const uint32_t keys_s = c_smem(base), cnt_s = keys_s + Cfg::HS * 4, first_s = cnt_s + Cfg::HS * 4;
+  const uint32_t segst_s = first_s + Cfg::HS * 4, segaid_s = segst_s + Cfg::NSEG * 4;
+  const uint32_t occ_s = segaid_s + Cfg::NSEG * 4, segtab_s = occ_s + Cfg::VCAP * 2;
+  uint64_t* ent = (uint64_t*)(base + ((size_t)Cfg::HS * 12 + (size_t)Cfg::NSEG * 8 + (size_t)Cfg::VCAP * 2 + (size_t)Cfg::NSEG + 15) / 16 * 16);
+  for (uint32_t h = lane; h < (uint32_t)Cfg::HS; h += 32) {
+    c_sts(keys_s + h * 4, 0u);
+    c_sts(cnt_s + h * 4, 0u);
+    c_sts(first_s + h * 4, 0xffffffffu);
+  }
+  __syncwarp();
+  const OttoCandidateSpec& sp = p.spec;
+  const int N = sp.top_n;
+  const int64_t n_warps = (int64_t)gridDim.x * CAND_WARPS;
+  const int64_t n_work = TIER == 0 ? p.n_sessions : (int64_t)p.counters[0];
+  for (int64_t w = (int64_t)blockIdx.x * CAND_WARPS + warp; w < n_work; w += n_warps) {
+    const int64_t s = TIER == 0 ? w : (int64_t)p.list_block[w];
+    const int32_t beg = p.off[s], end = p.off[s + 1];
+    const int L = end - beg;
+    if (TIER == 0 && L > lmax0) continue;     // listed for a cooperative tier by candidates_classify_kernel
+    // 1. events, most recent first, one per lane; unique aids (first occurrence in recency order) and their types
+    const bool active = (int)lane < L;
+    const int32_t a = active ? p.aid[end - 1 - (int)lane] : -1;
+    const uint32_t ty = active ? p.type[end - 1 - (int)lane] : 0u;
+    const uint32_t peers = __match_any_sync(FULL_MASK, active ? (uint32_t)a : (0x80000000u | lane));
+    const bool firsto = active && (peers & lt) == 0;
+    const uint32_t b0 = __ballot_sync(FULL_MASK, active && ty == 0), b1 = __ballot_sync(FULL_MASK, active && ty == 1),
+                   b2 = __ballot_sync(FULL_MASK, active && ty == 2);
+    const uint32_t tm = ((peers & b0) ? 1u : 0u) | ((peers & b1) ? 2u : 0u) | ((peers & b2) ? 4u : 0u);
+    const uint32_t umask = __ballot_sync(FULL_MASK, firsto);
+    const bool valid_a = (uint32_t)a < (uint32_t)sp.n_aids;
+    for (int ri = 0; ri < p.n_run; ++ri) {
+      const int tg = p.run_target[ri];
+      // 2. segments of the concatenation: one per non-empty (source, history aid) table row, in concatenation order
+      uint32_t nseg = 0, T = 0;
+      for (int si = 0; si < sp.target_n_sources[tg]; ++si) {
+        const int src = sp.target_sources[tg][si];
+        const int tb = sp.source_table[src], sel = sp.source_hist[src];
+        const bool flag = firsto && valid_a && (sel == OTTO_HIST_RECENCY || (tm & hist_mask(sel)) != 0);
+        const uint32_t len = flag ? (uint32_t)sp.table_len[tb][a] : 0u;
+        const uint32_t fm = __ballot_sync(FULL_MASK, len > 0);
+        if (fm == 0) continue;
+        uint32_t start = 0, ord = 0;
+        if (sel == OTTO_HIST_RECENCY) {
+          // history in recency order = lane order: exclusive prefix over the lanes
+          uint32_t inc = len;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL_MASK, inc, o);
+            if ((int)lane >= o) inc += v;
+          }
+          start = inc - len;
+          ord = __popc(fm & lt);
+        } else {
+          // np.unique: ascending aid
+          for (uint32_t m = fm; m; m &= m - 1) {
+            const int j = __ffs(m) - 1;
+            const int32_t aj = __shfl_sync(FULL_MASK, a, j);
+            const uint32_t lj = __shfl_sync(FULL_MASK, len, j);
+            if (aj < a) { start += lj; ++ord; }
+          }
+        }
+        uint32_t total = len;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL_MASK, total, o);
+        if (len > 0) {
+          const uint32_t sg = nseg + ord;
+          c_sts(segst_s + sg * 4, T + start);
+          c_sts(segaid_s + sg * 4, (uint32_t)a);
+          c_sts8(segtab_s + sg, (uint32_t)tb);
+        }
+        nseg += __popc(fm);
+        T += total;
+      }
+      __syncwarp();
+      // 3. votes: position q of the concatenation -> its segment (binary search over the starts) -> table entry
+      uint32_t d = 0;
+      for (uint32_t q0 = 0; q0 < T; q0 += 32) {
+        const uint32_t q = q0 + lane;
+        const bool has = q < T;
+        uint32_t lo = 0, hi = nseg - 1;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi + 1) >> 1;
+          if (c_lds(segst_s + mid * 4) <= (has ? q : 0u)) lo = mid;
+          else hi = mid - 1;
+        }
+        uint32_t y = 0;
+        if (has) {
+          const uint32_t r = q - c_lds(segst_s + lo * 4);
+          const uint32_t tb = c_lds8(segtab_s + lo);
+          y = (uint32_t)sp.table_aid_y[tb][(int64_t)c_lds(segaid_s + lo * 4) * sp.table_k[tb] + r];
+        }
+        // vote: claim or find the slot of y (keys hold y + 1), count it, keep the smallest position
+        uint32_t h = (y * 0x9E3779B1u) >> (32 - LOGHS);
+        uint32_t prev = y + 1u;
+        if (has) {
+          prev = c_cas(keys_s + h * 4, 0u, y + 1u);
+          while (prev != 0u && prev != y + 1u) {
+            h = (h + 1) & (Cfg::HS - 1);
+            prev = c_cas(keys_s + h * 4, 0u, y + 1u);
+          }
+        }
+        __syncwarp();
+        const uint32_t fresh = __ballot_sync(FULL_MASK, has && prev == 0u);
+        if (has && prev == 0u) c_sts16(occ_s + (d + __popc(fresh & lt)) * 2, h);
+        d += __popc(fresh);
+        if (has) {
+          c_red_add(cnt_s + h * 4, 1u);
+          c_red_min(first_s + h * 4, q);
+        }
+      }
+      __syncwarp();
+      // 4. most_common(N): key = count << 16 | (0xffff - first position), unique per entry; reset the claimed slots
+      int32_t* oa = p.out_aid + ((int64_t)tg * p.n_sessions + s) * N;
+      int32_t* os = p.out_score + ((int64_t)tg * p.n_sessions + s) * N;
+      const int n_top = (int)d < N ? (int)d : N;
+      auto entry = [&](uint32_t i, uint32_t& key, uint32_t& ay) {
+        const uint32_t h = c_lds16(occ_s + i * 2);
+        key = (c_lds(cnt_s + h * 4) << 16) | (0xffffu - c_lds(first_s + h * 4));
+        ay = c_lds(keys_s + h * 4) - 1u;
+      };
+      auto reset_all = [&]() {
+        for (uint32_t i = lane; i < d; i += 32) {
+          const uint32_t h = c_lds16(occ_s + i * 2);
+          c_sts(keys_s + h * 4, 0u);
+          c_sts(cnt_s + h * 4, 0u);
+          c_sts(first_s + h * 4, 0xffffffffu);
+        }
+      };
+      // drop the history aids AFTER the cut to N (reference order), compact, pad
+      auto in_history = [&](uint32_t ay, bool mine) {
+        bool hit = false;
+        for (uint32_t m = umask; m; m &= m - 1) {
+          const int32_t hj = __shfl_sync(FULL_MASK, a, __ffs(m) - 1);
+          hit |= mine && (uint32_t)hj == ay;
+        }
+        return hit;
+      };
+      int kept = 0;
+      if (N <= 32) {
+        uint32_t key = 0, ay = 0;
+        bool sorted = false;
+        if (d <= 32) {
+          if (lane < d) entry(lane, key, ay);
+          sorted = true;
+        } else {
+          uint32_t best = 0;
+          for (uint32_t i = lane; i < d; i += 32) {
+            uint32_t k2, y2;
+            entry(i, k2, y2);
+            best = max(best, k2);
+          }
+          const uint32_t thr = warp_kth_largest_u32(best, N);   // d > 32: every lane holds an entry
+          // survivors (key >= thr) into the dead segment arrays (NSEG >= 40), at most 32 kept
+          uint32_t n_c = 0;
+          for (uint32_t i0 = 0; i0 < d; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint32_t k2 = 0, y2 = 0;
+            if (i < d) entry(i, k2, y2);
+            const bool q = i < d && k2 >= thr;
+            const uint32_t m = __ballot_sync(FULL_MASK, q);
+            const uint32_t at = n_c + __popc(m & lt);
+            if (q && at < 32u) {
+              c_sts(segst_s + at * 4, k2);
+              c_sts(segaid_s + at * 4, y2);
+            }
+            n_c += __popc(m);
+          }
+          __syncwarp();
+          if (n_c <= 32u) {
+            if (lane < n_c) {
+              key = c_lds(segst_s + lane * 4);
+              ay = c_lds(segaid_s + lane * 4);
+            }
+            sorted = true;
+          }
+        }
+        if (sorted) {
+          warp_sort_desc_kv(key, ay);
+        } else {
+          // more than 32 survivors (one lane held many of the best): N rounds of exact extraction
+          uint32_t taken_below = 0xffffffffu;   // keys are unique: extract strictly below the last one
+          uint32_t rk = 0, ra = 0;
+          for (int r = 0; r < n_top; ++r) {
+            uint32_t bk = 0, ba = 0;
+            for (uint32_t i = lane; i < d; i += 32) {
+              uint32_t k2, y2;
+              entry(i, k2, y2);
+              if (k2 < taken_below && k2 > bk) { bk = k2; ba = y2; }
+            }
+            uint32_t mk = bk;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mk = max(mk, __shfl_xor_sync(FULL_MASK, mk, o));
+            const uint32_t src = __ffs(__ballot_sync(FULL_MASK, bk == mk)) - 1;
+            const uint32_t ma = __shfl_sync(FULL_MASK, ba, src);
+            if ((int)lane == r) { rk = mk; ra = ma; }
+            taken_below = mk;
+          }
+          key = rk;
+          ay = ra;
+        }
+        __syncwarp();
+        reset_all();
+        const bool mine = (int)lane < n_top;
+        const bool drop = sp.drop_history ? in_history(ay, mine) : false;
+        const bool keep = mine && !drop;
+        const uint32_t km = __ballot_sync(FULL_MASK, keep);
+        if (keep) {
+          const int at = __popc(km & lt);
+          oa[at] = (int32_t)ay;
+          os[at] = (int32_t)(key >> 16);
+        }
+        kept = __popc(km);
+      } else {
+        // ranker form (N = 100): sort all entries, inverted 64-bit keys ascending = most_common order
+        for (uint32_t i = lane; i < d; i += 32) {
+          uint32_t k2, y2;
+          entry(i, k2, y2);
+          ent[i] = ~(((uint64_t)k2 << 32) | y2);
+        }
+        const int np = pow2_at_least((int)d > 1 ? (int)d : 1);
+        for (int i = (int)d + (int)lane; i < np; i += 32) ent[i] = ~0ull;
+        __syncwarp();
+        bitonic_sort<32>(ent, np, (int)lane);
+        reset_all();
+        for (int r0 = 0; r0 < n_top; r0 += 32) {
+          const int r = r0 + (int)lane;
+          const bool mine = r < n_top;
+          const uint64_t e = mine ? ~ent[r] : 0ull;
+          const uint32_t ay = (uint32_t)e;
+          const bool drop = sp.drop_history ? in_history(ay, mine) : false;
+          const bool keep = mine && !drop;
+          const uint32_t km = __ballot_sync(FULL_MASK, keep);
+          if (keep) {
+            const int at = kept + __popc(km & lt);
+            oa[at] = (int32_t)ay;
+            os[at] = (int32_t)(e >> 48);
+          }
+          kept += __popc(km);
+        }
+      }
+      if (lane == 0) p.out_len[(int64_t)tg * p.n_sessions + s] = kept;
+      for (int r = kept + (int)lane; r < N; r += 32) {
+        oa[r] = -1;
+        os[r] = 0;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// =====================================================================================================
+// cooperative tiers (round 2): one block per session for the sessions the warp tiers do not take
+// =====================================================================================================
+// Same algorithm as the fast warp kernel with the session's events in shared memory: the unique aids come from a
+// small hash table keyed by aid (smallest recency index, OR of the event types), their recency / ascending ranks from
+// a count per unique aid, the segments from warp 0 (ordered prefix), the votes from all threads.  Seven barriers per
+// session instead of the ~100 (two shared-memory bitonic sorts per source, thread-0 loops) of the round-1 block tiers.
+template <int T, int LOGHS, int LCAP>
+struct CoopCfg {
+  static constexpr int HS = 1 << LOGHS;
+  static constexpr int VCAP = HS / 2;
+  static constexpr int NSEG = LCAP * OTTO_MAX_SOURCES < VCAP ? LCAP * OTTO_MAX_SOURCES : VCAP;
+  static constexpr int HU = 2 * LCAP;     // history hash slots (LCAP is a power of two)
+  // u32: keys cnt first [HS] | seg_start seg_aid [NSEG] | uh_key uh_idx uh_tm [HU] | H_aid H_tm asc_to_h uocc [LCAP] | cand_k cand_a [64]
+  // u16: occ [VCAP]   u8: seg_tab [NSEG]   u64: ent [VCAP] (top_n > 32)
+  __host__ __device__ static constexpr size_t words() { return (size_t)HS * 3 + NSEG * 2 + HU * 3 + LCAP * 4 + 128; }
+  __host__ __device__ static constexpr size_t bytes(bool with_ent) {
+    return (words() * 4 + (size_t)VCAP * 2 + NSEG + 15) / 16 * 16 + (with_ent ? (size_t)VCAP * 8 : 0);
+  }
+};
+
+// LIST 0: list_block, 1: list_large, 2: list_mid
+template <int T, int LOGHS, int LCAP, int LIST>
+__global__ void __launch_bounds__(T) candidates_coop_kernel(const CandParams p, int with_ent) {
+  using Cfg = CoopCfg<T, LOGHS, LCAP>;
+  constexpr int WARPS = T / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_item, s_U, s_nocc, s_T, s_nseg, s_ncand, s_thr;
+  __shared__ uint32_t s_gmax[WARPS][32];
+  const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5, lt = lanemask_lt();
+  const uint32_t keys_s = c_smem(smem_raw), cnt_s = keys_s + Cfg::HS * 4, first_s = cnt_s + Cfg::HS * 4;
+  const uint32_t segst_s = first_s + Cfg::HS * 4, segaid_s = segst_s + Cfg::NSEG * 4;
+  const uint32_t uhk_s = segaid_s + Cfg::NSEG * 4, uhi_s = uhk_s + Cfg::HU * 4, uht_s = uhi_s + Cfg::HU * 4;
+  const uint32_t Ha_s = uht_s + Cfg::HU * 4, Ht_s = Ha_s + LCAP * 4, a2h_s = Ht_s + LCAP * 4, uocc_s = a2h_s + LCAP * 4;
+  const uint32_t ck_s = uocc_s + LCAP * 4, ca_s = ck_s + 64 * 4;
+  const uint32_t occ_s = ca_s + 64 * 4, segtab_s = occ_s + Cfg::VCAP * 2;
+  uint64_t* ent = (uint64_t*)(smem_raw + (Cfg::words() * 4 + (size_t)Cfg::VCAP * 2 + Cfg::NSEG + 15) / 16 * 16);
+  const uint32_t nocc_s = c_smem(&s_nocc), U_s = c_smem(&s_U), ncand_s = c_smem(&s_ncand);
+
+  const uint32_t* list = LIST == 0 ? p.list_block : LIST == 1 ? p.list_large : p.list_mid;
+  const uint32_t n_items = p.counters[LIST == 0 ? 0 : LIST == 1 ? 4 : 6];
+  if (n_items == 0) return;
+  for (uint32_t h = tid; h < (uint32_t)Cfg::HS; h += T) {
+    c_sts(keys_s + h * 4, 0u);
+    c_sts(cnt_s + h * 4, 0u);
+    c_sts(first_s + h * 4, 0xffffffffu);
+  }
+  for (uint32_t h = tid; h < (uint32_t)Cfg::HU; h += T) {
+    c_sts(uhk_s + h * 4, 0u);
+    c_sts(uhi_s + h * 4, 0xffffffffu);
+    c_sts(uht_s + h * 4, 0u);
+  }
+  if (tid == 0) { s_U = 0; s_nocc = 0; s_ncand = 0; }
+  const OttoCandidateSpec& sp = p.spec;
+  const int N = sp.top_n;
+  while (true) {
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(&p.counters[LIST == 0 ? 2 : LIST == 1 ? 5 : 7], 1u);
+    __syncthreads();
+    const uint32_t item = s_item;
+    if (item >= n_items) break;
+    const int64_t s = (int64_t)list[item];
+    const int32_t end = p.off[s + 1];
+    const int L = end - p.off[s];
+    // 1. unique aids: hash keyed by aid -> smallest recency index, OR of 1 << type
+    for (int i = (int)tid; i < L; i += T) {
+      const uint32_t a = (uint32_t)p.aid[end - 1 - i];
+      const uint32_t ty = p.type[end - 1 - i];
+      uint32_t h = ((a * 0x9E3779B1u) >> 12) & (Cfg::HU - 1);
+      uint32_t prev = c_cas(uhk_s + h * 4, 0u, a + 1u);
+      while (prev != 0u && prev != a + 1u) {
+        h = (h + 1) & (Cfg::HU - 1);
+        prev = c_cas(uhk_s + h * 4, 0u, a + 1u);
+      }
+      if (prev == 0u) c_sts(uocc_s + atomicAdd(&s_U, 1u) * 4, h);
+      c_red_min(uhi_s + h * 4, (uint32_t)i);
+      asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(uht_s + h * 4), "r"(1u << ty) : "memory");
+    }
+    __syncthreads();
+    const uint32_t U = s_U;
+    // 2. recency rank (= position in H) and ascending-aid rank of every unique aid
+    for (uint32_t u = tid; u < U; u += T) {
+      const uint32_t h = c_lds(uocc_s + u * 4);
+      const uint32_t a = c_lds(uhk_s + h * 4) - 1u, idx = c_lds(uhi_s + h * 4), tm = c_lds(uht_s + h * 4);
+      uint32_t r_rec = 0, r_asc = 0;
+      for (uint32_t j = 0; j < U; ++j) {
+        const uint32_t hj = c_lds(uocc_s + j * 4);
+        r_rec += c_lds(uhi_s + hj * 4) < idx;
+        r_asc += (int32_t)(c_lds(uhk_s + hj * 4) - 1u) < (int32_t)a;
+      }
+      c_sts(Ha_s + r_rec * 4, a);
+      c_sts(Ht_s + r_rec * 4, tm);
+      c_sts(a2h_s + r_asc * 4, r_rec);
+    }
+    __syncthreads();
+    for (uint32_t u = tid; u < U; u += T) {   // the history hash is free again
+      const uint32_t h = c_lds(uocc_s + u * 4);
+      c_sts(uhk_s + h * 4, 0u);
+      c_sts(uhi_s + h * 4, 0xffffffffu);
+      c_sts(uht_s + h * 4, 0u);
+    }
+    if (tid == 0) s_U = 0;
+    for (int ri = 0; ri < p.n_run; ++ri) {
+      const int tg = p.run_target[ri];
+      // 3. segments (warp 0): elements of every source in concatenation order, 32 at a time
+      if (warp == 0) {
+        uint32_t nseg = 0, Tt = 0;
+        for (int si = 0; si < sp.target_n_sources[tg]; ++si) {
+          const int src = sp.target_sources[tg][si];
+          const int tb = sp.source_table[src], sel = sp.source_hist[src];
+          const uint32_t mask = hist_mask(sel);
+          for (uint32_t e0 = 0; e0 < U; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            uint32_t len = 0, a = 0;
+            if (e < U) {
+              const uint32_t hi = sel == OTTO_HIST_RECENCY ? e : c_lds(a2h_s + e * 4);
+              a = c_lds(Ha_s + hi * 4);
+              const bool flag = (sel == OTTO_HIST_RECENCY || (c_lds(Ht_s + hi * 4) & mask) != 0) && a < (uint32_t)sp.n_aids;
+              if (flag) len = (uint32_t)sp.table_len[tb][a];
+            }
+            const uint32_t fm = __ballot_sync(FULL_MASK, len > 0);
+            uint32_t inc = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const uint32_t v = __shfl_up_sync(FULL_MASK, inc, o);
+              if ((int)lane >= o) inc += v;
+            }
+            if (len > 0) {
+              const uint32_t sg = nseg + __popc(fm & lt);
+              c_sts(segst_s + sg * 4, Tt + inc - len);
+              c_sts(segaid_s + sg * 4, a);
+              c_sts8(segtab_s + sg, (uint32_t)tb);
+            }
+            nseg += __popc(fm);
+            Tt += __shfl_sync(FULL_MASK, inc, 31);
+          }
+        }
+        if (lane == 0) { s_T = Tt; s_nseg = nseg; }
+      }
+      __syncthreads();
+      const uint32_t Tt = s_T, nseg = s_nseg;
+      // 4. votes
+      for (uint32_t q0 = 0; q0 < Tt; q0 += T) {
+        const uint32_t q = q0 + tid;
+        const bool has = q < Tt;
+        uint32_t lo = 0, hi = nseg - 1;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi + 1) >> 1;
+          if (c_lds(segst_s + mid * 4) <= (has ? q : 0u)) lo = mid;
+          else hi = mid - 1;
+        }
+        uint32_t y = 0;
+        if (has) {
+          const uint32_t r = q - c_lds(segst_s + lo * 4);
+          const uint32_t tb = c_lds8(segtab_s + lo);
+          y = (uint32_t)sp.table_aid_y[tb][(int64_t)c_lds(segaid_s + lo * 4) * sp.table_k[tb] + r];
+        }
+        uint32_t h = (y * 0x9E3779B1u) >> (32 - LOGHS);
+        uint32_t prev = y + 1u;
+        if (has) {
+          prev = c_cas(keys_s + h * 4, 0u, y + 1u);
+          while (prev != 0u && prev != y + 1u) {
+            h = (h + 1) & (Cfg::HS - 1);
+            prev = c_cas(keys_s + h * 4, 0u, y + 1u);
+          }
+        }
+        __syncwarp();
+        const uint32_t fresh = __ballot_sync(FULL_MASK, has && prev == 0u);
+        if (fresh) {
+          uint32_t base = 0;
+          if (lane == 0) {
+            asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(nocc_s), "r"((uint32_t)__popc(fresh)) : "memory");
+          }
+          base = __shfl_sync(FULL_MASK, base, 0);
+          if (has && prev == 0u) c_sts16(occ_s + (base + __popc(fresh & lt)) * 2, h);
+        }
+        if (has) {
+          c_red_add(cnt_s + h * 4, 1u);
+          c_red_min(first_s + h * 4, q);
+        }
+      }
+      __syncthreads();
+      const uint32_t d = s_nocc;
+      int32_t* oa = p.out_aid + ((int64_t)tg * p.n_sessions + s) * N;
+      int32_t* os = p.out_score + ((int64_t)tg * p.n_sessions + s) * N;
+      const int n_top = (int)d < N ? (int)d : N;
+      auto entry = [&](uint32_t i, uint32_t& key, uint32_t& ay) {
+        const uint32_t h = c_lds16(occ_s + i * 2);
+        key = (c_lds(cnt_s + h * 4) << 16) | (0xffffu - c_lds(first_s + h * 4));
+        ay = c_lds(keys_s + h * 4) - 1u;
+      };
+      auto in_history = [&](uint32_t ay) {   // a membership scan over H (<= LCAP entries)
+        bool hit = false;
+        for (uint32_t u = 0; u < U; ++u) hit |= c_lds(Ha_s + u * 4) == ay;
+        return hit;
+      };
+      if (N <= 32) {
+        // 5. threshold from the lane-group maxima, survivors, exact order by one warp
+        uint32_t best = 0;
+        for (uint32_t i = tid; i < d; i += T) {
+          uint32_t k2, y2;
+          entry(i, k2, y2);
+          best = max(best, k2);
+        }
+        s_gmax[warp][lane] = best;
+        __syncthreads();
+        if (warp == 0) {
+          uint32_t g = 0;
+#pragma unroll
+          for (int w = 0; w < WARPS; ++w) g = max(g, s_gmax[w][lane]);
+          const uint32_t thr = warp_kth_largest_u32(g, N);   // 0 when fewer than N lane groups hold an entry
+          if (lane == 0) s_thr = thr;
+        }
+        __syncthreads();
+        const uint32_t thr = s_thr;
+        for (uint32_t i0 = 0; i0 < d; i0 += T) {
+          const uint32_t i = i0 + tid;
+          uint32_t k2 = 0, y2 = 0;
+          if (i < d) entry(i, k2, y2);
+          const bool q = i < d && k2 >= thr;
+          const uint32_t m = __ballot_sync(FULL_MASK, q);
+          if (m) {
+            uint32_t base = 0;
+            if (lane == 0) {
+              asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(ncand_s), "r"((uint32_t)__popc(m)) : "memory");
+            }
+            base = __shfl_sync(FULL_MASK, base, 0);
+            const uint32_t at = base + __popc(m & lt);
+            if (q && at < 64u) {
+              c_sts(ck_s + at * 4, k2);
+              c_sts(ca_s + at * 4, y2);
+            }
+          }
+        }
+        __syncthreads();
+        if (warp == 0) {
+          const uint32_t n_c = s_ncand;
+          uint32_t key = 0, ay = 0;
+          if (n_c <= 32u) {
+            if (lane < n_c) {
+              key = c_lds(ck_s + lane * 4);
+              ay = c_lds(ca_s + lane * 4);
+            }
+            warp_sort_desc_kv(key, ay);
+          } else {
+            // more survivors than lanes: N rounds of exact extraction over all entries (keys are unique)
+            uint32_t below = 0xffffffffu, rk = 0, ra = 0;
+            for (int r = 0; r < n_top; ++r) {
+              uint32_t bk = 0, ba = 0;
+              for (uint32_t i = lane; i < d; i += 32) {
+                uint32_t k2, y2;
+                entry(i, k2, y2);
+                if (k2 < below && k2 > bk) { bk = k2; ba = y2; }
+              }
+              uint32_t mk = bk;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) mk = max(mk, __shfl_xor_sync(FULL_MASK, mk, o));
+              const uint32_t srcl = __ffs(__ballot_sync(FULL_MASK, bk == mk)) - 1;
+              const uint32_t ma = __shfl_sync(FULL_MASK, ba, srcl);
+              if ((int)lane == r) { rk = mk; ra = ma; }
+              below = mk;
+            }
+            key = rk;
+            ay = ra;
+          }
+          const bool mine = (int)lane < n_top;
+          const bool keep = mine && !(sp.drop_history && in_history(ay));
+          const uint32_t km = __ballot_sync(FULL_MASK, keep);
+          if (keep) {
+            const int at = __popc(km & lt);
+            oa[at] = (int32_t)ay;
+            os[at] = (int32_t)(key >> 16);
+          }
+          const int kept = __popc(km);
+          if (lane == 0) p.out_len[(int64_t)tg * p.n_sessions + s] = kept;
+          for (int r = kept + (int)lane; r < N; r += 32) {
+            oa[r] = -1;
+            os[r] = 0;
+          }
+        }
+        __syncthreads();
+      } else {
+        // ranker form: sort all entries (inverted keys ascending = most_common order), cut, drop history, compact
+        for (uint32_t i = tid; i < d; i += T) {
+          uint32_t k2, y2;
+          entry(i, k2, y2);
+          ent[i] = ~(((uint64_t)k2 << 32) | y2);
+        }
+        const int np = pow2_at_least((int)d > 1 ? (int)d : 1);
+        for (int i = (int)d + (int)tid; i < np; i += T) ent[i] = ~0ull;
+        __syncthreads();
+        bitonic_sort<T>(ent, np, (int)tid);
+        if (warp == 0) {
+          int kept = 0;
+          for (int r0 = 0; r0 < n_top; r0 += 32) {
+            const int r = r0 + (int)lane;
+            const bool mine = r < n_top;
+            const uint64_t e = mine ? ~ent[r] : 0ull;
+            const uint32_t ay = (uint32_t)e;
+            const bool keep = mine && !(sp.drop_history && in_history(ay));
+            const uint32_t km = __ballot_sync(FULL_MASK, keep);
+            if (keep) {
+              const int at = kept + __popc(km & lt);
+              oa[at] = (int32_t)ay;
+              os[at] = (int32_t)(e >> 48);
+            }
+            kept += __popc(km);
+          }
+          if (lane == 0) p.out_len[(int64_t)tg * p.n_sessions + s] = kept;
+          for (int r = kept + (int)lane; r < N; r += 32) {
+            oa[r] = -1;
+            os[r] = 0;
+          }
+        }
+        __syncthreads();
+      }
+      // reset the claimed vote slots and the counters for the next target / session
+      for (uint32_t i = tid; i < d; i += T) {
+        const uint32_t h = c_lds16(occ_s + i * 2);
+        c_sts(keys_s + h * 4, 0u);
+        c_sts(cnt_s + h * 4, 0u);
+        c_sts(first_s + h * 4, 0xffffffffu);
+      }
+      __syncthreads();
+      if (tid == 0) { s_nocc = 0; s_ncand = 0; }
+    }
   }
 }
 
@@ -496,13 +1145,25 @@ static int check_cand_spec(const OttoCandidateSpec* sp) {
 
 constexpr int GLOBAL_BLOCKS = 296;
 
+static cudaStream_t g_cside[4];
+static cudaEvent_t g_cfork, g_cjoin[4];
+static bool g_cside_ready = false;
+static int cand_streams_init() {
+  if (g_cside_ready) return OTTO_OK;
+  for (auto& cs : g_cside) CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&g_cfork, cudaEventDisableTiming));
+  for (auto& e : g_cjoin) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  g_cside_ready = true;
+  return OTTO_OK;
+}
+
 extern "C" int64_t otto_candidates_scratch_bytes(int64_t n_sessions, int32_t max_session_len, const OttoCandidateSpec* spec) {
   if (check_cand_spec(spec)) return -1;
   if ((int64_t)max_session_len * spec_max_k_sum(spec) >= 65535) {
     otto_set_error("session too long: positions are 16-bit (max_session_len * sum of k must be < 65535)");
     return -1;
   }
-  const int64_t lists = align_up((n_sessions + 1) * 4, 256) * 3 + 256;
+  const int64_t lists = align_up((n_sessions + 1) * 4, 256) * 4 + 256;
   return lists + GLOBAL_BLOCKS * global_slab_words(max_session_len, spec_max_k_sum(spec)) * 8 + 256;
 }
 
@@ -531,8 +1192,9 @@ extern "C" int otto_candidates(const OttoSessions* sessions, int32_t max_session
   p.list_block = (uint32_t*)sc;
   p.list_global = (uint32_t*)(sc + list_bytes);
   p.list_large = (uint32_t*)(sc + 2 * list_bytes);
-  p.counters = (uint32_t*)(sc + 3 * list_bytes);
-  p.slab = (uint64_t*)(sc + 3 * list_bytes + 256);
+  p.list_mid = (uint32_t*)(sc + 3 * list_bytes);
+  p.counters = (uint32_t*)(sc + 4 * list_bytes);
+  p.slab = (uint64_t*)(sc + 4 * list_bytes + 256);
   p.max_k_sum = spec_max_k_sum(spec);
   p.max_len = max_session_len;
   p.slab_words = global_slab_words(max_session_len, p.max_k_sum);
@@ -554,27 +1216,55 @@ extern "C" int otto_candidates(const OttoSessions* sessions, int32_t max_session
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   {
-    constexpr size_t smem = CAND_WARPS * work_bytes<W_LCAP, W_MCAP>();
-    CUDA_TRY(cudaFuncSetAttribute(candidates_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // tiers by session length: <= lmax0 events the fast warp kernel (one event per lane, <= 256 votes), then the
+    // cooperative kernels (128 threads / 2048 slots, 128 / 4096, 256 / 8192) and the global-slab tier for the rest
+    using C0 = FastCfg<9, 8>;
+    using B0 = CoopCfg<128, 11, 32>;
+    using B2 = CoopCfg<128, 12, MID_LCAP>;
+    using B1 = CoopCfg<256, 13, X_LCAP>;
+    static_assert(B2::VCAP == MID_MCAP && B1::VCAP == X_MCAP, "tier bounds follow the table sizes");
+    const int ks = p.max_k_sum > 0 ? p.max_k_sum : 1;
+    const int lmax0 = C0::VCAP / ks < 8 ? C0::VCAP / ks : 8;
+    int lmax1 = B0::VCAP / ks < 32 ? B0::VCAP / ks : 32;
+    if (lmax1 < lmax0) lmax1 = lmax0;
+    const int with_ent = spec->top_n > 32 ? 1 : 0;
+    candidates_classify_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(p, lmax0, lmax1);
+    LAUNCH_CHECK();
+    // every tier under-fills the GPU on its own (the long-session tiers are latency bound at one block per SM), and
+    // they work on disjoint sessions: run them concurrently, largest footprint first
+    if ((rc = cand_streams_init())) return rc;
+    CUDA_TRY(cudaEventRecord(g_cfork, st));
+    for (auto& cs : g_cside) CUDA_TRY(cudaStreamWaitEvent(cs, g_cfork, 0));
+    auto k1 = candidates_coop_kernel<256, 13, X_LCAP, 1>;
+    auto k2 = candidates_coop_kernel<128, 12, MID_LCAP, 2>;
+    auto k0 = candidates_coop_kernel<128, 11, 32, 0>;
+    const size_t sm0 = B0::bytes(with_ent != 0), sm1 = B1::bytes(with_ent != 0), sm2 = B2::bytes(with_ent != 0);
+    CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
+    CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+    CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+    int occ0 = 1, occ1 = 1, occ2 = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, k0, 128, sm0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k1, 256, sm1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k2, 128, sm2);
+    k1<<<n_sm * (occ1 > 0 ? occ1 : 1), 256, sm1, g_cside[0]>>>(p, with_ent);
+    LAUNCH_CHECK();
+    candidates_block_kernel<2, 256><<<GLOBAL_BLOCKS, 256, 0, g_cside[1]>>>(p, global_lcap(max_session_len), global_mcap(max_session_len, p.max_k_sum));
+    LAUNCH_CHECK();
+    k2<<<n_sm * (occ2 > 0 ? occ2 : 1), 128, sm2, g_cside[2]>>>(p, with_ent);
+    LAUNCH_CHECK();
+    k0<<<n_sm * (occ0 > 0 ? occ0 : 1), 128, sm0, g_cside[3]>>>(p, with_ent);
+    LAUNCH_CHECK();
+    const size_t smem0 = CAND_WARPS * C0::bytes(with_ent != 0);
+    CUDA_TRY(cudaFuncSetAttribute(candidates_fast_kernel<9, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
     int64_t blocks = ceil_div(S, CAND_WARPS);
-    if (blocks > (int64_t)n_sm * 40) blocks = (int64_t)n_sm * 40;
-    candidates_warp_kernel<<<(unsigned)blocks, CAND_WARPS * 32, smem, st>>>(p);
+    if (blocks > (int64_t)n_sm * 32) blocks = (int64_t)n_sm * 32;
+    candidates_fast_kernel<9, 8, 0><<<(unsigned)blocks, CAND_WARPS * 32, smem0, st>>>(p, lmax0, lmax1, with_ent);
     LAUNCH_CHECK();
+    for (int i = 0; i < 4; ++i) {
+      CUDA_TRY(cudaEventRecord(g_cjoin[i], g_cside[i]));
+      CUDA_TRY(cudaStreamWaitEvent(st, g_cjoin[i], 0));
+    }
   }
-  {
-    constexpr size_t smem = work_bytes<B_LCAP, B_MCAP>();
-    CUDA_TRY(cudaFuncSetAttribute(candidates_block_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    candidates_block_kernel<0, 128><<<n_sm * 5, 128, smem, st>>>(p, 0, 0);
-    LAUNCH_CHECK();
-  }
-  {
-    constexpr size_t smem = work_bytes<X_LCAP, X_MCAP>();
-    CUDA_TRY(cudaFuncSetAttribute(candidates_block_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    candidates_block_kernel<1, 256><<<n_sm, 256, smem, st>>>(p, 0, 0);
-    LAUNCH_CHECK();
-  }
-  candidates_block_kernel<2, 256><<<GLOBAL_BLOCKS, 256, 0, st>>>(p, global_lcap(max_session_len), global_mcap(max_session_len, p.max_k_sum));
-  LAUNCH_CHECK();
   for (int tg = 0; tg < spec->n_targets; ++tg) {
     if (dup_of[tg] < 0) continue;
     const int64_t slab = S * spec->top_n;

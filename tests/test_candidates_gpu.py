@@ -245,7 +245,7 @@ def test_regular_candidate_form_matches_reference_loop(mods):
     sess = cv.ingest(frame, "asc", device="cuda:0")
     labels = {"click": {}, "cart": {int(df["session"].iloc[0]): {int(df["aid"].iloc[0])}}, "order": {}}
     for n, n_chunks in ((100, 15), (5, 1)):
-        got = cand_mod.regular_candidates(sess, tables, n, labels=labels, n_chunks=n_chunks)
+        got = cand_mod.regular_candidates(sess, tables, n, labels=labels)
         want = oc.regular_frame(df, otables, n)
         for event in ("click", "cart", "order"):
             g, w = got[event], want[event]
