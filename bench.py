@@ -451,6 +451,29 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = (lib.otto_launch_count() - launches0) // max(1, args.steps)
+    dist_phase_ms, nvlink = None, None
+    if world > 1:
+        # phase times at N > 1: three extra steps OUTSIDE the timed region with CUDA events recorded between the phases
+        # (no synchronisation inside a build), and the bytes this rank's scatter stored into OTHER owners' HBM
+        acc = {}
+        for _ in range(3):
+            tm = {"__events__": True}
+            distributed.build_topk_distributed(backend, timing=tm)
+            torch.cuda.synchronize(dev)
+            for k, v in distributed.phase_ms_from_events(tm).items():
+                acc.setdefault(k, []).append(v)
+        dist_phase_ms = {k: allmax(statistics.mean(v)) for k, v in acc.items()}
+        if backend.owner_direct and getattr(backend, "_gathered", None) is not None:
+            lo_o, hi_o = last["range"]
+            mine = backend._gathered[rank].to(torch.int64) & 0xFFFFFFFF
+            remote = int((mine.sum() - mine[lo_o:hi_o].sum()).item()) * 8
+            remote_max = allmax(float(remote))
+            sc = dist_phase_ms.get("scatter")
+            nvlink = {"off_rank_bytes_per_gpu_max": remote_max, "scatter_ms": sc,
+                      "achieved_gbs": remote_max / (sc * 1e-3) / 1e9 if sc else None,
+                      "peak_gbs": 770.0, "peak_source": "measured peer copy per direction (B200_PROFILING.md); nominal 900",
+                      "what": "bytes the scatter kernel stores into other owners' HBM (NVLink stores) / scatter phase time "
+                              "(kernel + the 4-byte all-reduce that orders 'all scatters have landed')"}
     if world == 1:
         # per-kernel times of the reduce phase: three extra steps OUTSIDE the timed region with the library's event
         # bracketing on (profiled calls run the block kernels back to back instead of concurrently)
@@ -567,7 +590,9 @@ def run_b200(args):
                                                if not backend.owner_direct else
                                                "owner-direct scatter (records stored into the owner's buffer over NVLink)"),
                                  "record_bytes_total": sent, "per_gpu_per_step": sent / world,
-                                 "note": "upper bound: includes the records a rank keeps for itself"}}
+                                 "note": "record_bytes_total includes the records a rank keeps for itself; nvlink = off-rank only",
+                                 "nvlink": nvlink},
+                    "phase_ms": dist_phase_ms}
 
     # ---- end to end from pinned host columns ----
     e2e = None

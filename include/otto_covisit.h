@@ -96,6 +96,9 @@ typedef struct {
   int64_t tier_records[4];   /* records accumulated by the warp / 128- / 256- / 512-thread reduce kernels */
   int64_t hot_pairs;         /* pairs of hot (split) rows: they pass through a staging area behind the P final records,
                                 so the record buffer must hold pairs + hot_pairs records */
+  /* otto_covisit_count_finish_owned only (identical on every rank: the layout of all owners is computed everywhere) */
+  int64_t owner_records_max; /* largest record buffer any owner needs (final + staged records) */
+  int64_t owner_bin_cuts[9]; /* [OTTO_MAX_OWNERS + 1] first bin of every owner's aid range; [n_owners] = bins */
 } OttoBuildStats;
 
 /* Pair records of one producer for a contiguous range of bins (multi-GPU: one segment per sender). */
@@ -242,6 +245,15 @@ typedef struct {
   int32_t aid_cuts[OTTO_MAX_OWNERS + 1];     /* owner o holds rows [aid_cuts[o], aid_cuts[o + 1]); [0] = 0, [G] = n_aids */
   void* owner_records[OTTO_MAX_OWNERS];      /* record buffer of every owner as mapped on THIS device (scatter only) */
 } OttoOwnerPlan;
+
+/* The plan on the device, from the all-gathered per-row counts counts_all [n_owners][n_aids] (uint32, rank-major):
+ * row_total [n_aids] := sum over ranks (pass the workspace view of otto_covisit_views), row_before [n_aids] := sum over
+ * the ranks below `rank`, aid_cuts_host [OTTO_MAX_OWNERS + 1] := contiguous aid ranges with (nearly) equal pair counts
+ * (cut g = first row with at least total * g / n_owners pairs in the rows before it).  One synchronisation.
+ * OTTO_EINVAL when a row holds 2^32 or more pairs. */
+int64_t otto_covisit_plan_scratch_bytes(int32_t n_aids);
+int otto_covisit_plan_owners(const uint32_t* counts_all, int32_t n_owners, int32_t rank, int32_t n_aids, uint32_t* row_total,
+                             uint32_t* row_before, void* scratch, int64_t scratch_bytes, int32_t* aid_cuts_host, void* stream);
 
 /* row_before: device uint32 [n_aids], pairs of each row held by ranks below this one.  Synchronises; returns
  * OTTO_EINVAL on every rank alike when any owner would exceed 2^32 - 1 records. */

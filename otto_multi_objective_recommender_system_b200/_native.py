@@ -39,11 +39,13 @@ class OttoBuildSizes(C.Structure):
 
 class OttoBuildStats(C.Structure):
     _fields_ = [("tail_events", i64), ("pairs", i64), ("bins", i64), ("split_rows", i64), ("distinct", i64),
-                ("pair_checksum", i64), ("table_overflow", i64), ("tier_records", i64 * 4), ("hot_pairs", i64)]
+                ("pair_checksum", i64), ("table_overflow", i64), ("tier_records", i64 * 4), ("hot_pairs", i64),
+                ("owner_records_max", i64), ("owner_bin_cuts", i64 * 9)]
 
     def as_dict(self) -> dict:
-        d = {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "tier_records"}
+        d = {n: int(getattr(self, n)) for n, _ in self._fields_ if n not in ("tier_records", "owner_bin_cuts")}
         d["tier_records"] = [int(x) for x in self.tier_records]
+        d["owner_bin_cuts"] = [int(x) for x in self.owner_bin_cuts]
         return d
 
 
@@ -107,6 +109,8 @@ _SIGNATURES = {
     "otto_covisit_scatter": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, vp, i64, vp]),
     "otto_covisit_count_finish_owned": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(OttoOwnerPlan), vp,
                                                   P(OttoBuildStats), vp]),
+    "otto_covisit_plan_scratch_bytes": (i64, [i32]),
+    "otto_covisit_plan_owners": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, i64, P(i32), vp]),
     "otto_covisit_scatter_owned": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(OttoOwnerPlan), vp]),
     "otto_covisit_partition": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, vp, i64, vp]),
     "otto_covisit_reduce_scratch_bytes": (i64, [P(OttoCovisitSpec), i64, i64]),

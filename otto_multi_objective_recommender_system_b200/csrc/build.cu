@@ -202,7 +202,7 @@ static Layout make_layout(int64_t S, int64_t E, const OttoCovisitSpec* spec) {
   if (scan_scratch_elems(L.Bmax + 1) > scan_elems) scan_elems = scan_scratch_elems(L.Bmax + 1);
   if (scan_scratch_elems(L.A + 1) > scan_elems) scan_elems = scan_scratch_elems(L.A + 1);
   L.scan = take(scan_elems * 8);
-  L.stats = take(256);
+  L.stats = take(512);
   L.total = o;
   return L;
 }
@@ -370,13 +370,18 @@ struct OwnerCuts {
   uint32_t cut[OTTO_MAX_OWNERS + 1];
 };
 constexpr int STAT_CUT_E = 8, STAT_CUT_H = 8 + OTTO_MAX_OWNERS + 1;   // stats[] slots of E / Hs at the cuts
+constexpr int STAT_CUT_B = STAT_CUT_H + OTTO_MAX_OWNERS + 1;          // first bin of every owner's range
+constexpr int STAT_WORDS = STAT_CUT_B + OTTO_MAX_OWNERS + 1;
+static_assert(STAT_WORDS * 8 <= 512, "stats region");
 
 __global__ void owner_cut_values_kernel(const OwnerCuts c, const unsigned long long* __restrict__ E,
-                                        const unsigned long long* __restrict__ Hs, unsigned long long* stats) {
+                                        const unsigned long long* __restrict__ Hs, const uint32_t* __restrict__ bin_base,
+                                        unsigned long long* stats) {
   const int o = threadIdx.x;
   if (o <= c.n) {
     stats[STAT_CUT_E + o] = E[c.cut[o]];
     stats[STAT_CUT_H + o] = Hs[c.cut[o]];
+    stats[STAT_CUT_B + o] = bin_base[c.cut[o]];
   }
 }
 
@@ -553,7 +558,7 @@ extern "C" int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitS
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t S = L.S;
   CUDA_TRY(cudaMemsetAsync(WS(uint32_t, row_count), 0, (L.A + 1) * 4, st));
-  CUDA_TRY(cudaMemsetAsync(WS(char, stats), 0, 256, st));
+  CUDA_TRY(cudaMemsetAsync(WS(char, stats), 0, 512, st));
   CUDA_TRY(cudaMemsetAsync(WS(uint32_t, tail_off), 0, (S + 2) * 4, st));
   if (S > 0) {
     tail_count_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(ev->session_offsets, ev->type, S,
@@ -718,7 +723,8 @@ extern "C" int otto_covisit_count_finish_owned(const OttoEvents* ev, const OttoC
   if ((rc = exclusive_scan<unsigned long long, unsigned long long>(WS(unsigned long long, hot_off), A, WS(unsigned long long, hot_off),
                                                                    WS(unsigned long long, scan), st)))
     return rc;
-  owner_cut_values_kernel<<<1, 32, 0, st>>>(cuts, WS(unsigned long long, row_off), WS(unsigned long long, hot_off), stats);
+  owner_cut_values_kernel<<<1, 32, 0, st>>>(cuts, WS(unsigned long long, row_off), WS(unsigned long long, hot_off),
+                                            WS(uint32_t, bin_base), stats);
   LAUNCH_CHECK();
   init_cursor_owned_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(
       cuts, WS(uint32_t, row_total), row_before, WS(uint32_t, bin_base), A, WS(unsigned long long, row_off),
@@ -734,7 +740,7 @@ extern "C" int otto_covisit_count_finish_owned(const OttoEvents* ev, const OttoC
   count_stats_kernel<<<1, 1, 0, st>>>(WS(uint32_t, tail_off), L.S, WS(uint32_t, bin_base), A, WS(unsigned long long, row_off),
                                       WS(unsigned long long, hot_off), stats);
   LAUNCH_CHECK();
-  unsigned long long h[32];
+  unsigned long long h[STAT_WORDS];
   CUDA_TRY(cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   if (h[STAT_BAD_EVENTS]) return bad_events_error(spec, h[STAT_BAD_EVENTS]);
@@ -743,8 +749,10 @@ extern "C" int otto_covisit_count_finish_owned(const OttoEvents* ev, const OttoC
                    "event count of all ranks", h[2], h[3], (long long)L.Bmax, (long long)L.Hmax);
     return OTTO_ENOSPC;
   }
+  unsigned long long need_max = 0;
   for (int o = 0; o < plan->n_owners; ++o) {      // the same verdict on every rank
     const unsigned long long need = (h[STAT_CUT_E + o + 1] - h[STAT_CUT_E + o]) + (h[STAT_CUT_H + o + 1] - h[STAT_CUT_H + o]);
+    if (need > need_max) need_max = need;
     if (need >= (1ull << 32)) {
       otto_set_error("owner %d would hold %llu pair records including its staged hot rows; the limit is 2^32 - 1 (32 GiB): use more owners", o, need);
       return OTTO_EINVAL;
@@ -758,7 +766,84 @@ extern "C" int otto_covisit_count_finish_owned(const OttoEvents* ev, const OttoC
     stats_host->bins = (int64_t)h[2];
     stats_host->split_rows = (int64_t)h[3];
     stats_host->hot_pairs = (int64_t)h[4];
+    stats_host->owner_records_max = (int64_t)need_max;
+    for (int o = 0; o <= OTTO_MAX_OWNERS; ++o)
+      stats_host->owner_bin_cuts[o] = (int64_t)h[STAT_CUT_B + (o <= plan->n_owners ? o : plan->n_owners)];
   }
+  return OTTO_OK;
+}
+
+// ---- owner plan on the device: totals, counts of lower ranks and balanced aid cuts from the all-gathered row counts ----
+__global__ void plan_rows_kernel(const uint32_t* __restrict__ counts, int G, int rank, int64_t A, uint32_t* __restrict__ row_total,
+                                 uint32_t* __restrict__ row_before, unsigned long long* __restrict__ total64, unsigned long long* flags) {
+  const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= A) return;
+  unsigned long long tot = 0, before = 0;
+  for (int g = 0; g < G; ++g) {
+    const unsigned long long c = counts[(int64_t)g * A + x];
+    tot += c;
+    if (g < rank) before += c;
+  }
+  if (tot >= (1ull << 32)) atomicOr(flags, 1ull);
+  row_total[x] = (uint32_t)tot;
+  row_before[x] = (uint32_t)before;
+  total64[x] = tot;
+}
+
+// cut g = first row x with (pairs in rows < x) >= total * g / G: contiguous ranges with (nearly) equal pair counts
+__global__ void plan_cuts_kernel(const unsigned long long* __restrict__ prefix, int64_t A, int G, int32_t* __restrict__ cuts) {
+  const int g = threadIdx.x;
+  if (g > G) return;
+  int64_t cut = g == 0 ? 0 : A;
+  if (g > 0 && g < G) {
+    const unsigned long long total = prefix[A];
+    const unsigned long long target = (unsigned long long)(((unsigned __int128)total * (unsigned)g) / (unsigned)G);
+    int64_t lo = 0, hi = A;     // first x in [0, A] with prefix[x] >= target
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (prefix[mid] >= target) hi = mid;
+      else lo = mid + 1;
+    }
+    cut = lo;
+  }
+  cuts[g] = (int32_t)cut;
+}
+
+extern "C" int64_t otto_covisit_plan_scratch_bytes(int32_t n_aids) {
+  return align_up(((int64_t)n_aids + 2) * 8, 256) + scan_scratch_elems((int64_t)n_aids + 1) * 8 + 512;
+}
+
+extern "C" int otto_covisit_plan_owners(const uint32_t* counts_all, int32_t n_owners, int32_t rank, int32_t n_aids,
+                                        uint32_t* row_total, uint32_t* row_before, void* scratch, int64_t scratch_bytes,
+                                        int32_t* aid_cuts_host, void* stream) {
+  if (!counts_all || !row_total || !row_before || !aid_cuts_host || n_aids <= 0 || n_owners < 1 || n_owners > OTTO_MAX_OWNERS ||
+      rank < 0 || rank >= n_owners) {
+    otto_set_error("bad argument");
+    return OTTO_EINVAL;
+  }
+  if (!scratch || scratch_bytes < otto_covisit_plan_scratch_bytes(n_aids)) { otto_set_error("plan scratch too small"); return OTTO_ENOSPC; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t A = n_aids;
+  char* sc = (char*)scratch;
+  unsigned long long* prefix = (unsigned long long*)sc;
+  unsigned long long* scan_sc = (unsigned long long*)(sc + align_up((A + 2) * 8, 256));
+  unsigned long long* flags = scan_sc + scan_scratch_elems(A + 1);
+  int32_t* cuts_dev = (int32_t*)(flags + 1);
+  CUDA_TRY(cudaMemsetAsync(flags, 0, 8, st));
+  plan_rows_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(counts_all, n_owners, rank, A, row_total, row_before, prefix, flags);
+  LAUNCH_CHECK();
+  int rc = exclusive_scan<unsigned long long, unsigned long long>(prefix, A, prefix, scan_sc, st);
+  if (rc) return rc;
+  plan_cuts_kernel<<<1, 32, 0, st>>>(prefix, A, n_owners, cuts_dev);
+  LAUNCH_CHECK();
+  struct { unsigned long long flag; int32_t cuts[OTTO_MAX_OWNERS + 2]; } h;
+  static_assert(sizeof(h) == 8 + 4 * (OTTO_MAX_OWNERS + 2), "layout");
+  CUDA_TRY(cudaMemcpyAsync(&h, flags, 8 + 4 * (n_owners + 1), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (h.flag) { otto_set_error("an aid_x row holds 2^32 or more pairs"); return OTTO_EINVAL; }
+  for (int o = 0; o <= OTTO_MAX_OWNERS; ++o) aid_cuts_host[o] = h.cuts[o <= n_owners ? o : n_owners];
+  for (int o = 1; o <= OTTO_MAX_OWNERS; ++o)
+    if (aid_cuts_host[o] < aid_cuts_host[o - 1]) aid_cuts_host[o] = aid_cuts_host[o - 1];
   return OTTO_OK;
 }
 

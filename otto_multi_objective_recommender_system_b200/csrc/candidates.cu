@@ -1242,6 +1242,18 @@ extern "C" int otto_candidates(const OttoSessions* sessions, int32_t max_session
     CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
     CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
     CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+    // one shared-memory carve-out for all tiers: kernels that ask for different L1 / shared splits cannot share an SM,
+    // which serialised the tiers (r02: the concurrent launch took exactly the sum of the serial kernel times)
+    static bool carved = false;
+    if (!carved) {
+      CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CUDA_TRY(cudaFuncSetAttribute(candidates_block_kernel<2, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CUDA_TRY(cudaFuncSetAttribute(candidates_fast_kernel<9, 8, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CUDA_TRY(cudaFuncSetAttribute(candidates_classify_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      carved = true;
+    }
     int occ0 = 1, occ1 = 1, occ2 = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, k0, 128, sm0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k1, 256, sm1);

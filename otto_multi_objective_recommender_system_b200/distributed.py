@@ -92,6 +92,13 @@ class PeerRecords:
         self.local = torch.as_tensor(_RawCuda(self.ptr, self.capacity), device=self.device)
         return self.local
 
+    def ensure_same(self, n_records: int) -> torch.Tensor:
+        """Like ensure() when every rank passes the SAME n_records (the owner-direct layout is computed identically
+        everywhere): no collective unless the buffers have to grow."""
+        if int(n_records) <= self.capacity:
+            return self.local
+        return self.ensure(n_records)
+
     def close(self) -> None:
         if self.ptr is None:
             return
@@ -119,6 +126,7 @@ class GpuRankBackend:
         self.b = CovisitBuilder(csr, spec, exact=exact)
         self.n_aids, self.k, self.device = csr.n_aids, spec.k, csr.aid.device
         self.peer = peer          # set: records are exchanged through peer memory instead of NCCL
+        self._plan_scratch = self._row_before = self._gathered = None
 
     def count_begin(self) -> torch.Tensor:
         self.b.count_begin()
@@ -142,12 +150,32 @@ class GpuRankBackend:
         return (self.peer is not None and os.environ.get("OTTO_OWNER_DIRECT", "1") != "0"
                 and dist.is_initialized() and 1 < dist.get_world_size(self.peer.group) <= N.MAX_OWNERS)
 
+    def plan_owners(self, gathered: torch.Tensor, world: int, rank: int):
+        """gathered: [world, A] per-row pair counts of every rank (uint32 bit patterns).  One kernel pass
+        (otto_covisit_plan_owners) writes the totals into the workspace's row_total, the counts of the lower ranks
+        into row_before and finds the balanced aid cuts; one synchronisation."""
+        A = self.n_aids
+        if self._plan_scratch is None:
+            need = int(self.b.lib.otto_covisit_plan_scratch_bytes(A))
+            self._plan_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._row_before = torch.empty(A, dtype=torch.int32, device=self.device)
+        cuts = (C.c_int32 * (N.MAX_OWNERS + 1))()
+        with torch.cuda.device(self.device):
+            N.check(self.b.lib.otto_covisit_plan_owners(gathered.data_ptr(), world, rank, A, self.b.views()["row_total"].data_ptr(),
+                                                        self._row_before.data_ptr(), self._plan_scratch.data_ptr(),
+                                                        self._plan_scratch.numel(), cuts, self.b._st()))
+        return [int(cuts[i]) for i in range(world + 1)], self._row_before
+
     def count_finish_owned(self, aid_cuts, rank, row_before):
         stats = self.b.count_finish_owned(aid_cuts, rank, row_before)
         return stats, self.b.views()["bin_base"]
 
+    def owner_bin_cuts(self, aid_cuts, bin_base) -> list:
+        return [int(self.b.stats.owner_bin_cuts[i]) for i in range(len(aid_cuts))]
+
     def scatter_owned(self, aid_cuts, rank) -> None:
-        self.b.records = self.peer.ensure(int(self.b.stats.pairs) + int(self.b.stats.hot_pairs))     # collective
+        # every rank computed the same layout, so the largest buffer any owner needs is known without a collective
+        self.b.records = self.peer.ensure_same(int(self.b.stats.owner_records_max))
         self.b.scatter_owned(aid_cuts, rank, self.peer.peers)
 
     def partition(self):
@@ -203,20 +231,28 @@ def plan_rows(row_total: torch.Tensor, world: int) -> list:
     return aid_cuts
 
 
-def _build_owner_direct(backend, group, mark, world: int, rank: int):
-    """The exchange fused into the scatter: records are stored straight into the owner's buffer (module docstring)."""
-    local = backend.count_begin()                                   # int32 view of this rank's uint32 row counts
-    mark("count_begin")
-    every = [torch.empty_like(local) for _ in range(world)]
-    dist.all_gather(every, local, group=group)
-    counts = torch.stack(every).to(torch.int64) & 0xFFFFFFFF       # [G, A]
+def plan_owners_host(gathered: torch.Tensor, world: int, rank: int):
+    """Host-side twin of otto_covisit_plan_owners (used by the CPU stand-in backend of the gloo tests):
+    -> (aid cuts, totals, counts of the lower ranks)."""
+    counts = gathered.to(torch.int64) & 0xFFFFFFFF                 # [G, A]
     total = counts.sum(0)
     if int(total.max().item()) >= 2 ** 32:
         raise ValueError("an aid_x row holds 2^32 or more pairs")
     before = counts[:rank].sum(0).to(torch.int32)                  # wraps into the uint32 bit pattern
-    sent = int(counts[rank].sum().item())
-    local.copy_(total.to(torch.int32))                             # the workspace's row_total: totals over all ranks
-    aid_cuts = plan_rows(total, world)
+    return plan_rows(total, world), total, before
+
+
+def _build_owner_direct(backend, group, mark, world: int, rank: int):
+    """The exchange fused into the scatter: records are stored straight into the owner's buffer (module docstring).
+    Host synchronisations per build: the aid cuts (plan), the buffer sizes (count_finish_owned), the final stats."""
+    local = backend.count_begin()                                   # int32 view of this rank's uint32 row counts
+    mark("count_begin")
+    gathered = getattr(backend, "_gathered", None)
+    if gathered is None or gathered.shape != (world, local.numel()) or gathered.device != local.device:
+        gathered = torch.empty((world, local.numel()), dtype=local.dtype, device=local.device)
+        backend._gathered = gathered
+    dist.all_gather(list(gathered.unbind(0)), local, group=group)
+    aid_cuts, before = backend.plan_owners(gathered, world, rank)  # workspace row_total := totals over all ranks
     mark("allgather_rows+plan")
     stats, bin_base = backend.count_finish_owned(aid_cuts, rank, before)
     mark("count_finish")
@@ -227,14 +263,13 @@ def _build_owner_direct(backend, group, mark, world: int, rank: int):
     mark("scatter")
     records, bin_off = backend.partition()
     mark("partition")
-    bin_cuts = [int(v) for v in bin_base.to(torch.int64)[torch.tensor(aid_cuts, device=bin_base.device)].tolist()]
+    bin_cuts = backend.owner_bin_cuts(aid_cuts, bin_base)
     plan = OwnerPlan(aid_cuts, bin_cuts)
     lo, hi = bin_cuts[rank], bin_cuts[rank + 1]
     table = backend.reduce([(records, bin_off[lo:hi + 1])], lo, hi, aid_cuts[rank], aid_cuts[rank + 1])
     mark("merge+reduce")
     out_stats = dict(backend.stats())
     out_stats["owned_aids"] = aid_cuts[rank + 1] - aid_cuts[rank]
-    out_stats["sent_records"] = sent
     return table, (aid_cuts[rank], aid_cuts[rank + 1]), out_stats, plan
 
 
@@ -245,13 +280,21 @@ def build_topk_distributed(backend, group=None, timing: dict | None = None):
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     import time
     t_last = [time.perf_counter()]
+    use_events = timing is not None and timing.get("__events__")
 
-    def mark(name):     # phase timing for profiling runs only (synchronises)
-        if timing is not None:
-            torch.cuda.synchronize()
-            now = time.perf_counter()
-            timing[name] = timing.get(name, 0.0) + (now - t_last[0]) * 1e3
-            t_last[0] = now
+    def mark(name):     # phase timing for profiling runs only
+        if timing is None:
+            return
+        if use_events:
+            # CUDA events on the build's stream, no synchronisation: read with phase_ms_from_events() after the build
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            timing.setdefault("__marks__", []).append((name, e))
+            return
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        timing[name] = timing.get(name, 0.0) + (now - t_last[0]) * 1e3
+        t_last[0] = now
     mark("start")
     if world > 1 and getattr(backend, "owner_direct", False):
         return _build_owner_direct(backend, group, mark, world, rank)
@@ -319,6 +362,16 @@ def build_topk_distributed(backend, group=None, timing: dict | None = None):
     out_stats["owned_aids"] = plan.aid_cuts[rank + 1] - plan.aid_cuts[rank]
     out_stats["sent_records"] = int(stats["pairs"])
     return table, (plan.aid_cuts[rank], plan.aid_cuts[rank + 1]), out_stats, plan
+
+
+def phase_ms_from_events(timing: dict) -> dict:
+    """{phase: ms} from the CUDA events a build recorded with timing = {"__events__": True} (call after a synchronise)."""
+    marks = timing.get("__marks__", [])
+    out = {}
+    for (_, a), (name, b) in zip(marks, marks[1:]):
+        if name != "start":
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+    return out
 
 
 def gather_table(table: TopKTable, plan: OwnerPlan, group=None) -> TopKTable:

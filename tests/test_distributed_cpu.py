@@ -79,6 +79,15 @@ class NumpyOwnerBackend(NumpyRankBackend):
     (position, record) lists that every owner applies to its own array."""
     owner_direct = True
 
+    def plan_owners(self, gathered, world, rank):
+        from otto_multi_objective_recommender_system_b200 import distributed
+        cuts, total, before = distributed.plan_owners_host(gathered, world, rank)
+        self.total.copy_(total.to(torch.int32))                     # the stand-in's "workspace row_total"
+        return cuts, before
+
+    def owner_bin_cuts(self, aid_cuts, bin_base):
+        return [int(bin_base[x]) for x in aid_cuts]
+
     def count_finish_owned(self, aid_cuts, rank, row_before):
         stats, bin_base = self.count_finish()                       # bins from the totals (self.total was summed in place)
         tot = self.total.numpy().astype(np.int64)

@@ -45,10 +45,22 @@ def _worker(rank, world, port, variant, split_ub, n_sessions, n_aids, transport)
 @pytest.mark.parametrize("transport", ["owner_direct", "peer_read", "nccl"])
 @pytest.mark.parametrize("variant,split_ub", [("CLICKS", 0), ("CARTS_ORDERS", 64), ("BUY2BUY", 0)])
 def test_multi_gpu_equals_single_gpu(native_lib, variant, split_ub, transport):
-    world = min(torch.cuda.device_count(), 4)
+    world = min(torch.cuda.device_count(), 8)      # every GPU of the box: the owner-direct scatter must hold at 8 ranks too
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     torch.multiprocessing.spawn(_worker, args=(world, port, variant, split_ub, 20000, 2500, transport), nprocs=world, join=True)
+
+
+def test_eight_rank_owner_direct_full_width(native_lib):
+    """The default transport at the full width of a box (8 ranks, or whatever the box has beyond 4): a larger frame, so
+    that every owner holds hot rows and receives records from every peer."""
+    world = min(torch.cuda.device_count(), 8)
+    if world <= 4:
+        pytest.skip("needs more than 4 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    torch.multiprocessing.spawn(_worker, args=(world, port, "CLICKS", 256, 60000, 4000, "owner_direct"), nprocs=world, join=True)
