@@ -359,6 +359,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"        # the version banner goes to stdout, where the one JSON line belongs
         dist.init_process_group("nccl", device_id=dev)
     lib = N.lib()
     spec = {"clicks": covisit.CLICKS, "carts_orders": covisit.CARTS_ORDERS, "buy2buy": covisit.BUY2BUY}[args.variant]
@@ -456,6 +458,7 @@ def run_b200(args):
         # phase times at N > 1: three extra steps OUTSIDE the timed region with CUDA events recorded between the phases
         # (no synchronisation inside a build), and the bytes this rank's scatter stored into OTHER owners' HBM
         acc = {}
+        barrier()                                      # rank 0 just spent ~0.2 s stopping the clock sampler
         for _ in range(3):
             tm = {"__events__": True}
             distributed.build_topk_distributed(backend, timing=tm)

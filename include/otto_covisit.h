@@ -148,6 +148,18 @@ int otto_frame_is_sorted(const int32_t* session, const int32_t* ts, int64_t n_ev
 int otto_frame_check(const int32_t* aid, const uint8_t* type, int64_t n_events, int32_t n_aids, void* count_dev,
                      int64_t* n_bad_host, void* stream);
 
+/* Frame -> session CSR in two passes over the session column (no per-event temporaries).  Pass 1 counts the session
+ * starts per tile and checks, in the same read, the (session, ts) order and the event contents: info_host [3] =
+ * {n_sessions, sorted (1 / 0), events with an aid outside [0, n_aids) or a type above 2} (aid == NULL skips the content
+ * check); synchronises.  Pass 2 (same scratch, untouched in between) writes the session ids [n_sessions], the offsets
+ * int32 [n_sessions + 1] and the longest session.  Replaces groupby('session') of covisitation/inference.py:117 and
+ * the chunk writer's sort check (utilities/split_dataset_writer_parquet.py:17). */
+int64_t otto_ingest_scratch_bytes(int64_t n_events);
+int otto_ingest_scan(const int32_t* session, const int32_t* aid, const int32_t* ts, const uint8_t* type, int64_t n_events,
+                     int32_t n_aids, void* scratch, int64_t scratch_bytes, int64_t* info_host /* [3] */, void* stream);
+int otto_ingest_offsets(const int32_t* session, int64_t n_events, int64_t n_sessions, void* scratch, int64_t scratch_bytes,
+                        int32_t* session_ids, int32_t* offsets, int32_t* max_len_dev, void* stream);
+
 /* From a frame sorted by (session, ts) ascending with run-length offsets (ascending CSR), writes the
  * most-recent-first CSR columns: inside each session ts descending, ties in original row order. */
 int otto_ingest_desc(const int32_t* session_offsets, int64_t n_sessions, const int32_t* aid, const int32_t* ts,
@@ -373,6 +385,58 @@ int otto_regular_row_counts(const OttoSessions* sessions, const int32_t* aid, co
 int otto_regular_rows(const OttoSessions* sessions, const int32_t* aid, const int32_t* score, const int32_t* len, int32_t top_n,
                       const int64_t* row_offsets, const int32_t* session_ids, const OttoLabels* labels, int32_t* session_out,
                       uint64_t* candidates_out, float* scores_out, uint8_t* labels_out, void* stream);
+
+/* ---- interaction features over a candidate frame (ranker/interaction_feature_engineering.py:47-113) ---- */
+
+/* One event type's candidate frame as flat device columns (what otto_explode_candidates / otto_regular_rows write and
+ * candidate/{event}_{validation,test}.pkl holds), sorted by session. */
+typedef struct {
+  int64_t n_rows;
+  const int32_t* session;
+  const uint64_t* candidates;
+  const float* candidate_scores;
+} OttoCandidateFrame;
+
+/* Output columns, each [n_rows]; a NULL pointer skips the column.  Names follow the script's columns with the
+ * "session_candidate_" / "aid_candidate_" / "aid_session_candidate_" prefixes shortened.  cumcount_last = 0 and the
+ * *_cumcount_last_mean = NaN stand for the script's nulls (candidate absent from the session / from every session of
+ * the group); *_score_std of a single row is NaN (ddof 1). */
+typedef struct {
+  uint16_t* occurrence_count;          /* events of the session with aid == candidate (:59, :70) */
+  uint16_t* cumcount_last;             /* 1-based position of the last such event (:55-57) */
+  uint16_t* click_occurrence_count;    /* the same per event type (:60, :72-83) */
+  uint16_t* cart_occurrence_count;
+  uint16_t* order_occurrence_count;
+  float* session_score_mean;           /* per session over its candidate rows (:86-97) */
+  float* session_score_std;
+  float* session_score_min;
+  float* session_score_max;
+  float* session_occurrence_count_mean;
+  uint32_t* session_occurrence_count_sum;
+  uint16_t* session_occurrence_count_max;
+  float* session_cumcount_last_mean;
+  uint32_t* session_cumcount_last_sum;
+  uint16_t* session_cumcount_last_max;
+  float* aid_score_mean;               /* per candidate aid over all its rows (:101-111) */
+  float* aid_score_std;
+  float* aid_score_max;
+  float* aid_occurrence_count_mean;
+  uint32_t* aid_occurrence_count_sum;
+  uint16_t* aid_occurrence_count_max;
+  float* aid_cumcount_last_mean;
+  uint32_t* aid_cumcount_last_sum;
+  uint16_t* aid_cumcount_last_max;
+} OttoInteractionFeatures;
+
+/* sessions: the event CSR in file order (ts ascending) of the frame the candidates were generated from; session_ids
+ * [n_sessions] ascending.  Scores are summed in fixed point with 8 fractional bits (exact for vote counts and history
+ * ranks), squares in 128 bits: the features do not depend on the order of the device atomics.  Every candidate session
+ * is expected in the event CSR (the script filters the events BY the candidate sessions, :47); rows of an unknown
+ * session get zero counts and zero session aggregates. */
+int64_t otto_interaction_scratch_bytes(int64_t n_sessions, int64_t n_rows, int32_t n_aids);
+int otto_interaction_features(const OttoSessions* sessions, const int32_t* session_ids, const OttoCandidateFrame* frame,
+                              int32_t n_aids, const OttoInteractionFeatures* out, void* scratch, int64_t scratch_bytes,
+                              void* stream);
 
 /* ---- long-session branch of the standalone model (covisitation/inference.py:142-199, :336-392) ----
  * Sessions with >= n unique aids (flagged by otto_assemble_predictions) are ranked by recency-weighted event

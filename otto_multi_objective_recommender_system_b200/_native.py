@@ -86,6 +86,26 @@ class OttoLabels(C.Structure):
     _fields_ = [("offsets", vp), ("aid", vp)]
 
 
+class OttoCandidateFrame(C.Structure):
+    _fields_ = [("n_rows", i64), ("session", vp), ("candidates", vp), ("candidate_scores", vp)]
+
+
+INTERACTION_COLUMNS = (
+    ("occurrence_count", "uint16"), ("cumcount_last", "uint16"), ("click_occurrence_count", "uint16"),
+    ("cart_occurrence_count", "uint16"), ("order_occurrence_count", "uint16"),
+    ("session_score_mean", "float32"), ("session_score_std", "float32"), ("session_score_min", "float32"),
+    ("session_score_max", "float32"), ("session_occurrence_count_mean", "float32"), ("session_occurrence_count_sum", "uint32"),
+    ("session_occurrence_count_max", "uint16"), ("session_cumcount_last_mean", "float32"), ("session_cumcount_last_sum", "uint32"),
+    ("session_cumcount_last_max", "uint16"),
+    ("aid_score_mean", "float32"), ("aid_score_std", "float32"), ("aid_score_max", "float32"),
+    ("aid_occurrence_count_mean", "float32"), ("aid_occurrence_count_sum", "uint32"), ("aid_occurrence_count_max", "uint16"),
+    ("aid_cumcount_last_mean", "float32"), ("aid_cumcount_last_sum", "uint32"), ("aid_cumcount_last_max", "uint16"))
+
+
+class OttoInteractionFeatures(C.Structure):
+    _fields_ = [(name, vp) for name, _ in INTERACTION_COLUMNS]
+
+
 class OttoCandidates(C.Structure):
     _fields_ = [("aid", vp), ("score", vp), ("len", vp)]
 
@@ -100,6 +120,9 @@ _SIGNATURES = {
     "otto_profile_scatter_ms": (C.c_int, [P(C.c_float)]),
     "otto_frame_is_sorted": (C.c_int, [vp, vp, i64, vp, P(i32), vp]),
     "otto_frame_check": (C.c_int, [vp, vp, i64, i32, vp, P(i64), vp]),
+    "otto_ingest_scratch_bytes": (i64, [i64]),
+    "otto_ingest_scan": (C.c_int, [vp, vp, vp, vp, i64, i32, vp, i64, P(i64), vp]),
+    "otto_ingest_offsets": (C.c_int, [vp, i64, i64, vp, i64, vp, vp, vp, vp]),
     "otto_ingest_desc": (C.c_int, [vp, i64, vp, vp, vp, i64, vp, vp, vp, vp]),
     "otto_covisit_sizes": (C.c_int, [i64, i64, P(OttoCovisitSpec), P(OttoBuildSizes)]),
     "otto_covisit_count_begin": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, vp]),
@@ -136,6 +159,8 @@ _SIGNATURES = {
     "otto_recall_counts": (C.c_int, [vp, i64, i32, P(OttoLabels), i32, vp, vp]),
     "otto_regular_row_counts": (C.c_int, [P(OttoSessions), vp, vp, vp, i32, vp, vp]),
     "otto_regular_rows": (C.c_int, [P(OttoSessions), vp, vp, vp, i32, vp, vp, P(OttoLabels), vp, vp, vp, vp, vp]),
+    "otto_interaction_scratch_bytes": (i64, [i64, i64, i32]),
+    "otto_interaction_features": (C.c_int, [P(OttoSessions), vp, P(OttoCandidateFrame), i32, P(OttoInteractionFeatures), vp, i64, vp]),
     "otto_recency_scratch_bytes": (i64, [i32, i32]),
     "otto_recency_long": (C.c_int, [P(OttoSessions), vp, i32, i32, P(OttoRecencySpec), vp, i64, vp, vp]),
     "otto_recency_scored": (C.c_int, [P(OttoSessions), vp, i32, i32, P(OttoRecencySpec), vp, i64, i32, vp, vp, vp, vp]),

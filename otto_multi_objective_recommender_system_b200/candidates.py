@@ -153,6 +153,8 @@ def _sessions_struct(csr: EventCSR) -> N.OttoSessions:
 def max_session_len(csr: EventCSR) -> int:
     if csr.n_sessions == 0:
         return 1
+    if getattr(csr, "max_len_dev", None) is not None:
+        return max(1, int(csr.max_len_dev.item()))          # computed by otto_ingest_offsets
     return int((csr.offsets[1:] - csr.offsets[:-1]).max().item())
 
 

@@ -109,6 +109,7 @@ class EventCSR:
     type: torch.Tensor          # uint8 [E]
     n_aids: int
     order: str
+    max_len_dev: torch.Tensor | None = None   # int32 [1] longest session (filled by ingest)
 
     @property
     def n_sessions(self) -> int:
@@ -122,8 +123,9 @@ class EventCSR:
         """Sessions [lo, hi) as their own CSR (the multi-GPU shard of a rank)."""
         lo, hi = max(0, lo), min(self.n_sessions, hi)
         e0, e1 = int(self.offsets[lo].item()), int(self.offsets[hi].item())
+        # the whole frame's longest session stays a valid upper bound for the slice
         return EventCSR(self.session_ids[lo:hi], (self.offsets[lo:hi + 1] - e0).contiguous(), self.aid[e0:e1],
-                        self.ts[e0:e1], self.type[e0:e1], self.n_aids, self.order)
+                        self.ts[e0:e1], self.type[e0:e1], self.n_aids, self.order, self.max_len_dev)
 
 
 def ingest(frame: EventFrame, order: str = "desc", device=None) -> EventCSR:
@@ -142,26 +144,37 @@ def ingest(frame: EventFrame, order: str = "desc", device=None) -> EventCSR:
         raise ValueError("frames are limited to 2^31 - 1 events per device")
     with torch.cuda.device(device):
         st = _stream_ptr(device)
-        flag = torch.zeros(2, dtype=torch.int64, device=device)
-        # aid in [0, n_aids), type in {0, 1, 2}: every later kernel indexes with them (raises OttoError otherwise)
-        n_bad = C.c_int64(0)
-        N.check(lib.otto_frame_check(aid.data_ptr(), typ.data_ptr(), E, int(frame.n_aids), flag[1:].data_ptr(), C.byref(n_bad), st))
-        is_sorted = C.c_int32(0)
-        N.check(lib.otto_frame_is_sorted(sess.data_ptr(), ts.data_ptr(), E, flag.data_ptr(), C.byref(is_sorted), st))
-        if not is_sorted.value:
-            # unsorted input: sort by (session, ts), stable, like df.sort_values(['session', 'ts'])
+        need = int(lib.otto_ingest_scratch_bytes(E))
+        scratch = torch.empty(need, dtype=torch.uint8, device=device)
+        info = (C.c_int64 * 3)()
+
+        def scan():
+            # one read of the frame: session starts per tile, (session, ts) order, aid in [0, n_aids) and type in {0, 1, 2}
+            N.check(lib.otto_ingest_scan(sess.data_ptr(), aid.data_ptr(), ts.data_ptr(), typ.data_ptr(), E, int(frame.n_aids),
+                                         scratch.data_ptr(), need, info, st))
+            if info[2]:
+                raise N.OttoError(N.OTTO_EINVAL, f"{info[2]} events have an aid outside [0, {frame.n_aids}) or a type above 2")
+        scan()
+        if not info[1]:
+            # unsorted input: sort by (session, ts), stable, like df.sort_values(['session', 'ts']).  The reference's
+            # frames are written sorted (utilities/split_dataset_writer_parquet.py:17), so this is the rare path and the
+            # only place where a torch op does the work.
             o = torch.sort(ts, stable=True).indices
             o = o[torch.sort(sess[o], stable=True).indices]
-            sess, aid, ts, typ = sess[o], aid[o], ts[o], typ[o]
-        ids, counts = torch.unique_consecutive(sess, return_counts=True)
-        offsets = torch.zeros(ids.numel() + 1, dtype=torch.int32, device=device)
-        offsets[1:] = torch.cumsum(counts, 0).to(torch.int32)
+            sess, aid, ts, typ = sess[o].contiguous(), aid[o].contiguous(), ts[o].contiguous(), typ[o].contiguous()
+            scan()
+        S = int(info[0])
+        ids = torch.empty(S, dtype=torch.int32, device=device)
+        offsets = torch.empty(S + 1, dtype=torch.int32, device=device)
+        max_len = torch.zeros(1, dtype=torch.int32, device=device)
+        N.check(lib.otto_ingest_offsets(sess.data_ptr(), E, S, scratch.data_ptr(), need, ids.data_ptr(), offsets.data_ptr(),
+                                        max_len.data_ptr(), st))
         if order == "asc":
-            return EventCSR(ids, offsets, aid, ts, typ, frame.n_aids, "asc")
+            return EventCSR(ids, offsets, aid, ts, typ, frame.n_aids, "asc", max_len)
         aid_d, ts_d, typ_d = torch.empty_like(aid), torch.empty_like(ts), torch.empty_like(typ)
         N.check(lib.otto_ingest_desc(offsets.data_ptr(), ids.numel(), aid.data_ptr(), ts.data_ptr(), typ.data_ptr(), E,
                                      aid_d.data_ptr(), ts_d.data_ptr(), typ_d.data_ptr(), st))
-    return EventCSR(ids, offsets, aid_d, ts_d, typ_d, frame.n_aids, "desc")
+    return EventCSR(ids, offsets, aid_d, ts_d, typ_d, frame.n_aids, "desc", max_len)
 
 
 @dataclass

@@ -77,6 +77,161 @@ extern "C" int otto_frame_check(const int32_t* aid, const uint8_t* type, int64_t
   return OTTO_OK;
 }
 
+// ---- frame -> session CSR without materialising per-event flags: boundaries are counted per tile, the tile counts
+// scanned, and the second pass recomputes the flags of its tile (replaces torch.unique_consecutive + cumsum of round 1).
+// Pass 1 also checks the (session, ts) order and the event contents, so a frame is read once before it is used.
+constexpr int ING_THREADS = 256, ING_ITEMS = 8, ING_TILE = ING_THREADS * ING_ITEMS;
+
+__global__ void __launch_bounds__(ING_THREADS)
+    ingest_scan_kernel(const int32_t* __restrict__ session, const int32_t* __restrict__ aid, const int32_t* __restrict__ ts,
+                       const uint8_t* __restrict__ type, int64_t n, uint32_t n_aids, uint32_t* __restrict__ tile_count,
+                       unsigned long long* __restrict__ info /* [0] unsorted [1] bad events */) {
+  const int64_t base = (int64_t)blockIdx.x * ING_TILE;
+  uint32_t cnt = 0, unsorted = 0, bad = 0;
+#pragma unroll
+  for (int u = 0; u < ING_ITEMS; ++u) {
+    const int64_t i = base + u * ING_THREADS + threadIdx.x;
+    if (i < n) {
+      const int32_t s1 = session[i];
+      if (i == 0) {
+        cnt += 1;
+      } else {
+        const int32_t s0 = session[i - 1];
+        cnt += s0 != s1;
+        unsorted |= (s0 > s1) || (s0 == s1 && ts[i - 1] > ts[i]);
+      }
+      if (aid) bad += ((uint32_t)aid[i] >= n_aids) || (type[i] > 2);
+    }
+  }
+  __shared__ uint32_t s_cnt[ING_THREADS / 32], s_bad[ING_THREADS / 32];
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(FULL_MASK, cnt, o);
+    bad += __shfl_xor_sync(FULL_MASK, bad, o);
+  }
+  if (__any_sync(FULL_MASK, unsorted) && lane_id() == 0) atomicOr(&info[0], 1ull);
+  if (lane_id() == 0) { s_cnt[threadIdx.x >> 5] = cnt; s_bad[threadIdx.x >> 5] = bad; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t c = 0, b = 0;
+    for (int w = 0; w < ING_THREADS / 32; ++w) { c += s_cnt[w]; b += s_bad[w]; }
+    tile_count[blockIdx.x] = c;
+    if (b) atomicAdd(&info[1], (unsigned long long)b);
+  }
+}
+
+__global__ void __launch_bounds__(ING_THREADS)
+    ingest_offsets_kernel(const int32_t* __restrict__ session, int64_t n, const uint32_t* __restrict__ tile_base,
+                          int32_t* __restrict__ ids, int32_t* __restrict__ offsets, int64_t n_sessions) {
+  // thread t owns ING_ITEMS CONSECUTIVE events of the tile, so its session starts are written in order
+  __shared__ uint32_t s_warp[ING_THREADS / 32 + 1];
+  const int64_t base = (int64_t)blockIdx.x * ING_TILE + (int64_t)threadIdx.x * ING_ITEMS;
+  uint32_t flags = 0, cnt = 0;
+  int32_t prev = base > 0 && base <= n ? session[base - 1] : 0;
+#pragma unroll
+  for (int u = 0; u < ING_ITEMS; ++u) {
+    const int64_t i = base + u;
+    if (i < n) {
+      const int32_t s1 = session[i];
+      if (i == 0 || s1 != prev) { flags |= 1u << u; ++cnt; }
+      prev = s1;
+    }
+  }
+  uint32_t inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(FULL_MASK, inc, o);
+    if ((int)lane_id() >= o) inc += v;
+  }
+  if (lane_id() == 31) s_warp[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int w = 0; w < ING_THREADS / 32; ++w) { const uint32_t v = s_warp[w]; s_warp[w] = run; run += v; }
+  }
+  __syncthreads();
+  uint32_t at = tile_base[blockIdx.x] + s_warp[threadIdx.x >> 5] + inc - cnt;
+#pragma unroll
+  for (int u = 0; u < ING_ITEMS; ++u) {
+    if ((flags >> u) & 1u) {
+      ids[at] = session[base + u];
+      offsets[at] = (int32_t)(base + u);
+      ++at;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) offsets[n_sessions] = (int32_t)n;
+}
+
+__global__ void offsets_max_len_kernel(const int32_t* __restrict__ offsets, int64_t S, int32_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int32_t l = i < S ? offsets[i + 1] - offsets[i] : 0;
+  for (int o = 16; o > 0; o >>= 1) l = max(l, __shfl_xor_sync(FULL_MASK, l, o));
+  if (lane_id() == 0 && l > 0) atomicMax(out, l);
+}
+
+extern "C" int64_t otto_ingest_scratch_bytes(int64_t n_events) {
+  const int64_t tiles = ceil_div(n_events > 0 ? n_events : 1, ING_TILE);
+  return align_up((tiles + 2) * 4, 256) + scan_scratch_elems(tiles + 1) * 4 + 512;
+}
+
+// pass 1.  info_host: [0] n_sessions, [1] sorted by (session, ts) (1 / 0), [2] events with an aid outside [0, n_aids)
+// or a type above 2 (aid == NULL skips the content check).  Synchronises.
+extern "C" int otto_ingest_scan(const int32_t* session, const int32_t* aid, const int32_t* ts, const uint8_t* type,
+                                int64_t n_events, int32_t n_aids, void* scratch, int64_t scratch_bytes, int64_t* info_host,
+                                void* stream) {
+  if (!session || !ts || !info_host || n_events < 0 || n_events >= (1ll << 31) || (aid && (!type || n_aids <= 0))) {
+    otto_set_error("bad argument");
+    return OTTO_EINVAL;
+  }
+  if (!scratch || scratch_bytes < otto_ingest_scratch_bytes(n_events)) { otto_set_error("ingest scratch too small"); return OTTO_ENOSPC; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t tiles = ceil_div(n_events > 0 ? n_events : 1, ING_TILE);
+  char* sc = (char*)scratch;
+  uint32_t* tile_count = (uint32_t*)sc;
+  uint32_t* scan_sc = (uint32_t*)(sc + align_up((tiles + 2) * 4, 256));
+  unsigned long long* info = (unsigned long long*)(scan_sc + scan_scratch_elems(tiles + 1));
+  info = (unsigned long long*)(((uintptr_t)info + 7) & ~(uintptr_t)7);
+  CUDA_TRY(cudaMemsetAsync(info, 0, 16, st));
+  CUDA_TRY(cudaMemsetAsync(tile_count, 0, (tiles + 2) * 4, st));
+  if (n_events > 0) {
+    ingest_scan_kernel<<<(unsigned)tiles, ING_THREADS, 0, st>>>(session, aid, ts, type, n_events, (uint32_t)n_aids, tile_count, info);
+    LAUNCH_CHECK();
+  }
+  int rc = exclusive_scan<uint32_t, uint32_t>(tile_count, tiles, tile_count, scan_sc, st);
+  if (rc) return rc;
+  unsigned long long h[2];
+  uint32_t total = 0;
+  CUDA_TRY(cudaMemcpyAsync(h, info, 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&total, tile_count + tiles, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  info_host[0] = n_events > 0 ? (int64_t)total : 0;
+  info_host[1] = h[0] ? 0 : 1;
+  info_host[2] = (int64_t)h[1];
+  return OTTO_OK;
+}
+
+// pass 2 (same scratch, untouched since otto_ingest_scan of the same session column): session ids [n_sessions],
+// offsets int32 [n_sessions + 1], *max_len_dev = longest session
+extern "C" int otto_ingest_offsets(const int32_t* session, int64_t n_events, int64_t n_sessions, void* scratch,
+                                   int64_t scratch_bytes, int32_t* session_ids, int32_t* offsets, int32_t* max_len_dev,
+                                   void* stream) {
+  if (!session || !session_ids || !offsets || n_events < 0 || n_sessions < 0) { otto_set_error("bad argument"); return OTTO_EINVAL; }
+  if (!scratch || scratch_bytes < otto_ingest_scratch_bytes(n_events)) { otto_set_error("ingest scratch too small"); return OTTO_ENOSPC; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t tiles = ceil_div(n_events > 0 ? n_events : 1, ING_TILE);
+  if (max_len_dev) CUDA_TRY(cudaMemsetAsync(max_len_dev, 0, 4, st));
+  if (n_events == 0) {
+    CUDA_TRY(cudaMemsetAsync(offsets, 0, 4, st));
+    return OTTO_OK;
+  }
+  ingest_offsets_kernel<<<(unsigned)tiles, ING_THREADS, 0, st>>>(session, n_events, (const uint32_t*)scratch, session_ids, offsets, n_sessions);
+  LAUNCH_CHECK();
+  if (max_len_dev && n_sessions > 0) {
+    offsets_max_len_kernel<<<(unsigned)ceil_div(n_sessions, 256), 256, 0, st>>>(offsets, n_sessions, max_len_dev);
+    LAUNCH_CHECK();
+  }
+  return OTTO_OK;
+}
+
 // One warp per session: reverse the ascending session so that ts is descending, keeping runs of equal
 // ts in their original order (what the stable ts-descending sort of builder step 2 produces).
 __global__ void __launch_bounds__(256)

@@ -1258,19 +1258,22 @@ extern "C" int otto_candidates(const OttoSessions* sessions, int32_t max_session
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, k0, 128, sm0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k1, 256, sm1);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k2, 128, sm2);
-    k1<<<n_sm * (occ1 > 0 ? occ1 : 1), 256, sm1, g_cside[0]>>>(p, with_ent);
-    LAUNCH_CHECK();
-    candidates_block_kernel<2, 256><<<GLOBAL_BLOCKS, 256, 0, g_cside[1]>>>(p, global_lcap(max_session_len), global_mcap(max_session_len, p.max_k_sum));
-    LAUNCH_CHECK();
-    k2<<<n_sm * (occ2 > 0 ? occ2 : 1), 128, sm2, g_cside[2]>>>(p, with_ent);
-    LAUNCH_CHECK();
-    k0<<<n_sm * (occ0 > 0 ? occ0 : 1), 128, sm0, g_cside[3]>>>(p, with_ent);
-    LAUNCH_CHECK();
+    // launch order = dispatch priority: the two throughput-bound tiers (80 % and 16 % of the sessions) first, the
+    // latency-bound long-session tiers fill the SMs as those drain (r02: with the long-session tiers first their
+    // 136 KB blocks kept the short-session blocks off the SMs and the whole call took the sum of the tiers)
     const size_t smem0 = CAND_WARPS * C0::bytes(with_ent != 0);
     CUDA_TRY(cudaFuncSetAttribute(candidates_fast_kernel<9, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
     int64_t blocks = ceil_div(S, CAND_WARPS);
     if (blocks > (int64_t)n_sm * 32) blocks = (int64_t)n_sm * 32;
     candidates_fast_kernel<9, 8, 0><<<(unsigned)blocks, CAND_WARPS * 32, smem0, st>>>(p, lmax0, lmax1, with_ent);
+    LAUNCH_CHECK();
+    k0<<<n_sm * (occ0 > 0 ? occ0 : 1), 128, sm0, g_cside[3]>>>(p, with_ent);
+    LAUNCH_CHECK();
+    k2<<<n_sm * (occ2 > 0 ? occ2 : 1), 128, sm2, g_cside[2]>>>(p, with_ent);
+    LAUNCH_CHECK();
+    k1<<<n_sm * (occ1 > 0 ? occ1 : 1), 256, sm1, g_cside[0]>>>(p, with_ent);
+    LAUNCH_CHECK();
+    candidates_block_kernel<2, 256><<<GLOBAL_BLOCKS, 256, 0, g_cside[1]>>>(p, global_lcap(max_session_len), global_mcap(max_session_len, p.max_k_sum));
     LAUNCH_CHECK();
     for (int i = 0; i < 4; ++i) {
       CUDA_TRY(cudaEventRecord(g_cjoin[i], g_cside[i]));

@@ -33,7 +33,8 @@ def test_library_exports_every_declared_function(native_lib):
 def test_struct_layouts_match_the_c_compiler(native_lib, tmp_path):
     from otto_multi_objective_recommender_system_b200 import _native as N
     structs = ["OttoEvents", "OttoCovisitSpec", "OttoBuildSizes", "OttoBuildStats", "OttoPairSegment", "OttoTopK", "OttoSessions",
-               "OttoCandidateSpec", "OttoCandidates", "OttoRecencySpec", "OttoOwnerPlan"]
+               "OttoCandidateSpec", "OttoCandidates", "OttoRecencySpec", "OttoOwnerPlan", "OttoLabels", "OttoCandidateFrame",
+               "OttoInteractionFeatures"]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
     for s in structs:
         lines.append(f'  printf("{s} %zu\\n", sizeof({s}));')
