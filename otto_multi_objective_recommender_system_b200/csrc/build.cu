@@ -1280,7 +1280,7 @@ static int launch_reduce(const ReduceParams& p, int n_sm, cudaStream_t st) {
     if ((rc = launch_tier<TIME, 1>(p, n_sm, st))) return rc;
     PROF_MARK(4);
   }
-  merge_split_rows_kernel<<<n_sm * 4, 256, 0, st>>>(p);
+  merge_split_rows_kernel<<<n_sm * 8, MERGE_WARPS * 32, 0, st>>>(p);
   LAUNCH_CHECK();
   PROF_MARK(5);
   g_prof_valid = g_profile != 0;
