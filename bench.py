@@ -545,10 +545,11 @@ def run_b200(args):
         phase_ms = {p: statistics.mean(m[i].elapsed_time(m[i + 1]) for m in marks) for i, p in enumerate(phases)}
         # per-kernel view: the count / scatter phases are one hot kernel each (plus scans of a few us); the reduce
         # phase is five launches that the library brackets with CUDA events on this stream (otto_profile_reduce_ms)
-        tiers = ["reduce_classify + reduce_warp_kernel<512 slots> (bins <= 256 records)",
-                 "reduce_block_kernel<512 threads, 8192 slots> (bins > 3072)",
-                 "reduce_block_kernel<256 threads, 4096 slots> (bins <= 3072)",
-                 "reduce_block_kernel<128 threads, 2048 slots> (bins <= 1024)", "merge_split_rows_kernel"]
+        tiers = ["reduce_classify + otable_warp_kernel (bins <= 384 records)",
+                 "otable_block_kernel<512 threads> (bins <= 6144)",
+                 "otable_block_kernel<256 threads> (bins <= 3072)",
+                 "otable_block_kernel<128 threads> (bins <= 1536)",
+                 "reduce_block_kernel<hash table> (hand-overs, bins > 8192) + merge_split_rows_kernel"]
         tier_of = [0, 3, 2, 1]       # launch order (warp, 512, 256, 128) -> index into stats.tier_records
         red_ms = [statistics.mean(r[i] for r in reduce_ms) for i in range(5)] if reduce_ms else [0.0] * 5
         tr = stats.get("tier_records", [0, 0, 0, 0])

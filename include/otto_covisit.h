@@ -93,7 +93,7 @@ typedef struct {
   int64_t distinct;          /* D: distinct (aid_x, aid_y) accumulated by this rank (after reduce) */
   int64_t pair_checksum;     /* sum of counts over all accumulated entries (== pairs received) */
   int64_t table_overflow;    /* != 0: a hash table overflowed (result invalid) */
-  int64_t tier_records[4];   /* records accumulated by the warp / 128- / 256- / 512-thread reduce kernels */
+  int64_t tier_records[4];   /* records accumulated by the warp / 128- / 256- / 512-thread (and hash-table) reduce kernels */
   int64_t hot_pairs;         /* pairs of hot (split) rows: they pass through a staging area behind the P final records,
                                 so the record buffer must hold pairs + hot_pairs records */
   /* otto_covisit_count_finish_owned only (identical on every rank: the layout of all owners is computed everywhere) */

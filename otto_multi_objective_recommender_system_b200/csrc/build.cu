@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "pairgen.cuh"
 #include "reduce.cuh"
+#include "otable.cuh"
 #include "scan.cuh"
 
 static thread_local char g_error[512] = "";
@@ -293,10 +294,11 @@ struct Layout {
 };
 
 // A row whose pair count (over all ranks) exceeds split_ub is "hot": it is split into aid_y-hash sub-bins of
-// about split_ub / 4 records (2048 by default), which the 256-thread reduce kernel - the most efficient tier -
-// takes in one pass; sub-bins of ~4096 records all landed in the 512-thread kernel and doubled its time.
-static int32_t effective_split_ub(const OttoCovisitSpec* spec) { return spec->split_ub > 0 ? spec->split_ub : 8192; }
-static int32_t sub_bin_target(const OttoCovisitSpec* spec) { return effective_split_ub(spec) >= 4 ? effective_split_ub(spec) / 4 : 1; }
+// about split_ub / 3 records (2048 by default), which the 256-thread owner-table kernel takes (bins <= 3072).  The
+// default split_ub is the largest bin the owner-table tiers take (6144 records), so that the hash-table kernel of
+// reduce.cuh only ever sees hand-overs (round 1 / v5: 8192 and split_ub / 4).
+static int32_t effective_split_ub(const OttoCovisitSpec* spec) { return spec->split_ub > 0 ? spec->split_ub : 6144; }
+static int32_t sub_bin_target(const OttoCovisitSpec* spec) { return effective_split_ub(spec) >= 3 ? effective_split_ub(spec) / 3 : 1; }
 constexpr uint32_t MAX_SUB_BINS = 4096;   // shared-memory cursors of the partition kernels
 
 static int check_spec(const OttoCovisitSpec* spec) {
@@ -1131,7 +1133,7 @@ extern "C" int otto_covisit_partition(const OttoEvents* ev, const OttoCovisitSpe
 // ------------------------------------------------------------------ reduce
 
 struct ScratchLayout {
-  int64_t p_key, p_sum, p_cnt, p_len, list[4], counters, stats, total;
+  int64_t p_key, p_sum, p_cnt, p_len, list[N_TIERS], counters, stats, total;
 };
 
 static ScratchLayout make_scratch(int k, int64_t n_bins, int64_t n_aids_range) {
@@ -1145,7 +1147,7 @@ static ScratchLayout make_scratch(int k, int64_t n_bins, int64_t n_aids_range) {
   s.p_sum = take(slots * k * 8);
   s.p_cnt = take(slots * k * 4);
   s.p_len = take(slots * 4);
-  for (int t = 0; t < 4; ++t) s.list[t] = take((n_bins + 1) * 4);
+  for (int t = 0; t < N_TIERS; ++t) s.list[t] = take((n_bins + 1) * 4);
   s.counters = take(64);
   s.stats = take(64);
   s.total = o;
@@ -1220,25 +1222,30 @@ template <bool TIME, int TIER>
 static int launch_tier(const ReduceParams& p, int n_sm, cudaStream_t st) {
   int rc;
   if (TIER == 0) {
-    auto kern = reduce_warp_kernel<TIME, 9, 256, 0>;
-    constexpr size_t smem = (size_t)WARP_TIER_WARPS * warp_tier_bytes<TIME, 9, 256>();
-    if ((rc = set_smem(kern, smem))) return rc;
-    static const int occ = occupancy_blocks((const void*)kern, WARP_TIER_WARPS * 32, smem);
-    kern<<<n_sm * occ, WARP_TIER_WARPS * 32, smem, st>>>(p);
+    auto kern = otable_warp_kernel<TIME>;
+    static const int occ = occupancy_blocks((const void*)kern, OTW_WARPS * 32, 0);
+    kern<<<n_sm * occ, OTW_WARPS * 32, 0, st>>>(p);
   } else if (TIER == 1) {
-    auto kern = reduce_block_kernel<TIME, 128, 11, 1, false>;
-    constexpr size_t smem = reduce_block_smem<TIME, 128, 11, false>();
+    auto kern = otable_block_kernel<TIME, 128, 11, 1>;
+    constexpr size_t smem = otable_block_smem<TIME, 11>();
     if ((rc = set_smem(kern, smem))) return rc;
     static const int occ = occupancy_blocks((const void*)kern, 128, smem);
     kern<<<n_sm * occ, 128, smem, st>>>(p);
   } else if (TIER == 2) {
-    auto kern = reduce_block_kernel<TIME, 256, 12, 2, false>;
-    constexpr size_t smem = reduce_block_smem<TIME, 256, 12, false>();
+    auto kern = otable_block_kernel<TIME, 256, 12, 2>;
+    constexpr size_t smem = otable_block_smem<TIME, 12>();
     if ((rc = set_smem(kern, smem))) return rc;
     static const int occ = occupancy_blocks((const void*)kern, 256, smem);
     kern<<<n_sm * occ, 256, smem, st>>>(p);
+  } else if (TIER == 3) {
+    auto kern = otable_block_kernel<TIME, 512, 13, 3>;
+    constexpr size_t smem = otable_block_smem<TIME, 13>();
+    if ((rc = set_smem(kern, smem))) return rc;
+    static const int occ = occupancy_blocks((const void*)kern, 512, smem);
+    kern<<<n_sm * occ, 512, smem, st>>>(p);
   } else {
-    auto kern = reduce_block_kernel<TIME, 512, 13, 3, true>;
+    // bins beyond 6144 records and bins handed over by the owner-table tiers: the v5 hash-table kernel (multi-pass)
+    auto kern = reduce_block_kernel<TIME, 512, 13, 4, true>;
     constexpr size_t smem = reduce_block_smem<TIME, 512, 13, true>();
     if ((rc = set_smem(kern, smem))) return rc;
     static const int occ = occupancy_blocks((const void*)kern, 512, smem);
@@ -1248,7 +1255,8 @@ static int launch_tier(const ReduceParams& p, int n_sm, cudaStream_t st) {
   return OTTO_OK;
 }
 
-// profile slots: [0] classify + warp tier 0, [1] block tier 3, [2] block tier 2, [3] block tier 1, [4] split-row merge
+// profile slots: [0] classify + warp tier 0, [1] block tier 3, [2] block tier 2, [3] block tier 1, [4] hash-table tier
+// (hand-overs) + split-row merge
 template <bool TIME>
 static int launch_reduce(const ReduceParams& p, int n_sm, cudaStream_t st) {
   int rc;
@@ -1280,6 +1288,8 @@ static int launch_reduce(const ReduceParams& p, int n_sm, cudaStream_t st) {
     if ((rc = launch_tier<TIME, 1>(p, n_sm, st))) return rc;
     PROF_MARK(4);
   }
+  // after every owner-table tier: their hand-overs join the oversized bins on list 4
+  if ((rc = launch_tier<TIME, 4>(p, n_sm, st))) return rc;
   merge_split_rows_kernel<<<n_sm * 8, MERGE_WARPS * 32, 0, st>>>(p);
   LAUNCH_CHECK();
   PROF_MARK(5);
@@ -1336,7 +1346,7 @@ extern "C" int otto_covisit_reduce(const OttoCovisitSpec* spec, const uint32_t* 
   p.p_sum = (uint64_t*)(sc + SL.p_sum);
   p.p_cnt = (uint32_t*)(sc + SL.p_cnt);
   p.p_len = (int32_t*)(sc + SL.p_len);
-  for (int t = 0; t < 4; ++t) p.list[t] = (uint32_t*)(sc + SL.list[t]);
+  for (int t = 0; t < N_TIERS; ++t) p.list[t] = (uint32_t*)(sc + SL.list[t]);
   p.counters = (uint32_t*)(sc + SL.counters);
   p.stats = (unsigned long long*)(sc + SL.stats);
   CUDA_TRY(cudaMemsetAsync(p.counters, 0, 64, st));

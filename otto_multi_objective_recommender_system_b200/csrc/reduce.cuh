@@ -57,13 +57,14 @@ struct ReduceParams {
   uint64_t* p_sum;
   uint32_t* p_cnt;
   int32_t* p_len;
-  uint32_t* list[4];         // work list of every tier: bin - bin_lo
-  uint32_t* counters;        // [0..3] items per tier, [4..7] next item per tier
+  uint32_t* list[5];         // work list of every tier: bin - bin_lo; [4] = bins the owner-table tiers hand to the hash-table kernel
+  uint32_t* counters;        // [0..4] items per tier, [8..12] next item per tier
   unsigned long long* stats; // [0] distinct  [1] checksum  [2] overflow  [3] slow-path selections  [4..7] records per tier
 };
 
 constexpr uint32_t TINY_MAX = 32;     // records: one step of one warp, no table at all
-constexpr uint32_t TIER0_MAX = 256, TIER1_MAX = 1024, TIER2_MAX = 3072;   // records per bin of tiers 0, 1, 2; tier 3 takes the rest
+constexpr uint32_t TIER0_MAX = 384, TIER1_MAX = 1536, TIER2_MAX = 3072, TIER3_MAX = 6144;   // records per bin of tiers 0..3; tier 4 takes the rest
+constexpr int N_TIERS = 5, NEXT_ITEM = 8;   // counters[NEXT_ITEM + t] = next work item of tier t
 constexpr int N_CAND = 64;            // candidates a fast selection may produce
 constexpr int N_CAND_BUF = N_CAND + OTTO_MAX_K;   // block tiers: + the best list carried between hash passes
 constexpr uint32_t KEY_NONE = 0u;     // table keys are aid_y + 1
@@ -81,11 +82,11 @@ __global__ void __launch_bounds__(256) reduce_classify_kernel(const ReduceParams
   int tier = -1;
   if (b < p.bin_hi) {
     const uint64_t n = p.offsets[b - p.bin_lo + 1] - p.offsets[b - p.bin_lo];
-    tier = n <= TIER0_MAX ? 0 : n <= TIER1_MAX ? 1 : n <= TIER2_MAX ? 2 : 3;
+    tier = n <= TIER0_MAX ? 0 : n <= TIER1_MAX ? 1 : n <= TIER2_MAX ? 2 : n <= TIER3_MAX ? 3 : 4;
   }
   const uint32_t lt = lanemask_lt();
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < N_TIERS; ++t) {
     const uint32_t m = __ballot_sync(FULL_MASK, tier == t);
     if (m == 0) continue;
     const int leader = __ffs(m) - 1;
@@ -416,15 +417,6 @@ struct BinStats {
   bool overflow = false;
 };
 
-// =====================================================================================================
-// warp tiers: one warp per bin, no block-level synchronisation
-// =====================================================================================================
-constexpr int WARP_TIER_WARPS = 4;
-
-template <bool TIME, int LOG, int NMAX>
-__host__ __device__ constexpr uint32_t warp_tier_bytes() {   // per warp: cand key / sum (u64) | table | cand cnt | occ (u16)
-  return N_CAND * 16 + Table<TIME, LOG>::BYTES + N_CAND * 4 + NMAX * 2;
-}
 
 // the whole bin is one step: fold duplicates with match_any, rank the group leaders
 template <bool TIME>
@@ -456,168 +448,6 @@ __device__ __forceinline__ void tiny_bin(const ReduceParams& p, const BinOut& o,
   emit_finish(p, o, nl < p.k ? nl : p.k);
   if (lane == 0) st.occ += nl;
   if (lead) st.pay += TIME ? (uint64_t)cnt : sum;
-}
-
-template <bool TIME, int LOG, int NMAX, int TIER>
-__global__ void __launch_bounds__(WARP_TIER_WARPS * 32) reduce_warp_kernel(const ReduceParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, lt = lanemask_lt();
-  unsigned char* base = smem_raw + warp * warp_tier_bytes<TIME, LOG, NMAX>();
-  Cands c;
-  c.key = (uint64_t*)base;
-  c.sum = c.key + N_CAND;
-  Table<TIME, LOG> t;
-  unsigned char* tb = (unsigned char*)(c.sum + N_CAND);
-  c.cnt = (uint32_t*)(tb + Table<TIME, LOG>::BYTES);
-  t.carve(tb, c.cnt + N_CAND);
-  t.clear_all(lane, 32);
-  __syncwarp();
-  constexpr int EPT = NMAX / 32;   // entries per lane: d <= n <= NMAX
-
-  BinStats st;
-  const uint32_t n_items = p.counters[TIER];
-  const uint32_t* list = p.list[TIER];
-  // A warp takes 32 consecutive list items at a time (one atomic per 32 bins): lane l walks the dependent metadata
-  // loads of item c0 + l (list -> record offsets -> bin -> aid_x -> first bin of the row), so their latency is paid
-  // once per 32 bins.
-  while (true) {
-    uint32_t c0 = 0;
-    if (lane == 0) c0 = atomicAdd(&p.counters[4 + TIER], 32u);
-    c0 = __shfl_sync(FULL_MASK, c0, 0);
-    if (c0 >= n_items) break;
-    const bool inb = c0 + lane < n_items;
-    uint32_t n_l = 0;
-    BinOut o_l;
-    o_l.whole = true;
-    o_l.row = 0;
-    o_l.x = 0;
-    const uint2* run_l = nullptr;
-    if (inb) {
-      const int64_t bl = p.bin_lo + list[c0 + lane];
-      const uint64_t beg = p.offsets[bl - p.bin_lo], end = p.offsets[bl - p.bin_lo + 1];
-      n_l = (uint32_t)(end - beg);
-      o_l = bin_out(p, bl);
-      run_l = p.records + (beg - p.offsets[0]);
-    }
-    const int n_here = min(32u, n_items - c0);
-    for (int srcl = 0; srcl < n_here; ++srcl) {
-      const uint32_t n = __shfl_sync(FULL_MASK, n_l, srcl);
-      BinOut o;
-      o.whole = __shfl_sync(FULL_MASK, (int)o_l.whole, srcl) != 0;
-      o.row = (int64_t)shfl_u64((uint64_t)o_l.row, srcl);
-      o.x = __shfl_sync(FULL_MASK, o_l.x, srcl);
-      const uint2* run = (const uint2*)shfl_u64((uint64_t)(uintptr_t)run_l, srcl);
-      if (n == 0) {
-        emit_finish(p, o, 0);
-        continue;
-      }
-      if (lane == 0) st.rec += n;
-      if (n <= TINY_MAX) {
-        tiny_bin<TIME>(p, o, run, n, st);
-        continue;
-      }
-      const KeyCfg cfg = make_cfg<TIME>(p, n);
-      bool slow = false;
-      while (true) {
-        // ---- insert: two records per lane and step, the next two in flight while the current ones are inserted
-        uint32_t d = 0;
-        {
-          bool h0 = lane < n, h1 = 32 + lane < n;
-          uint2 q0 = make_uint2(0, 0), q1 = make_uint2(0, 0);
-          if (h0) q0 = ld_stream_u2(run + lane);
-          if (h1) q1 = ld_stream_u2(run + 32 + lane);
-          for (uint32_t i0 = 0; i0 < n; i0 += 64) {
-            const bool a0 = h0, a1 = h1;
-            const uint2 r0 = q0, r1 = q1;
-            h0 = i0 + 64 + lane < n;
-            h1 = i0 + 96 + lane < n;
-            if (h0) q0 = ld_stream_u2(run + i0 + 64 + lane);
-            if (h1) q1 = ld_stream_u2(run + i0 + 96 + lane);
-            if (!t.template insert2<true>(a0, r0.x, r0.y, a1, r1.x, r1.y, d, 0u)) st.overflow = true;
-          }
-        }
-        __syncwarp();
-        if (slow) {   // exact selection straight from the table (candidate list overflowed on the first attempt)
-          for (uint32_t i = lane; i < d; i += 32) st.pay += TIME ? (uint64_t)t.count(t.occ(i)) : t.sum(t.occ(i));
-          const int n_c = warp_select_slow<TIME, LOG>(t, 0, d, p.k, p.w_scale, c, 0);
-          const int found = warp_rank_emit(c, n_c, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) { emit_entry(p, o, r, kk, cnt, sum); });
-          emit_finish(p, o, found);
-          for (uint32_t i = lane; i < d; i += 32) t.clear_slot(t.occ(i));
-          if (lane == 0) { st.occ += d; ++st.slow; }
-          __syncwarp();
-          break;
-        }
-        // ---- sweep 1: 32-bit keys into registers, lane maxima -> threshold
-        uint32_t k32[EPT];
-        uint32_t best = 0, pay = 0;
-#pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-          k32[j] = 0;
-          if ((uint32_t)j * 32 >= d) break;
-          const uint32_t i = j * 32 + lane;
-          if (i < d) {
-            const uint32_t h = t.occ(i);
-            const uint2 pl = t.payload(h);
-            k32[j] = key32<TIME>(cfg, TIME ? 0u : t.key(h), pl.x, pl.y) + 1u;   // + 1: 0 means "no entry" (saturation is harmless)
-            if (k32[j] == 0) k32[j] = 0xffffffffu;
-            pay += TIME ? (pl.y & 0xffffffu) + 1u : pl.x;
-            best = max(best, k32[j]);
-          }
-        }
-        uint32_t thr = 0;
-        if (d > 32) thr = cand_threshold<TIME>(warp_kth_largest32(best, p.k));
-        // ---- sweep 2: candidates read their payload again; every entry resets its slot
-        uint32_t n_c = 0;
-#pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-          if ((uint32_t)j * 32 >= d) break;
-          const uint32_t i = j * 32 + lane;
-          const bool mine = i < d;
-          const bool q = mine && k32[j] >= thr;
-          const uint32_t m = __ballot_sync(FULL_MASK, q);
-          const uint32_t h = mine ? t.occ(i) : 0u;
-          if (q) {
-            const uint32_t at = n_c + __popc(m & lt);
-            if (at < (uint32_t)N_CAND) {
-              const uint2 pl = t.payload(h);
-              const uint32_t cnt = t.count_of(pl);
-              const uint64_t sum = t.sum_of(pl);
-              c.key[at] = float_key(TIME, t.key(h) - 1u, cnt, sum, p.w_scale);
-              c.sum[at] = sum;
-              c.cnt[at] = cnt;
-            }
-          }
-          n_c += __popc(m);
-          if (mine) t.clear_slot(h);
-        }
-        __syncwarp();
-        if (n_c > (uint32_t)N_CAND) {   // adversarial ties: insert again and select exactly
-          slow = true;
-          continue;
-        }
-        const int found = warp_rank_emit(c, (int)n_c, p.k, [&](int r, uint64_t kk, uint32_t cnt, uint64_t sum) { emit_entry(p, o, r, kk, cnt, sum); });
-        emit_finish(p, o, found);
-        st.pay += pay;
-        if (lane == 0) st.occ += d;
-        __syncwarp();
-        break;
-      }
-    }
-  }
-  // one stats update per warp
-  for (int off = 16; off > 0; off >>= 1) {
-    st.occ += shfl_u64(st.occ, lane ^ off);
-    st.slow += __shfl_xor_sync(FULL_MASK, st.slow, off);
-    st.pay += shfl_u64(st.pay, lane ^ off);
-    st.rec += shfl_u64(st.rec, lane ^ off);
-  }
-  if (lane == 0 && (st.occ || st.pay)) {
-    atomicAdd(&p.stats[0], (unsigned long long)st.occ);
-    atomicAdd(&p.stats[1], (unsigned long long)st.pay);
-    if (st.slow) atomicAdd(&p.stats[3], (unsigned long long)st.slow);
-  }
-  if (lane == 0 && st.rec) atomicAdd(&p.stats[4 + TIER], (unsigned long long)st.rec);
-  if (st.overflow) atomicOr(&p.stats[2], 1ull);
 }
 
 // =====================================================================================================
@@ -673,6 +503,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 7 : THREADS == 256 ?
 
   const uint32_t* list = p.list[TIER];
   const uint32_t n_items = p.counters[TIER];
+  if (n_items == 0) return;   // the usual case of the hand-over tier: nothing to clear, nothing to do
   BinStats st;
   t.clear_all(threadIdx.x, THREADS);
   if (threadIdx.x < 2) {
@@ -685,7 +516,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 7 : THREADS == 256 ?
   // fetched by BATCH lanes of warp 1 into buffer `buf`; one chain of round trips per batch
   auto fetch_batch = [&](int buf) {   // called by warp 1 only
     uint32_t first = 0;
-    if (lane == 0) first = atomicAdd(&p.counters[4 + TIER], (uint32_t)BATCH);
+    if (lane == 0) first = atomicAdd(&p.counters[NEXT_ITEM + TIER], (uint32_t)BATCH);
     first = __shfl_sync(FULL_MASK, first, 0);
     if (lane == 0) s_first[buf] = first;
     if (lane < BATCH && first + lane < n_items) {
@@ -947,7 +778,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? 7 : THREADS == 256 ?
     atomicAdd(&p.stats[1], (unsigned long long)st.pay);
     if (st.slow) atomicAdd(&p.stats[3], (unsigned long long)st.slow);
   }
-  if (threadIdx.x == 0 && st.rec) atomicAdd(&p.stats[4 + TIER], (unsigned long long)st.rec);
+  if (threadIdx.x == 0 && st.rec) atomicAdd(&p.stats[4 + (TIER < 3 ? TIER : 3)], (unsigned long long)st.rec);
   if (st.overflow) atomicOr(&p.stats[2], 1ull);
 }
 

@@ -132,6 +132,30 @@ def test_hot_rows_large_bins_multipass(cv, variant):
     check_against_oracle(cv, frame, spec, f"{variant} hot rows")
 
 
+@pytest.mark.parametrize("variant", ["CLICKS", "CARTS_ORDERS"])
+def test_tied_entries_hand_over_to_the_hash_table_kernel(cv, variant):
+    """More than 64 entries tie around the K-th weight of a row (one aid_x seen with hundreds of partners, every
+    partner once, every event at one timestamp): the owner-table tiers cannot hold the candidates and hand the bin
+    to the hash-table kernel, whose exact K-round selection breaks the ties by aid_y."""
+    rows, ts = [], 1660000000
+    partner = 10
+    for s in range(4):            # aid 0: 4 x 29 = 116 partners -> warp tier (<= 384 records)
+        rows += [(s, 0, ts, 0)] + [(s, partner + j, ts, 0) for j in range(29)]
+        partner += 29
+    for s in range(4, 30):        # aid 1: 26 x 29 = 754 partners -> 128-thread tier
+        rows += [(s, 1, ts, 0)] + [(s, partner + j, ts, 0) for j in range(29)]
+        partner += 29
+    df = pd.DataFrame(rows, columns=["session", "aid", "ts", "type"])
+    frame = frame_from_df(df, partner + 5)
+    got, stats = check_against_oracle(cv, frame, getattr(cv, variant), f"{variant} tied entries")
+    if variant == "CLICKS":
+        # every bin is far below 6144 records, so records counted by the last tier were handed over (type / unit
+        # weights carry aid_y bits in the 32-bit selection key: their ties never overflow the candidate list)
+        assert stats["tier_records"][3] >= 116 + 754, stats["tier_records"]
+    top0 = got[got["aid_x"] == 0]["aid_y"].tolist()
+    assert top0 == list(range(10, 10 + getattr(cv, variant).k)), top0
+
+
 def test_edge_sessions(cv):
     """Lengths 1, 2, 30, 31, 32, 33, 500; ts ties across the tail boundary; window edge |dt| == W."""
     rng = np.random.default_rng(0)
