@@ -72,7 +72,7 @@ typedef struct {
   int32_t k;                 /* rows kept per aid_x (15 / 20) */
   int32_t ts_min;            /* OTTO_WEIGHT_TIME constants: 1659304800, 1662328791 */
   int32_t ts_max;
-  int32_t split_ub;          /* rows with more pairs than this are split into aid_y-hash sub-bins of ~split_ub / 2; 0 = default */
+  int32_t split_ub;          /* rows with more pairs than this are split into aid_y-hash sub-bins of ~split_ub / 3; 0 = default (6144) */
   int64_t global_events;     /* multi-GPU: events of ALL ranks (bins are formed from the all-reduced bounds, so the
                                 bin arrays must be sized for the global frame); 0 = this rank's frame is the whole frame */
 } OttoCovisitSpec;
@@ -127,9 +127,11 @@ uint64_t otto_launch_count(void);
 
 /* Measurement aid for bench.py: with profiling on, otto_covisit_reduce brackets each of its kernels with CUDA
  * events on the caller's stream; otto_profile_reduce_ms synchronises the last one and returns the five
- * durations of the most recent call (classify + warp tier 0 [bins <= 256 records], block tier 3 [> 3072], block tier 2
- * [<= 3072], warp tier 1 [<= 1024], merge_split_rows) in milliseconds.  Profiled calls run the block kernels back to back on the caller's stream; unprofiled calls run
- * them concurrently on two internal side streams (forked from and joined to the caller's stream). */
+ * durations of the most recent call in milliseconds: classify + owner-table warp tier [bins <= 384 records],
+ * 512-thread tier [<= 6144], 256-thread tier [<= 3072], 128-thread tier [<= 1536], hash-table kernel [hand-overs
+ * and larger bins] + merge_split_rows.  Profiled calls run the tier kernels back to back on the caller's stream;
+ * unprofiled calls run them concurrently on three internal side streams (forked from and joined to the caller's
+ * stream). */
 int otto_profile_enable(int on);
 int otto_profile_reduce_ms(float* ms_host /* [5] */);
 /* Same for otto_covisit_scatter: pairgen scatter kernel; bin counts + partition count + offset scan; partition move. */

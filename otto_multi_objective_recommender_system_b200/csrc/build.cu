@@ -276,7 +276,7 @@ struct EventLimits {
   uint32_t n_aids;
   int32_t ts_lo, ts_hi;   // inclusive range (INT32_MIN .. INT32_MAX outside time mode)
 };
-constexpr int STAT_BAD_EVENTS = 6;
+constexpr int STAT_BAD_EVENTS = 6, STAT_MAX_BIN = 7;
 
 __device__ __forceinline__ void check_event(const EventLimits& lim, int32_t& a, uint32_t& ty, int32_t& t, unsigned long long* stats) {
   if ((uint32_t)a >= lim.n_aids || ty > 2u || t < lim.ts_lo || t > lim.ts_hi) {
@@ -491,6 +491,10 @@ __global__ void bins_count_kernel(const uint32_t* __restrict__ row_total, const 
   }
   nb[x] = n;
   hot_cnt[x] = hc;
+  // largest bin this layout can produce (sub-bins: four times the mean covers the aid_y-hash imbalance); the
+  // hash-table kernel of reduce.cuh holds a 24-bit count and a 40-bit time sum per entry (STAT_MAX_BIN guard)
+  const unsigned long long est = n > 1 ? 4ull * ((tot + n - 1) / n) : tot;
+  if (est > TIER3_MAX) atomicMax(&stats[STAT_MAX_BIN], est);   // bins the owner-table tiers take cannot overflow
 }
 
 __global__ void bins_fill_kernel(const uint32_t* __restrict__ bin_base, int64_t A, uint32_t* __restrict__ bin_x) {
@@ -753,6 +757,26 @@ extern "C" int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitS
   return OTTO_OK;
 }
 
+// The owner-table tiers take bins of up to 6144 records, where nothing can overflow.  Larger bins (split_ub raised,
+// or a row beyond 4096 sub-bins) go to the hash-table kernel, whose entries hold a 24-bit count and, in time mode, a
+// 40-bit sum of ts_x - ts_min: refuse layouts in which an entry could exceed either.
+static int check_max_bin(const OttoCovisitSpec* spec, unsigned long long max_bin, int64_t n_sessions) {
+  // a session contributes a pair (aid_x, aid_y) at most once (in-session dedupe), so an entry counts at most the sessions of
+  // all ranks (bounded by their events when only those are known)
+  const unsigned long long sessions = spec->global_events > 0 ? (unsigned long long)spec->global_events : (unsigned long long)n_sessions;
+  if (max_bin > sessions) max_bin = sessions;
+  if (max_bin >= (1ull << 24)) {
+    otto_set_error("a bin may hold %llu records; the accumulators count to 2^24 per (aid_x, aid_y): lower split_ub", max_bin);
+    return OTTO_EINVAL;
+  }
+  if (spec->weight_mode == OTTO_WEIGHT_TIME && max_bin * (unsigned long long)((int64_t)spec->ts_max - spec->ts_min) >= (1ull << 40)) {
+    otto_set_error("a bin may hold %llu records over a time range of %lld s; the time sums hold 40 bits: lower split_ub", max_bin,
+                   (long long)((int64_t)spec->ts_max - spec->ts_min));
+    return OTTO_EINVAL;
+  }
+  return OTTO_OK;
+}
+
 static int bad_events_error(const OttoCovisitSpec* spec, unsigned long long n) {
   if (spec->weight_mode == OTTO_WEIGHT_TIME)
     otto_set_error("%llu tail events have an aid outside [0, %d), a type above 2 or a ts outside [ts_min, ts_max] = [%d, %d] "
@@ -773,6 +797,7 @@ extern "C" int otto_covisit_count_finish(const OttoEvents* ev, const OttoCovisit
   const int64_t A = L.A;
   CUDA_TRY(cudaMemsetAsync(WS(uint32_t, bin_base), 0, (A + 2) * 4, st));
   CUDA_TRY(cudaMemsetAsync(WS(unsigned long long, stats) + 3, 0, 8, st));
+  CUDA_TRY(cudaMemsetAsync(WS(unsigned long long, stats) + STAT_MAX_BIN, 0, 8, st));
   bins_count_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(
       WS(uint32_t, row_total), WS(uint32_t, row_count), A, (uint32_t)effective_split_ub(spec), (uint32_t)sub_bin_target(spec),
       WS(uint32_t, bin_base), WS(unsigned long long, hot_off), WS(uint32_t, hot_rows), L.Hmax, WS(unsigned long long, stats));
@@ -792,6 +817,7 @@ extern "C" int otto_covisit_count_finish(const OttoEvents* ev, const OttoCovisit
   CUDA_TRY(cudaMemcpyAsync(h, WS(char, stats), sizeof(h), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   if (h[STAT_BAD_EVENTS]) return bad_events_error(spec, h[STAT_BAD_EVENTS]);
+  if ((rc = check_max_bin(spec, h[STAT_MAX_BIN], L.S))) return rc;
   // the bin arrays were sized from the event count: refuse before anything is written past them
   if ((int64_t)h[2] > L.Bmax || (int64_t)h[3] > L.Hmax) {
     otto_set_error("%llu bins / %llu hot rows exceed the %lld / %lld the workspace was sized for: set spec.global_events to the "
@@ -867,6 +893,7 @@ extern "C" int otto_covisit_count_finish_owned(const OttoEvents* ev, const OttoC
   unsigned long long* stats = WS(unsigned long long, stats);
   CUDA_TRY(cudaMemsetAsync(WS(uint32_t, bin_base), 0, (A + 2) * 4, st));
   CUDA_TRY(cudaMemsetAsync(stats + 3, 0, 8, st));
+  CUDA_TRY(cudaMemsetAsync(stats + STAT_MAX_BIN, 0, 8, st));
   // hot_off := totals of the hot rows (the "own count" input is the total here)
   bins_count_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(
       WS(uint32_t, row_total), WS(uint32_t, row_total), A, (uint32_t)effective_split_ub(spec), (uint32_t)sub_bin_target(spec),
@@ -901,6 +928,7 @@ extern "C" int otto_covisit_count_finish_owned(const OttoEvents* ev, const OttoC
   CUDA_TRY(cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   if (h[STAT_BAD_EVENTS]) return bad_events_error(spec, h[STAT_BAD_EVENTS]);
+  if ((rc = check_max_bin(spec, h[STAT_MAX_BIN], L.S))) return rc;
   if ((int64_t)h[2] > L.Bmax || (int64_t)h[3] > L.Hmax) {
     otto_set_error("%llu bins / %llu hot rows exceed the %lld / %lld the workspace was sized for: set spec.global_events to the "
                    "event count of all ranks", h[2], h[3], (long long)L.Bmax, (long long)L.Hmax);

@@ -156,6 +156,23 @@ def test_tied_entries_hand_over_to_the_hash_table_kernel(cv, variant):
     assert top0 == list(range(10, 10 + getattr(cv, variant).k)), top0
 
 
+def test_accumulator_width_guard(cv):
+    """Bins beyond the owner-table tiers go to the hash-table kernel (24-bit counts, 40-bit time sums): a layout in which
+    an entry could exceed them is refused instead of wrapping silently."""
+    from dataclasses import replace
+    from otto_multi_objective_recommender_system_b200 import _native as N
+    frame = synth_frame(70000, 24, seed=5)
+    csr = cv.ingest(frame, "desc", device="cuda:0")
+    # 70,000 sessions over 24 aids: rows of about a million pairs, unsplit; the real time range passes ...
+    cv.build_topk(csr, replace(cv.CLICKS, split_ub=1 << 30))
+    # ... a range of 2^24 - 1 seconds times 70,000 possible sessions per entry does not fit 40 bits
+    wide = replace(cv.CLICKS, split_ub=1 << 30, ts_min=cv.CLICKS.ts_max - (1 << 24) + 1)
+    with pytest.raises(N.OttoError, match="40 bits"):
+        cv.build_topk(csr, wide)
+    # with the default split_ub no bin leaves the owner-table tiers and the same range is fine
+    cv.build_topk(csr, replace(wide, split_ub=0))
+
+
 def test_edge_sessions(cv):
     """Lengths 1, 2, 30, 31, 32, 33, 500; ts ties across the tail boundary; window edge |dt| == W."""
     rng = np.random.default_rng(0)
