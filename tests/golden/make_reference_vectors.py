@@ -64,19 +64,31 @@ class StubAnnoy:
         return [i]            # only the query item itself: the loops drop element 0
 
 
-def make_inputs(seed=7, n_aids=80, n_sessions=60, k=6):
+PROFILES = {
+    # the round-1 set: 60 short sessions, 80 aids, rows of <= 6 neighbours
+    "reference_candidates.json": dict(seed=7, n_aids=80, k=6, full_rows=False,
+                                      lengths=([1, 2, 2, 3, 3, 4, 5, 6, 8, 10, 12, 15, 19, 20, 21, 22, 25, 30, 40, 60] * 3)),
+    # the wide set: full K = 15 rows, sessions up to OTTO's longest test session (458 events),
+    # hundreds of distinct candidates so that most_common(100) truncates, long histories for the recency branch
+    "reference_candidates_wide.json": dict(seed=11, n_aids=900, k=15, full_rows=True,
+                                           lengths=[1, 2, 3, 5, 8, 13, 19, 20, 21, 30, 45, 60, 80, 81, 82, 100, 128, 200, 256,
+                                                    300, 400, 458, 458, 257, 129, 83, 64, 33, 32, 31]),
+}
+
+
+def make_inputs(seed=7, n_aids=80, k=6, full_rows=False, lengths=()):
     rng = np.random.default_rng(seed)
+    n_sessions = len(lengths)
     stems = ("time_weighted", "click_weighted", "cart_weighted", "order_weighted", "click_cart", "click_order", "cart_order")
     tables = {}
     for stem in stems:
         rows = {}
         for x in range(n_aids):
             if rng.random() < 0.8:
-                n = int(rng.integers(1, k + 1))
+                n = k if full_rows and rng.random() < 0.9 else int(rng.integers(1, k + 1))
                 rows[x] = [int(y) for y in rng.choice(n_aids, size=n, replace=False)]
         tables[stem] = rows
     sessions = []
-    lengths = [1, 2, 2, 3, 3, 4, 5, 6, 8, 10, 12, 15, 19, 20, 21, 22, 25, 30, 40, 60] * 3
     for s, L in enumerate(lengths[:n_sessions]):
         pool = n_aids if s % 3 else max(3, L // 2)
         aids = [int(a) for a in rng.integers(0, pool, size=L)]
@@ -122,8 +134,13 @@ def run(body: str, ns: dict, sessions, style: str, only=None, frame_name: str = 
 
 
 def main():
-    n_aids, tables, sessions, popular = make_inputs()
-    out = {"n_aids": n_aids, "tables": {st: {str(x): ys for x, ys in rows.items()} for st, rows in tables.items()},
+    for name, profile in PROFILES.items():
+        make(name, profile)
+
+
+def make(name, profile):
+    n_aids, tables, sessions, popular = make_inputs(**profile)
+    out = {"n_aids": n_aids, "table_k": profile["k"], "tables": {st: {str(x): ys for x, ys in rows.items()} for st, rows in tables.items()},
            "sessions": sessions, "popular": popular}
 
     p = REF / "ranker" / "covisitation_candidate_generation.py"
@@ -191,8 +208,10 @@ def main():
         if isinstance(o, (np.floating,)):
             return float(o)
         raise TypeError(type(o))
-    json.dump(out, open(OUT / "reference_candidates.json", "w"), default=plain)
-    print("sessions", len(sessions), "long", sum(is_long(s) for s in sessions), "bytes", (OUT / "reference_candidates.json").stat().st_size)
+    json.dump(out, open(OUT / name, "w"), default=plain, separators=(",", ":"))
+    most = max(len(out["ranker"][i]["click"][0]) for i in range(len(sessions)))
+    print(name, "sessions", len(sessions), "long", sum(is_long(s) for s in sessions), "longest", max(len(s["aid"]) for s in sessions),
+          "most ranker candidates", most, "bytes", (OUT / name).stat().st_size)
 
 
 if __name__ == "__main__":

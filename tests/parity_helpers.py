@@ -57,10 +57,15 @@ def assert_time_table_close(got: pd.DataFrame, acc: pd.DataFrame, k: int, what: 
 
 # ---- vectors produced by executing the reference's own loop bodies (tests/golden/make_reference_vectors.py) ----
 
-def reference_vectors():
+REFERENCE_VECTOR_FILES = ["reference_candidates.json", "reference_candidates_wide.json"]
+
+
+def reference_vectors(name="reference_candidates.json"):
+    """reference_candidates.json: 60 short sessions, 80 aids, rows of <= 6; reference_candidates_wide.json: K = 15 rows,
+    sessions of up to 458 events, more than 100 distinct candidates (most_common(100) truncates)."""
     import json
     import pathlib
-    return json.load(open(pathlib.Path(__file__).resolve().parent / "golden" / "reference_candidates.json"))
+    return json.load(open(pathlib.Path(__file__).resolve().parent / "golden" / name))
 
 
 def reference_vector_inputs(g):

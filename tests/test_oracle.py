@@ -189,12 +189,13 @@ def _attach_labels(frames, labels):
     return frames
 
 
-def test_oracle_matches_vectors_from_the_reference_loop_bodies():
-    """tests/golden/reference_candidates.json was produced by executing the reference's own loop bodies
-    (make_reference_vectors.py): the restatements in oracle/candidates_oracle.py must reproduce it exactly."""
+@pytest.mark.parametrize("vectors", ["reference_candidates.json", "reference_candidates_wide.json"])
+def test_oracle_matches_vectors_from_the_reference_loop_bodies(vectors):
+    """tests/golden/reference_candidates*.json were produced by executing the reference's own loop bodies
+    (make_reference_vectors.py): the restatements in oracle/candidates_oracle.py must reproduce them exactly."""
     import parity_helpers as H
     from oracle import candidates_oracle as oc
-    g = H.reference_vectors()
+    g = H.reference_vectors(vectors)
     df, tables, labels, popular = H.reference_vector_inputs(g)
     H.check_candidate_frames(g, "ranker", _attach_labels(oc.ranker_frame(df, tables, 100), labels))
     H.check_candidate_frames(g, "regular", _attach_labels(oc.regular_frame(df, tables, 100), labels))
@@ -226,4 +227,5 @@ def test_reference_vectors_are_reproducible(tmp_path, monkeypatch):
     monkeypatch.setattr(mod, "OUT", tmp_path)
     (tmp_path / "popular.json").write_text((GOLDEN / "popular.json").read_text())
     mod.main()
-    assert json.load(open(tmp_path / "reference_candidates.json")) == json.load(open(GOLDEN / "reference_candidates.json"))
+    for name in mod.PROFILES:
+        assert json.load(open(tmp_path / name)) == json.load(open(GOLDEN / name)), name

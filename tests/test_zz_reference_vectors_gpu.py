@@ -13,13 +13,15 @@ def mods(native_lib):
     return covisit, candidates, synth
 
 
-def test_cuda_path_matches_vectors_from_the_reference_loop_bodies(mods):
+@pytest.mark.parametrize("vectors", ["reference_candidates.json", "reference_candidates_wide.json"])
+def test_cuda_path_matches_vectors_from_the_reference_loop_bodies(mods, vectors):
     """tests/golden/reference_candidates.json holds outputs of the reference's OWN loop bodies (executed as text by
     tests/golden/make_reference_vectors.py): ranker form, regular form, recency-weighted generator and the standalone
-    model with its long-session branch, on 60 sessions and all seven stems.  The CUDA path must reproduce them."""
+    model with its long-session branch, all seven stems - on 60 short sessions with rows of <= 6 neighbours, and on the
+    wide set (K = 15 rows, sessions of up to 458 events, most_common(100) truncating).  The CUDA path must reproduce them."""
     import parity_helpers as H
     cv, cand_mod, synth = mods
-    g = H.reference_vectors()
+    g = H.reference_vectors(vectors)
     df, otables, labels, popular = H.reference_vector_inputs(g)
     n_aids = g["n_aids"]
     tables = {}
@@ -27,7 +29,7 @@ def test_cuda_path_matches_vectors_from_the_reference_loop_bodies(mods):
         r = H.table_rows(rows)
         tables[stem] = cv.TopKTable.from_rows(torch.tensor(r["aid_x"].to_numpy(), device="cuda:0"),
                                               torch.tensor(r["aid_y"].to_numpy(), device="cuda:0"),
-                                              torch.tensor(r["wgt"].to_numpy(), dtype=torch.float32, device="cuda:0"), n_aids, 6)
+                                              torch.tensor(r["wgt"].to_numpy(), dtype=torch.float32, device="cuda:0"), n_aids, g.get("table_k", 6))
     sess = cv.ingest(synth.EventFrame.from_pandas(df, n_aids), "asc", device="cuda:0")
     ranker = cand_mod.generate_candidates(sess, tables, cand_mod.reference_spec(tables.keys(), 100)).to_frames(labels)
     H.check_candidate_frames(g, "ranker", ranker)
