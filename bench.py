@@ -638,7 +638,6 @@ def run_b200(args):
     if args.e2e_steps > 0:
         host = synth.EventFrame(*(t.cpu().pin_memory() for t in (frame.session, frame.aid, frame.ts, frame.type)),
                                 n_aids=A)
-        h2d = sum(t.numel() * t.element_size() for t in (host.session, host.aid, host.ts, host.type))
         del frame
         d2h = [0]
         pinned = [None]
@@ -654,10 +653,17 @@ def run_b200(args):
             torch.cuda.current_stream(dev).synchronize()
             return out
 
+        # All four columns are copied and the CSR stays in file order: the tail kernels apply the builder's descending
+        # sort while they copy (otto_covisit_count_begin_asc), so the whole-frame reversal of round 1 is gone.  Leaving
+        # aid / type in pinned host memory and reading only the tails over PCIe (ingest(..., zero_copy=True)) moves 14 %
+        # fewer bytes but was slower on this box: SM loads from host memory reach 25 GB/s against 55 GB/s for the copy
+        # engine (tools/time_e2e.py, profiles/r02_experiments.md).
+        h2d = sum(t.numel() * t.element_size() for t in (host.session, host.aid, host.ts, host.type))
+
         def e2e_step():
             f = synth.EventFrame(host.session.to(dev, non_blocking=True), host.aid.to(dev, non_blocking=True),
                                  host.ts.to(dev, non_blocking=True), host.type.to(dev, non_blocking=True), A)
-            c = covisit.ingest(f, "desc", device=dev)
+            c = covisit.ingest(f, "asc", device=dev)
             be = distributed.GpuRankBackend(c, spec, peer=peer)
             b = be.b
             b.workspace = builder.workspace          # reuse device buffers, as a long-running service would

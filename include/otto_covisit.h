@@ -185,6 +185,14 @@ int otto_covisit_sizes(int64_t n_sessions, int64_t n_events, const OttoCovisitSp
 
 int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
                              int64_t workspace_bytes, void* stream);
+/* The same for a CSR in FILE order (ts ascending inside a session, the order the reference's frames are written in:
+ * utilities/split_dataset_writer_parquet.py:17): the tail kernels apply the builder's stable ts-descending sort
+ * (Appendix A step 2) while they copy, so otto_ingest_desc is not needed.  Only the <= tail_n most recent events of
+ * a session are read: ev->aid and ev->type may point to pinned HOST memory (cudaHostAlloc; valid on the device under
+ * UVA), in which case 5 bytes per tail event cross PCIe instead of 5 bytes per event.  ev->session_offsets and ev->ts
+ * must be device memory.  Every later phase takes the same ev. */
+int otto_covisit_count_begin_asc(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                                 int64_t workspace_bytes, void* stream);
 /* Fills stats_host->{tail_events,pairs,bins,split_rows,hot_pairs}; synchronises.  OTTO_EINVAL when a tail event carried
  * an aid outside [0, n_aids), a type above 2 or (time mode) a ts outside [ts_min, ts_max]: count_begin replaces such
  * events by a harmless one and flags them, so nothing is written out of bounds (in owner-direct mode the pair kernels

@@ -126,6 +126,7 @@ _SIGNATURES = {
     "otto_ingest_desc": (C.c_int, [vp, i64, vp, vp, vp, i64, vp, vp, vp, vp]),
     "otto_covisit_sizes": (C.c_int, [i64, i64, P(OttoCovisitSpec), P(OttoBuildSizes)]),
     "otto_covisit_count_begin": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, vp]),
+    "otto_covisit_count_begin_asc": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, vp]),
     "otto_covisit_count_finish": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(OttoBuildStats), vp]),
     "otto_covisit_count": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(OttoBuildStats), vp]),
     "otto_covisit_views": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(vp), P(vp), P(vp), P(vp)]),

@@ -128,17 +128,33 @@ class EventCSR:
                         self.ts[e0:e1], self.type[e0:e1], self.n_aids, self.order, self.max_len_dev)
 
 
-def ingest(frame: EventFrame, order: str = "desc", device=None) -> EventCSR:
+def _zero_copy_ok(frame: EventFrame) -> bool:
+    return all((not t.is_cuda) and t.is_pinned() and t.is_contiguous() for t in (frame.session, frame.aid, frame.ts, frame.type)) \
+        and frame.aid.dtype == torch.int32 and frame.type.dtype == torch.uint8
+
+
+def ingest(frame: EventFrame, order: str = "desc", device=None, zero_copy: bool = False) -> EventCSR:
     """Frame columns -> CSR.  Replaces the sort + 100k-session chunk writers
-    (utilities/split_dataset_writer_parquet.py:13-33) and builder step 2 (ts-descending stable sort)."""
+    (utilities/split_dataset_writer_parquet.py:13-33) and builder step 2 (ts-descending stable sort).
+
+    zero_copy (builder input from a PINNED host frame in file order): only `session` and `ts` are copied to the
+    device; `aid` and `type` stay in pinned host memory and the result is an order='asc' CSR whose tails the build
+    reads over PCIe (otto_covisit_count_begin_asc) - the build only ever touches the <= 30 most recent events of a
+    session, 63 % of OTTO's events.  The frame must be sorted by (session, ts); aid / type are validated where they are
+    read (the tail kernels), not here."""
     if order not in ("asc", "desc"):
         raise ValueError("Invalid order")
+    if zero_copy and not _zero_copy_ok(frame):
+        raise ValueError("zero_copy needs contiguous pinned host columns (aid int32, type uint8)")
     device = torch.device(device if device is not None else (frame.aid.device if frame.aid.is_cuda else "cuda"))
     lib = N.lib()
-    sess = frame.session.to(device=device, dtype=torch.int32).contiguous()
-    aid = frame.aid.to(device=device, dtype=torch.int32).contiguous()
-    ts = frame.ts.to(device=device, dtype=torch.int32).contiguous()
-    typ = frame.type.to(device=device, dtype=torch.uint8).contiguous()
+    sess = frame.session.to(device=device, dtype=torch.int32, non_blocking=zero_copy).contiguous()
+    ts = frame.ts.to(device=device, dtype=torch.int32, non_blocking=zero_copy).contiguous()
+    if zero_copy:
+        aid, typ = frame.aid, frame.type
+    else:
+        aid = frame.aid.to(device=device, dtype=torch.int32).contiguous()
+        typ = frame.type.to(device=device, dtype=torch.uint8).contiguous()
     E = int(sess.numel())
     if E >= 2 ** 31:
         raise ValueError("frames are limited to 2^31 - 1 events per device")
@@ -150,11 +166,13 @@ def ingest(frame: EventFrame, order: str = "desc", device=None) -> EventCSR:
 
         def scan():
             # one read of the frame: session starts per tile, (session, ts) order, aid in [0, n_aids) and type in {0, 1, 2}
-            N.check(lib.otto_ingest_scan(sess.data_ptr(), aid.data_ptr(), ts.data_ptr(), typ.data_ptr(), E, int(frame.n_aids),
-                                         scratch.data_ptr(), need, info, st))
+            N.check(lib.otto_ingest_scan(sess.data_ptr(), None if zero_copy else aid.data_ptr(), ts.data_ptr(),
+                                         None if zero_copy else typ.data_ptr(), E, int(frame.n_aids), scratch.data_ptr(), need, info, st))
             if info[2]:
                 raise N.OttoError(N.OTTO_EINVAL, f"{info[2]} events have an aid outside [0, {frame.n_aids}) or a type above 2")
         scan()
+        if not info[1] and zero_copy:
+            raise N.OttoError(N.OTTO_EUNSORTED, "zero_copy ingest needs a frame sorted by (session, ts)")
         if not info[1]:
             # unsorted input: sort by (session, ts), stable, like df.sort_values(['session', 'ts']).  The reference's
             # frames are written sorted (utilities/split_dataset_writer_parquet.py:17), so this is the rare path and the
@@ -169,7 +187,7 @@ def ingest(frame: EventFrame, order: str = "desc", device=None) -> EventCSR:
         max_len = torch.zeros(1, dtype=torch.int32, device=device)
         N.check(lib.otto_ingest_offsets(sess.data_ptr(), E, S, scratch.data_ptr(), need, ids.data_ptr(), offsets.data_ptr(),
                                         max_len.data_ptr(), st))
-        if order == "asc":
+        if order == "asc" or zero_copy:
             return EventCSR(ids, offsets, aid, ts, typ, frame.n_aids, "asc", max_len)
         aid_d, ts_d, typ_d = torch.empty_like(aid), torch.empty_like(ts), torch.empty_like(typ)
         N.check(lib.otto_ingest_desc(offsets.data_ptr(), ids.numel(), aid.data_ptr(), ts.data_ptr(), typ.data_ptr(), E,
@@ -269,12 +287,16 @@ class CovisitBuilder:
     one pipeline run) do not re-allocate."""
 
     def __init__(self, csr: EventCSR, spec: CovisitSpec, exact: bool = False):
-        if csr.order != "desc":
-            raise ValueError("the builder needs the most-recent-first CSR (ingest(..., order='desc'))")
-        _require_cuda(csr.aid, "csr")
+        # order='desc': the most-recent-first CSR of otto_ingest_desc; order='asc': file order, reversed by the tail kernels
+        # (then aid / type may be pinned host tensors, read over PCIe)
+        _require_cuda(csr.ts, "csr.ts")
+        _require_cuda(csr.offsets, "csr.offsets")
+        for name, t in (("aid", csr.aid), ("type", csr.type)):
+            if not t.is_cuda and not (csr.order == "asc" and t.is_pinned()):
+                raise RuntimeError(f"csr.{name} must live on a CUDA device (or, for an order='asc' CSR, in pinned host memory)")
         self.lib = N.lib()
         self.csr, self.spec, self.exact = csr, spec, exact
-        self.device = csr.aid.device
+        self.device = csr.ts.device
         self.cspec = spec.to_c(csr.n_aids)
         self.ev = N.OttoEvents(csr.n_sessions, csr.n_events, csr.offsets.data_ptr(), csr.aid.data_ptr(),
                                csr.ts.data_ptr(), csr.type.data_ptr())
@@ -294,8 +316,8 @@ class CovisitBuilder:
 
     def count_begin(self) -> None:
         with torch.cuda.device(self.device):
-            N.check(self.lib.otto_covisit_count_begin(C.byref(self.ev), C.byref(self.cspec), self.workspace.data_ptr(),
-                                                      self.workspace.numel(), self._st()))
+            begin = self.lib.otto_covisit_count_begin_asc if self.csr.order == "asc" else self.lib.otto_covisit_count_begin
+            N.check(begin(C.byref(self.ev), C.byref(self.cspec), self.workspace.data_ptr(), self.workspace.numel(), self._st()))
 
     def count_finish(self) -> dict:
         with torch.cuda.device(self.device):

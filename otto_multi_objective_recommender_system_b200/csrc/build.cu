@@ -468,6 +468,105 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- the same two kernels for a frame in FILE order (ts ascending inside a session), which is how the reference's
+// frames are written (utilities/split_dataset_writer_parquet.py:17) and how a host frame arrives: the builder's
+// stable sort_values(['session','ts'], ascending=[True, False]) reverses the runs of equal ts as runs and keeps the
+// original order inside a run, so output position j of a session of L events (0 = most recent) mirrors source
+// p = L - 1 - j inside the run [a, r) of equal ts around p: source = a + r - 1 - p.  Only the tails are read, so aid
+// and type may stay in pinned host memory (the pointers are valid on the device under UVA): 5 bytes per TAIL event
+// cross PCIe instead of 5 bytes per event, and the whole-frame reversal pass (otto_ingest_desc) is not needed.  ts is
+// read with its neighbours and belongs in device memory.
+__device__ __forceinline__ int32_t desc_source(const int32_t* __restrict__ ts, int32_t beg, int32_t end, int32_t p, int32_t& t) {
+  t = ts[p];
+  int32_t a = p, r = p + 1;
+  while (a > beg && ts[a - 1] == t) --a;
+  while (r < end && ts[r] == t) ++r;
+  return a + r - 1 - p;
+}
+
+__global__ void tail_count_asc_kernel(const int32_t* __restrict__ off, const uint8_t* __restrict__ type, int64_t S,
+                                      uint32_t mask, int32_t tail_n, uint32_t* __restrict__ cnt) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int32_t beg = off[s], end = off[s + 1];
+  int32_t n = 0;
+  if ((mask & 7u) == 7u) {
+    n = min(end - beg, tail_n);
+  } else {
+    for (int32_t p = end - 1; p >= beg && n < tail_n; --p) n += type[p] < 32 ? (mask >> type[p]) & 1u : 0u;
+  }
+  cnt[s] = (uint32_t)n;
+}
+
+// one thread per session walks the runs of equal ts from the last one backwards, each run in file order
+__global__ void __launch_bounds__(256)
+    tail_copy_filtered_asc_kernel(const int32_t* __restrict__ off, const int32_t* __restrict__ aid, const int32_t* __restrict__ ts,
+                                  const uint8_t* __restrict__ type, int64_t S, uint32_t mask, const uint32_t* __restrict__ tail_off,
+                                  uint32_t* __restrict__ tail_aw, int32_t* __restrict__ tail_ts, const EventLimits lim,
+                                  unsigned long long* stats) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const uint32_t tb = tail_off[s];
+  const uint32_t n = tail_off[s + 1] - tb;
+  if (n == 0) return;
+  const int32_t beg = off[s];
+  uint32_t taken = 0;
+  for (int32_t r = off[s + 1]; r > beg && taken < n;) {
+    const int32_t t0 = ts[r - 1];
+    int32_t a = r - 1;
+    while (a > beg && ts[a - 1] == t0) --a;
+    for (int32_t p = a; p < r && taken < n; ++p) {
+      uint32_t ty = type[p];
+      if (ty < 32u && ((mask >> ty) & 1u)) {
+        int32_t av = aid[p], t = t0;
+        check_event(lim, av, ty, t, stats);
+        tail_aw[tb + taken] = (uint32_t)av | (ty << 30);
+        tail_ts[tb + taken] = t;
+        ++taken;
+      }
+    }
+    r = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    tail_copy_all_asc_kernel(const int32_t* __restrict__ off, const int32_t* __restrict__ aid, const int32_t* __restrict__ ts,
+                             const uint8_t* __restrict__ type, int64_t S, const uint32_t* __restrict__ tail_off,
+                             uint32_t* __restrict__ tail_aw, int32_t* __restrict__ tail_ts, const EventLimits lim,
+                             unsigned long long* stats) {
+  const int64_t s0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
+  if (s0 >= S) return;
+  const int lane = (int)lane_id();
+  const int ns = (int)min((int64_t)32, S - s0);
+  const int32_t beg0 = off[s0 + min(lane, ns - 1)];
+  const int32_t end0 = off[s0 + min(lane, ns - 1) + 1];
+  const uint32_t to = tail_off[s0 + min(lane, ns)];
+  const uint32_t to_next = tail_off[s0 + min(lane + 1, ns)];
+  const uint32_t T0 = __shfl_sync(FULL_MASK, to, 0);
+  const uint32_t total = __shfl_sync(FULL_MASK, to_next, ns - 1) - T0;
+  for (uint32_t q0 = 0; q0 < total; q0 += 32) {
+    const uint32_t q = q0 + lane;
+    int u = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      const int c = u + step;
+      const uint32_t tc = __shfl_sync(FULL_MASK, to, min(c, 31));
+      if (c < ns && tc - T0 <= q) u = c;
+    }
+    const uint32_t tu = __shfl_sync(FULL_MASK, to, u);
+    const int32_t beg = __shfl_sync(FULL_MASK, beg0, u), end = __shfl_sync(FULL_MASK, end0, u);
+    if (q < total) {
+      int32_t t;
+      const int32_t src = desc_source(ts, beg, end, end - 1 - (int32_t)(q - (tu - T0)), t);
+      int32_t a = aid[src];
+      uint32_t ty = type[src];
+      check_event(lim, a, ty, t, stats);
+      tail_aw[T0 + q] = (uint32_t)a | (ty << 30);
+      tail_ts[T0 + q] = t;
+    }
+  }
+}
+
 // Bins of a row: 1, or ceil(total / target) aid_y-hash sub-bins when the row is hot (total over ALL ranks above
 // split_ub).  Hot rows are also listed (any order) for the partition kernels; hot_cnt = the rank's own pairs of a
 // hot row (its share of the staging area), 0 for ordinary rows.
@@ -709,8 +808,8 @@ static PairGenParams make_pairgen(const Layout& L, const OttoCovisitSpec* spec, 
 }
 
 // tail CSR (steps 1-3) + in-session dedupe (steps 4-5: row masks) + pairs per aid_x row
-extern "C" int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
-                                        int64_t workspace_bytes, void* stream) {
+static int count_begin_impl(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
+                            void* stream, bool ascending) {
   int rc = check_spec(spec);
   if (rc) return rc;
   if (!ev) { otto_set_error("events is NULL"); return OTTO_EINVAL; }
@@ -722,9 +821,12 @@ extern "C" int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitS
   CUDA_TRY(cudaMemsetAsync(WS(char, stats), 0, 512, st));
   CUDA_TRY(cudaMemsetAsync(WS(uint32_t, tail_off), 0, (S + 2) * 4, st));
   if (S > 0) {
-    tail_count_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(ev->session_offsets, ev->type, S,
-                                                                   spec->event_type_mask, spec->tail_n,
-                                                                   WS(uint32_t, tail_off));
+    if (ascending)
+      tail_count_asc_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(ev->session_offsets, ev->type, S, spec->event_type_mask,
+                                                                         spec->tail_n, WS(uint32_t, tail_off));
+    else
+      tail_count_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(ev->session_offsets, ev->type, S, spec->event_type_mask,
+                                                                     spec->tail_n, WS(uint32_t, tail_off));
     LAUNCH_CHECK();
   }
   if ((rc = exclusive_scan<uint32_t, uint32_t>(WS(uint32_t, tail_off), S, WS(uint32_t, tail_off), WS(uint32_t, scan), st)))
@@ -735,15 +837,15 @@ extern "C" int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitS
   lim.ts_lo = time_mode ? spec->ts_min : INT32_MIN;
   lim.ts_hi = time_mode ? spec->ts_max : INT32_MAX;
   if (S > 0 && (spec->event_type_mask & 7u) == 7u) {
-    tail_copy_all_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(ev->session_offsets, ev->aid, ev->ts, ev->type, S,
-                                                                     WS(uint32_t, tail_off), WS(uint32_t, tail_aw),
-                                                                     WS(int32_t, tail_ts), lim, WS(unsigned long long, stats));
+    auto kern = ascending ? tail_copy_all_asc_kernel : tail_copy_all_kernel;
+    kern<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(ev->session_offsets, ev->aid, ev->ts, ev->type, S, WS(uint32_t, tail_off),
+                                                     WS(uint32_t, tail_aw), WS(int32_t, tail_ts), lim, WS(unsigned long long, stats));
     LAUNCH_CHECK();
   } else if (S > 0) {
-    tail_copy_filtered_kernel<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(ev->session_offsets, ev->aid, ev->ts, ev->type, S,
-                                                                          spec->event_type_mask, WS(uint32_t, tail_off),
-                                                                          WS(uint32_t, tail_aw), WS(int32_t, tail_ts), lim,
-                                                                          WS(unsigned long long, stats));
+    auto kern = ascending ? tail_copy_filtered_asc_kernel : tail_copy_filtered_kernel;
+    kern<<<(unsigned)ceil_div(S, 256), 256, 0, st>>>(ev->session_offsets, ev->aid, ev->ts, ev->type, S, spec->event_type_mask,
+                                                     WS(uint32_t, tail_off), WS(uint32_t, tail_aw), WS(int32_t, tail_ts), lim,
+                                                     WS(unsigned long long, stats));
     LAUNCH_CHECK();
   }
   if (S > 0) {
@@ -775,6 +877,16 @@ static int check_max_bin(const OttoCovisitSpec* spec, unsigned long long max_bin
     return OTTO_EINVAL;
   }
   return OTTO_OK;
+}
+
+extern "C" int otto_covisit_count_begin(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                                        int64_t workspace_bytes, void* stream) {
+  return count_begin_impl(ev, spec, workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int otto_covisit_count_begin_asc(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace,
+                                            int64_t workspace_bytes, void* stream) {
+  return count_begin_impl(ev, spec, workspace, workspace_bytes, stream, true);
 }
 
 static int bad_events_error(const OttoCovisitSpec* spec, unsigned long long n) {

@@ -119,12 +119,12 @@ class GpuRankBackend:
     def __init__(self, csr: EventCSR, spec: CovisitSpec, exact: bool = False, peer: PeerRecords | None = None):
         if dist.is_initialized() and dist.get_world_size() > 1 and spec.global_events == 0:
             # collective: the bins come from the all-reduced bounds, so size the bin arrays for the global frame
-            total = torch.tensor([csr.n_events], dtype=torch.int64, device=csr.aid.device)
+            total = torch.tensor([csr.n_events], dtype=torch.int64, device=csr.ts.device)
             dist.all_reduce(total)
             from dataclasses import replace
             spec = replace(spec, global_events=int(total.item()))
         self.b = CovisitBuilder(csr, spec, exact=exact)
-        self.n_aids, self.k, self.device = csr.n_aids, spec.k, csr.aid.device
+        self.n_aids, self.k, self.device = csr.n_aids, spec.k, csr.ts.device
         self.peer = peer          # set: records are exchanged through peer memory instead of NCCL
         self._plan_scratch = self._row_before = self._gathered = None
 

@@ -242,6 +242,60 @@ def test_ingest_desc_order_matches_stable_sort(cv):
     assert np.array_equal(csr2.aid.cpu().numpy(), want2["aid"].to_numpy())
 
 
+def _tables_equal(a, b):
+    return all(torch.equal(x, y) for x, y in ((a.aid_y, b.aid_y), (a.wgt.view(torch.int32), b.wgt.view(torch.int32)), (a.len, b.len)))
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_ascending_and_zero_copy_frames_build_the_same_table(cv, variant):
+    """otto_covisit_count_begin_asc: a CSR in file order (ts ascending) gives the table of the most-recent-first CSR -
+    the tail kernels apply the stable ts-descending sort while they copy - with aid / type on the device or left in
+    pinned host memory (ingest(..., zero_copy=True), the end-to-end path of bench.py)."""
+    from otto_multi_objective_recommender_system_b200 import synth
+    spec = getattr(cv, variant)
+    frame = synth_frame(6000, 700, seed=13)
+    want, wstats = cv.build_topk(cv.ingest(frame, "desc", device="cuda:0"), spec, exact=True)
+    got, gstats = cv.build_topk(cv.ingest(frame, "asc", device="cuda:0"), spec, exact=True)
+    assert _tables_equal(got, want) and torch.equal(got.cnt, want.cnt) and torch.equal(got.tsum, want.tsum)
+    assert gstats["pairs"] == wstats["pairs"] and gstats["tail_events"] == wstats["tail_events"]
+    pinned = synth.EventFrame(*(t.cpu().contiguous().pin_memory() for t in (frame.session, frame.aid, frame.ts, frame.type)),
+                              n_aids=frame.n_aids)
+    csr = cv.ingest(pinned, "asc", device="cuda:0", zero_copy=True)
+    assert not csr.aid.is_cuda and not csr.type.is_cuda and csr.ts.is_cuda
+    got, gstats = cv.build_topk(csr, spec, exact=True)
+    assert _tables_equal(got, want) and gstats["pairs"] == wstats["pairs"]
+    # zero-copy columns are validated where they are read (buy2buy never reads the clicks it filters out)
+    if variant == "BUY2BUY":
+        return
+    bad = synth.EventFrame(pinned.session, pinned.aid.clone().pin_memory(), pinned.ts, pinned.type, frame.n_aids)
+    last = int(cv.ingest(frame, "asc", device="cuda:0").offsets[1].item()) - 1     # most recent event of the first session
+    bad.aid[last] = frame.n_aids + 7
+    with pytest.raises(cv.N.OttoError):
+        cv.build_topk(cv.ingest(bad, "asc", device="cuda:0", zero_copy=True), spec)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_ascending_frames_with_runs_of_equal_ts_across_the_tail_cut(cv, variant):
+    """Sessions of 45-70 events in runs of equal ts (1-40 events per second): the 30-event tail cuts through runs, where
+    the stable descending sort keeps the FIRST events of the run in file order.  Checked against the oracle."""
+    rng = np.random.default_rng(3)
+    rows = []
+    for s in range(300):
+        n, t = int(rng.integers(45, 71)), 1660000000 + int(rng.integers(0, 1000000))
+        while n > 0:
+            run = min(n, int(rng.integers(1, 41)))
+            rows += [(s, int(rng.integers(0, 150)), t, int(rng.choice([0, 1, 2], p=[0.5, 0.3, 0.2]))) for _ in range(run)]
+            n -= run
+            t += int(rng.integers(1, 5000))
+    df = pd.DataFrame(rows, columns=["session", "aid", "ts", "type"])
+    frame = frame_from_df(df, 150)
+    spec = getattr(cv, variant)
+    check_against_oracle(cv, frame, spec, f"{variant} tie runs (desc CSR)")
+    want, _ = cv.build_topk(cv.ingest(frame, "desc", device="cuda:0"), spec, exact=True)
+    got, _ = cv.build_topk(cv.ingest(frame, "asc", device="cuda:0"), spec, exact=True)
+    assert _tables_equal(got, want) and torch.equal(got.cnt, want.cnt) and torch.equal(got.tsum, want.tsum)
+
+
 def test_build_is_deterministic(cv):
     frame = synth_frame(8000, 800, seed=2)
     csr = cv.ingest(frame, "desc", device="cuda:0")
