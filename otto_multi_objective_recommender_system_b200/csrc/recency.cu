@@ -11,7 +11,7 @@
 // Everything is fp64 and bit-exact against the Python loop: the recency weights come from the host (numpy, the
 // same libm pow), every `+=` is one __dadd_rn in the reference's order (an aid's events in file order, then its
 // bonuses one by one), products are __dmul_rn (no FMA contraction).
-// Long sessions are rare (about one test session in fifty) and at most a few hundred events: one 256-thread
+// Long sessions are rare (about one test session in fifty) and at most a few hundred events: one 128-thread
 // block per session over a global scratch slab; this kernel is not on the throughput path.
 #include <string.h>
 
@@ -48,6 +48,8 @@ struct RecencyParams {
   int32_t max_k;              // largest table_k among the present tables
 };
 
+constexpr int REC_THREADS = 128;   // threads per session (see RECENCY_BLOCKS)
+
 struct RecWork {
   int32_t* uaid;      // [lcap] unique aids in file order of first occurrence
   int32_t* utm;       // [lcap] type mask per unique aid
@@ -76,11 +78,15 @@ __device__ __forceinline__ uint32_t rec_find_or_claim(const RecWork& w, uint32_t
   }
 }
 
-__global__ void __launch_bounds__(256) recency_long_kernel(const RecencyParams p) {
-  constexpr int T = 256;
+__global__ void __launch_bounds__(REC_THREADS) recency_long_kernel(const RecencyParams p) {
+  constexpr int T = REC_THREADS;
   __shared__ int32_t s_n_occ, s_U, s_ne;
   __shared__ unsigned long long s_best_v[T / 32];
   __shared__ uint32_t s_best_p[T / 32], s_best_i[T / 32];
+  constexpr int REC_CANDS = 96;
+  __shared__ unsigned long long s_cv[REC_CANDS];
+  __shared__ uint32_t s_cq[REC_CANDS], s_ci[REC_CANDS];
+  __shared__ int s_selected;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned char* base = (unsigned char*)(p.slab + (int64_t)blockIdx.x * p.slab_words);
   RecWork w;
@@ -102,7 +108,22 @@ __global__ void __launch_bounds__(256) recency_long_kernel(const RecencyParams p
 
   // the slab is sized for the longest session (tens of thousands of slots): clear it once, afterwards only the
   // claimed slots are reset (a full reset per session and target wrote 40 GB for 27 k sessions)
-  for (int64_t h = tid; h < hs; h += T) {
+  // ... and only as far as the longest session this block will see needs it
+  __shared__ int s_lmax;
+  if (tid == 0) s_lmax = 0;
+  __syncthreads();
+  {
+    int lmax = 0;
+    for (int64_t item = blockIdx.x + (int64_t)tid * gridDim.x; item < p.n_list; item += (int64_t)T * gridDim.x) {
+      const int64_t s = p.list[item];
+      lmax = max(lmax, p.off[s + 1] - p.off[s]);
+    }
+    if (lmax) atomicMax(&s_lmax, lmax);
+  }
+  __syncthreads();
+  int64_t hs_clear = 64;
+  while (hs_clear < 2 * (int64_t)s_lmax * (1 + p.max_k) && hs_clear < hs) hs_clear <<= 1;
+  for (int64_t h = tid; h < hs_clear; h += T) {
     w.keys[h] = KEY_EMPTY;
     w.cnt[h] = 0;
     w.first[h] = 0xffffffffu;
@@ -229,7 +250,74 @@ __global__ void __launch_bounds__(256) recency_long_kernel(const RecencyParams p
         if (out_score) out_score[r] = 0.0;
       }
       if (tid == 0 && p.out_len) p.out_len[(int64_t)tg * p.rows + row] = rounds;
-      for (int r = 0; r < rounds; ++r) {
+      // Fast selection (n <= 32, the standalone model's 20): one warp takes the n-th largest of its 32 lane maxima in
+      // the full order (weight desc, insertion asc) as a lower bound of the n-th best entry, collects the entries at or
+      // above it (the order is strict, so there are about n .. 2n of them) and ranks those.  The n rounds of block-wide
+      // arg-max below cost 60 rounds x 8 warps x ~150 instructions per session (two thirds of this kernel's 112 k
+      // warp-instructions per session, profiles/r02_cand_full_launch_table.txt); they stay as the path for n > 32
+      // (otto_recency_scored keeps every aid) and for a candidate list that overflows.
+      bool selected = false;
+      if (p.n <= 32 && rounds > 0) {
+        if (warp == 0) {
+          auto gt = [](unsigned long long av, uint32_t aq, unsigned long long bv, uint32_t bq) { return av > bv || (av == bv && aq > bq); };
+          unsigned long long bv = 0;
+          uint32_t bq = 0;
+          for (int i = lane; i < d; i += 32) {
+            const unsigned long long v = (unsigned long long)__double_as_longlong(w.val[i]);
+            const uint32_t q = ~w.pos[i];
+            if (gt(v, q, bv, bq)) { bv = v; bq = q; }
+          }
+          unsigned long long sv = bv;
+          uint32_t sq = bq;
+#pragma unroll
+          for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+              const unsigned long long ov = shfl_u64(sv, lane ^ j);
+              const uint32_t oq = __shfl_xor_sync(FULL_MASK, sq, j);
+              const bool keep_max = ((lane & j) == 0) == ((lane & kk) == 0);
+              const bool take = keep_max ? gt(ov, oq, sv, sq) : gt(sv, sq, ov, oq);
+              if (take) { sv = ov; sq = oq; }
+            }
+          }
+          const unsigned long long tv = shfl_u64(sv, rounds - 1);   // (0, 0) when fewer than `rounds` lanes hold an entry: d < 32
+          const uint32_t tq = __shfl_sync(FULL_MASK, sq, rounds - 1);
+          int n_c = 0;
+          for (int i0 = 0; i0 < d; i0 += 32) {
+            const int i = i0 + lane;
+            unsigned long long v = 0;
+            uint32_t q = 0;
+            if (i < d) {
+              v = (unsigned long long)__double_as_longlong(w.val[i]);
+              q = ~w.pos[i];
+            }
+            const bool cand = i < d && !gt(tv, tq, v, q);
+            const uint32_t m = __ballot_sync(FULL_MASK, cand);
+            if (cand) {
+              const int at = n_c + __popc(m & ((1u << lane) - 1u));
+              if (at < REC_CANDS) { s_cv[at] = v; s_cq[at] = q; s_ci[at] = (uint32_t)i; }
+            }
+            n_c += __popc(m);
+          }
+          __syncwarp();
+          if (n_c <= REC_CANDS) {
+            for (int c = lane; c < n_c; c += 32) {
+              const unsigned long long v = s_cv[c];
+              const uint32_t q = s_cq[c];
+              int rank = 0;
+              for (int j = 0; j < n_c; ++j) rank += gt(s_cv[j], s_cq[j], v, q) ? 1 : 0;
+              if (rank < rounds) {
+                out[rank] = (int32_t)w.keys[w.occ[s_ci[c]]];
+                if (out_score) out_score[rank] = __longlong_as_double((long long)v);
+              }
+            }
+          }
+          if (lane == 0) s_selected = n_c <= REC_CANDS ? 1 : 0;
+        }
+        __syncthreads();
+        selected = s_selected != 0;
+      }
+      for (int r = 0; r < rounds && !selected; ++r) {
         unsigned long long bv = 0;
         uint32_t bp = 0xffffffffu, bi = 0xffffffffu;
         for (int i = tid; i < d; i += T) {
@@ -281,7 +369,8 @@ static void recency_caps(int32_t max_len, int32_t max_k, int64_t* lcap, int64_t*
   while (h < need) h <<= 1;
   *hs = h;
 }
-constexpr int RECENCY_BLOCKS = 1184;   // 8 per SM: the kernel is bound by latency (global-memory table, barriers), not by throughput
+constexpr int RECENCY_BLOCKS = 2368;   // 16 per SM: the kernel is bound by latency (global-memory table, barriers), not by throughput -
+                                       // sessions in flight are what counts (256 threads x 8 per SM: 4.5 ms; 128 x 16: see profiles/)
 
 extern "C" int64_t otto_recency_scratch_bytes(int32_t max_session_len, int32_t max_table_k) {
   int64_t lcap, hs;
@@ -337,7 +426,7 @@ extern "C" int otto_recency_scored(const OttoSessions* sessions, const int32_t* 
   p.slab = (uint64_t*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
   p.slab_words = recency_slab_words(lcap, hs);
   const int blocks = n_list < RECENCY_BLOCKS ? n_list : RECENCY_BLOCKS;
-  recency_long_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  recency_long_kernel<<<blocks, REC_THREADS, 0, (cudaStream_t)stream>>>(p);
   LAUNCH_CHECK();
   return OTTO_OK;
 }
