@@ -584,7 +584,7 @@ def run_b200(args):
                  "otable_block_kernel<512 threads> (bins <= 6144)",
                  "otable_block_kernel<256 threads> (bins <= 3072)",
                  "otable_block_kernel<128 threads> (bins <= 1536)",
-                 "reduce_block_kernel<hash table> (hand-overs, bins > 8192) + merge_split_rows_kernel"]
+                 "reduce_block_kernel<hash table> (hand-overs, bins > 6144) + merge_split_rows_kernel"]
         tier_of = [0, 3, 2, 1]       # launch order (warp, 512, 256, 128) -> index into stats.tier_records
         red_ms = [statistics.mean(r[i] for r in reduce_ms) for i in range(5)] if reduce_ms else [0.0] * 5
         tr = stats.get("tier_records", [0, 0, 0, 0])
