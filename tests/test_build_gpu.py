@@ -156,6 +156,29 @@ def test_tied_entries_hand_over_to_the_hash_table_kernel(cv, variant):
     assert top0 == list(range(10, 10 + getattr(cv, variant).k)), top0
 
 
+@pytest.mark.parametrize("variant", ["CLICKS", "CARTS_ORDERS"])
+def test_bins_at_the_tier_bounds(cv, variant):
+    """Rows of exactly 31 .. 6145 records around every bound of the reduce tiers (32: no table; 384: one warp; 1536 /
+    3072 / 6144: 128 / 256 / 512 threads; 6145: split into sub-bins) - once with all-distinct partners (a table at its
+    three-quarters fill) and once with 50 partners (every owner followed by ~n / 50 records)."""
+    sizes = [31, 32, 33, 383, 384, 385, 1535, 1536, 1537, 3071, 3072, 3073, 6143, 6144, 6145]
+    rng = np.random.default_rng(17)
+    rows, s, ts = [], 0, 1660000000
+    first_partner = 100
+    for i, n in enumerate(sizes):
+        for x, pool in ((i, n), (50 + i, 50)):           # aid x: n two-event sessions [x, partner]
+            for j in range(n):
+                y = first_partner + (j if pool == n else int(rng.integers(0, pool)))
+                ty = rng.choice([0, 1, 2], size=2, p=[0.6, 0.25, 0.15])
+                rows += [(s, x, ts, int(ty[0])), (s, y, ts + 1, int(ty[1]))]
+                s += 1
+                ts += int(rng.integers(1, 60))
+    df = pd.DataFrame(rows, columns=["session", "aid", "ts", "type"])
+    frame = frame_from_df(df, first_partner + max(sizes) + 5)
+    got, stats = check_against_oracle(cv, frame, getattr(cv, variant), f"{variant} tier bounds")
+    assert stats["split_rows"] == 2 and all(r > 0 for r in stats["tier_records"][:3])
+
+
 def test_accumulator_width_guard(cv):
     """Bins beyond the owner-table tiers go to the hash-table kernel (24-bit counts, 40-bit time sums): a layout in which
     an entry could exceed them is refused instead of wrapping silently."""
