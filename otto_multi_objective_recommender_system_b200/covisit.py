@@ -451,3 +451,84 @@ def build_topk(csr: EventCSR, spec: CovisitSpec, exact: bool = False):
     b = CovisitBuilder(csr, spec, exact=exact)
     t = b.build()
     return t, b.stats.as_dict()
+
+
+class FramePipeline:
+    """Builds one matrix per frame from a STREAM of pinned host frames, two frames in flight: while frame i is being
+    ingested and built on the compute stream, frame i + 1 is uploaded on a copy stream and the rows of frame i - 1
+    travel back (PCIe is full duplex).  A step of the pipeline costs max(upload, build + rows back) instead of their
+    sum; every frame is still uploaded, built and read back in full.  Use: `for ax, ay, w in FramePipeline(spec,
+    device).run(frames): ...` - the yielded tensors are pinned host views that stay valid until two frames later.
+    The reference has nothing comparable (its builder is absent); the case it serves is a sequence of different
+    frames (train + validation, train + test, the chunked frames of a larger catalogue)."""
+
+    def __init__(self, spec: CovisitSpec, device, exact: bool = False):
+        self.spec, self.device, self.exact = spec, torch.device(device), exact
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.out_stream = torch.cuda.Stream(self.device)
+        self.slots = [dict(cols=None, uploaded=None, consumed=None, out=None, out_done=None, builder=None) for _ in range(2)]
+
+    def _upload(self, slot: dict, frame: EventFrame) -> None:
+        if not all(t.is_pinned() for t in (frame.session, frame.aid, frame.ts, frame.type)):
+            raise ValueError("FramePipeline needs pinned host frames")
+        n = len(frame)
+        if slot["cols"] is None or slot["cols"][0].numel() < n:
+            slot["cols"] = [torch.empty(n, dtype=d, device=self.device) for d in (torch.int32, torch.int32, torch.int32, torch.uint8)]
+        with torch.cuda.stream(self.copy_stream):
+            if slot["consumed"] is not None:
+                self.copy_stream.wait_event(slot["consumed"])     # the build that read this slot's columns is done
+            for dst, src in zip(slot["cols"], (frame.session, frame.aid, frame.ts, frame.type)):
+                dst[:n].copy_(src, non_blocking=True)
+            slot["uploaded"] = torch.cuda.Event()
+            slot["uploaded"].record(self.copy_stream)
+        slot["n"], slot["n_aids"] = n, frame.n_aids
+
+    def _build(self, slot: dict) -> None:
+        st = torch.cuda.current_stream(self.device)
+        st.wait_event(slot["uploaded"])
+        n = slot["n"]
+        f = EventFrame(*(c[:n] for c in slot["cols"]), n_aids=slot["n_aids"])
+        csr = ingest(f, "asc", device=self.device)
+        b = CovisitBuilder(csr, self.spec, exact=self.exact)
+        old = slot["builder"]
+        if old is not None and old.workspace.numel() >= b.workspace.numel():
+            b.workspace, b.records, b.scratch, b.table = old.workspace, old.records, old.scratch, old.table
+        slot["builder"] = b
+        rows = b.build().to_rows()
+        slot["consumed"] = torch.cuda.Event()
+        slot["consumed"].record(st)
+        if slot["out_done"] is not None:
+            slot["out_done"].synchronize()                        # the previous rows of this slot have left
+        if slot["out"] is None or any(o.numel() < r.numel() for o, r in zip(slot["out"], rows)):
+            slot["out"] = [torch.empty(max(1, r.numel()), dtype=r.dtype, pin_memory=True) for r in rows]
+        self.out_stream.wait_event(slot["consumed"])
+        with torch.cuda.stream(self.out_stream):
+            views = []
+            for o, r in zip(slot["out"], rows):
+                o[:r.numel()].copy_(r, non_blocking=True)
+                r.record_stream(self.out_stream)
+                views.append(o[:r.numel()])
+            slot["out_done"] = torch.cuda.Event()
+            slot["out_done"].record(self.out_stream)
+        slot["views"] = views
+
+    def run(self, frames):
+        it = iter(frames)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        self._upload(self.slots[0], nxt)
+        i, pending = 0, None
+        while nxt is not None:
+            cur = self.slots[i & 1]
+            nxt = next(it, None)
+            if nxt is not None:
+                self._upload(self.slots[(i + 1) & 1], nxt)         # enqueued before the host starts driving the build
+            self._build(cur)
+            if pending is not None:
+                pending["out_done"].synchronize()
+                yield tuple(pending["views"])
+            pending = cur
+            i += 1
+        pending["out_done"].synchronize()
+        yield tuple(pending["views"])

@@ -319,6 +319,21 @@ def test_ascending_frames_with_runs_of_equal_ts_across_the_tail_cut(cv, variant)
     assert _tables_equal(got, want) and torch.equal(got.cnt, want.cnt) and torch.equal(got.tsum, want.tsum)
 
 
+def test_frame_pipeline_equals_sequential_builds(cv):
+    """FramePipeline (upload of frame i + 1 on a copy stream while frame i is built, rows of frame i - 1 on their way
+    back): the rows of every frame equal a plain ingest + build of that frame, for frames of different sizes."""
+    from otto_multi_objective_recommender_system_b200 import synth
+    frames = [synth_frame(n, 300, seed=s) for n, s in ((2000, 1), (3500, 2), (800, 3), (2600, 4), (2000, 1))]
+    pinned = [synth.EventFrame(*(t.cpu().contiguous().pin_memory() for t in (f.session, f.aid, f.ts, f.type)), n_aids=f.n_aids)
+              for f in frames]
+    got = [tuple(x.clone() for x in rows) for rows in cv.FramePipeline(cv.CARTS_ORDERS, "cuda:0").run(pinned)]
+    assert len(got) == len(frames)
+    for f, (ax, ay, w) in zip(frames, got):
+        t, _ = cv.build_topk(cv.ingest(f, "desc", device="cuda:0"), cv.CARTS_ORDERS)
+        wx, wy, ww = (x.cpu() for x in t.to_rows())
+        assert torch.equal(ax, wx) and torch.equal(ay, wy) and torch.equal(w.view(torch.int32), ww.view(torch.int32))
+
+
 def test_build_is_deterministic(cv):
     frame = synth_frame(8000, 800, seed=2)
     csr = cv.ingest(frame, "desc", device="cuda:0")
