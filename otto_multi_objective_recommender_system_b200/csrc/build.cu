@@ -729,46 +729,133 @@ __global__ void init_sub_cur_kernel(const unsigned long long* __restrict__ bin_o
     sub_cur[b] = (uint32_t)bin_off[b];
 }
 
+// A tile is 16 KB of CONTIGUOUS staged records: it is brought into shared memory by one bulk asynchronous copy
+// (cp.async.bulk.shared::cluster.global, the 1-D TMA path: UBLKCP in SASS) that thread 0 issues one tile ahead into
+// the other of two buffers and that completes on an mbarrier - the loads of a tile cost the SM no issue slots and no
+// registers, and the next tile streams in while this one is histogrammed and moved (round 1 / early round 2: eight
+// LDG.64 per thread up front, which held 16 registers per thread and left the copy engine idle between tiles).
+// Bulk copies need 16-byte aligned addresses and sizes and a record is 8 bytes: the copy covers the 16-byte aligned
+// span inside the tile's bytes; a first or last record outside it is read with a plain load.
+constexpr int PART_STAGES = 2;
+constexpr uint32_t PART_BUF_BYTES = PART_TILE * 8 + 16;
+
+struct PartTile {
+  uint32_t b0, nb, m, head;      // first bin of the row, its sub-bins, records of the tile, bytes in front of record 0 in the buffer
+  uint32_t bulk_bytes, pad;
+  const uint2* src;              // record 0 of the tile in the staging area
+};
+
+__device__ __forceinline__ void mbar_init(uint32_t bar_s, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar_s, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar_s) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar_s, uint32_t phase) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar_s), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void* src, uint32_t bytes, uint32_t bar_s) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s), "l"(src),
+               "r"(bytes), "r"(bar_s) : "memory");
+}
+
+template <bool MOVE>
+constexpr size_t partition_smem() { return (size_t)PART_STAGES * PART_BUF_BYTES + (size_t)MAX_SUB_BINS * 4 * (MOVE ? 2 : 1); }
+
 template <bool MOVE>
 __global__ void __launch_bounds__(PART_THREADS) partition_kernel(const PartParams p) {
-  __shared__ uint32_t s_hist[MAX_SUB_BINS];
-  __shared__ uint32_t s_base[MOVE ? MAX_SUB_BINS : 1];
+  extern __shared__ __align__(128) unsigned char part_smem[];
+  __shared__ __align__(8) unsigned long long s_bar[PART_STAGES];
+  __shared__ PartTile s_tile[PART_STAGES];
+  uint32_t* s_hist = (uint32_t*)(part_smem + PART_STAGES * PART_BUF_BYTES);
+  uint32_t* s_base = s_hist + MAX_SUB_BINS;     // MOVE only
+  const uint32_t buf_s = (uint32_t)__cvta_generic_to_shared(part_smem);
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(s_bar);
   unsigned long long n_tiles = *p.n_tiles;
   if ((int64_t)n_tiles > p.tile_cap) n_tiles = (unsigned long long)p.tile_cap;
-  const uint2* stage = p.records + p.row_off[p.A];
-  for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+  const uint2* stage_area = p.records + p.row_off[p.A];
+  // thread 0: metadata of tile t into s_tile[st], bulk copy of its aligned span into buffer st
+  auto issue = [&](unsigned long long t, int st) {
     const uint32_t x = p.hot_rows[p.tile_row[t]];
-    const uint32_t b0 = p.bin_base[x], nb = p.bin_base[x + 1] - b0;
+    PartTile ti;
+    ti.b0 = p.bin_base[x];
+    ti.nb = p.bin_base[x + 1] - ti.b0;
     const uint32_t n = p.row_count[x];
     const uint32_t t0 = p.tile_idx[t] * PART_TILE;
-    const uint2* src = stage + p.hot_off[x] + t0;
-    const uint32_t m = min((uint32_t)PART_TILE, n - t0);
-    for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS) s_hist[j] = 0u;
-    uint2 r[PART_PER_THREAD];
-#pragma unroll
-    for (int u = 0; u < PART_PER_THREAD; ++u) {
-      const uint32_t j = u * PART_THREADS + threadIdx.x;
-      r[u] = j < m ? ld_stream_u2(src + j) : make_uint2(0, 0);
+    ti.m = min((uint32_t)PART_TILE, n - t0);
+    ti.src = stage_area + p.hot_off[x] + t0;
+    const uintptr_t a = (uintptr_t)ti.src, e = a + (uintptr_t)ti.m * 8;
+    const uintptr_t a0 = (a + 15) & ~(uintptr_t)15, a1 = e & ~(uintptr_t)15;     // aligned span inside [a, e)
+    ti.head = (uint32_t)(a0 - a);                                                 // 0 or 8: record 0 lies in front of the span
+    ti.bulk_bytes = a1 > a0 ? (uint32_t)(a1 - a0) : 0u;
+    ti.pad = 0;
+    s_tile[st] = ti;
+    if (ti.bulk_bytes) {
+      mbar_expect_tx(bar_s + st * 8, ti.bulk_bytes);
+      bulk_g2s(buf_s + st * PART_BUF_BYTES, (const void*)a0, ti.bulk_bytes, bar_s + st * 8);
+    } else {
+      mbar_arrive(bar_s + st * 8);
     }
+  };
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < PART_STAGES; ++i) mbar_init(bar_s + i * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+  }
+  __syncthreads();
+  uint32_t it = 0;
+  for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    const int st = it & 1;
+    // the other buffer was consumed in the previous iteration (trailing barrier): refill it while this tile is processed
+    if (threadIdx.x == 0 && t + gridDim.x < n_tiles) issue(t + gridDim.x, st ^ 1);
+    const PartTile ti = s_tile[st];
+    for (uint32_t j = threadIdx.x; j < ti.nb; j += PART_THREADS) s_hist[j] = 0u;
+    mbar_wait(bar_s + st * 8, (it >> 1) & 1u);
+    const uint32_t tile_s = buf_s + st * PART_BUF_BYTES;
+    // record j: inside the copied span at byte 8 j - head, else (first / last record of a misaligned tile) from global memory
+    auto record = [&](uint32_t j) {
+      const uint32_t off = 8u * j - ti.head;          // wraps to 0xfffffff8 for j = 0 with head = 8: outside the span
+      uint2 r;
+      if (ti.bulk_bytes >= 8u && off <= ti.bulk_bytes - 8u) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(tile_s + off) : "memory");
+      else r = ld_stream_u2(ti.src + j);
+      return r;
+    };
     __syncthreads();
     uint32_t sub[PART_PER_THREAD], rank[PART_PER_THREAD];
 #pragma unroll
     for (int u = 0; u < PART_PER_THREAD; ++u) {
-      sub[u] = sub_bin(r[u].x, nb);
+      const uint32_t j = u * PART_THREADS + threadIdx.x;
+      sub[u] = 0;
       rank[u] = 0;
-      if (u * PART_THREADS + threadIdx.x < m) rank[u] = atomicAdd(&s_hist[sub[u]], 1u);
+      if (j < ti.m) {
+        sub[u] = sub_bin(record(j).x, ti.nb);
+        rank[u] = atomicAdd(&s_hist[sub[u]], 1u);
+      }
     }
     __syncthreads();
     if (!MOVE) {
-      for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS)
-        if (s_hist[j]) atomicAdd(&p.bin_cnt[b0 + j], s_hist[j]);
+      for (uint32_t j = threadIdx.x; j < ti.nb; j += PART_THREADS)
+        if (s_hist[j]) atomicAdd(&p.bin_cnt[ti.b0 + j], s_hist[j]);
     } else {
-      for (uint32_t j = threadIdx.x; j < nb; j += PART_THREADS)
-        if (s_hist[j]) s_base[j] = atomicAdd(&p.sub_cur[b0 + j], s_hist[j]);
+      for (uint32_t j = threadIdx.x; j < ti.nb; j += PART_THREADS)
+        if (s_hist[j]) s_base[j] = atomicAdd(&p.sub_cur[ti.b0 + j], s_hist[j]);
       __syncthreads();
 #pragma unroll
-      for (int u = 0; u < PART_PER_THREAD; ++u)
-        if (u * PART_THREADS + threadIdx.x < m) p.records[s_base[sub[u]] + rank[u]] = r[u];
+      for (int u = 0; u < PART_PER_THREAD; ++u) {
+        const uint32_t j = u * PART_THREADS + threadIdx.x;
+        if (j < ti.m) p.records[s_base[sub[u]] + rank[u]] = record(j);
+      }
     }
     __syncthreads();
   }
@@ -1211,7 +1298,9 @@ static int partition_records(const Layout& L, void* workspace, void* records, cu
   CUDA_TRY(cudaMemsetAsync(WS(unsigned long long, stats) + 5, 0, 8, st));
   partition_tiles_kernel<<<(unsigned)ceil_div(L.Hmax, 256), 256, 0, st>>>(pp);
   LAUNCH_CHECK();
-  partition_kernel<false><<<n_sm * 6, PART_THREADS, 0, st>>>(pp);
+  CUDA_TRY(cudaFuncSetAttribute(partition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)partition_smem<false>()));
+  CUDA_TRY(cudaFuncSetAttribute(partition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)partition_smem<true>()));
+  partition_kernel<false><<<n_sm * 4, PART_THREADS, partition_smem<false>(), st>>>(pp);
   LAUNCH_CHECK();
   if ((rc = exclusive_scan<uint32_t, unsigned long long>(WS(uint32_t, bin_cnt), L.Bmax, WS(unsigned long long, bin_off),
                                                          WS(unsigned long long, scan), st)))
@@ -1219,7 +1308,7 @@ static int partition_records(const Layout& L, void* workspace, void* records, cu
   init_sub_cur_kernel<<<592, 256, 0, st>>>(WS(unsigned long long, bin_off), WS(uint32_t, bin_base), A, WS(uint32_t, sub_cur));
   LAUNCH_CHECK();
   if (g_profile) CUDA_TRY(cudaEventRecord(g_prof_sc[2], st));
-  partition_kernel<true><<<n_sm * 4, PART_THREADS, 0, st>>>(pp);
+  partition_kernel<true><<<n_sm * 3, PART_THREADS, partition_smem<true>(), st>>>(pp);
   LAUNCH_CHECK();
   if (g_profile) {
     CUDA_TRY(cudaEventRecord(g_prof_sc[3], st));
