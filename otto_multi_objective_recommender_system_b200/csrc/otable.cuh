@@ -65,7 +65,7 @@ struct OTable {
     constexpr uint32_t MASK = SLOTS * 4 - 1;
     const uint32_t k0 = y0 + 1u, k1 = y1 + 1u;
     uint32_t a0 = ((y0 * 0x9E3779B1u) >> (32 - LOG)) << 2, a1 = ((y1 * 0x9E3779B1u) >> (32 - LOG)) << 2;
-    uint32_t prev0 = 1u, prev1 = 1u;      // has == false: neither owner (0) nor follower (k >= 1 ... k == 1 only for y == 0, see below)
+    uint32_t prev0 = 1u, prev1 = 1u;      // placeholders of absent records: every use below is guarded by has0 / has1
     if (has0) prev0 = atoms_cas(keys_s + a0, KEY_NONE, k0);
     if (has1) prev1 = atoms_cas(keys_s + a1, KEY_NONE, k1);
     if (has0 && prev0 != KEY_NONE && prev0 != k0) {
