@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--split-ub", type=int, default=0)
     ap.add_argument("--nccl-exchange", action="store_true", help="N > 1: exchange records with an NCCL all-to-all instead of NVLink peer memory")
     ap.add_argument("--peer-read", action="store_true", help="N > 1: owners read the senders' slabs over NVLink (the variant before the owner-direct scatter)")
+    ap.add_argument("--staged", type=int, default=None, choices=[0, 1],
+                    help="N > 1: 1 = staged scatter (sender-side combining, owners pull their buckets over NVLink), 0 = direct "
+                         "scatter (NVLink stores); default: distributed.STAGED_DEFAULT / OTTO_STAGED")
     ap.add_argument("--dist-timing", action="store_true", help="N > 1: synchronise between phases and print their times (stderr)")
     return ap.parse_args()
 
@@ -419,6 +422,8 @@ def run_b200(args):
     E, S, A = csr.n_events, csr.n_sessions, csr.n_aids
     if args.peer_read:
         os.environ["OTTO_OWNER_DIRECT"] = "0"
+    if args.staged is not None:
+        os.environ["OTTO_STAGED"] = str(args.staged)
     peer = distributed.PeerRecords(dev) if world > 1 and not args.nccl_exchange else None
     backend = distributed.GpuRankBackend(csr, spec, peer=peer)
     builder = backend.b
@@ -510,8 +515,11 @@ def run_b200(args):
             nvlink = {"off_rank_bytes_per_gpu_max": remote_max, "scatter_ms": sc,
                       "achieved_gbs": remote_max / (sc * 1e-3) / 1e9 if sc else None,
                       "peak_gbs": 770.0, "peak_source": "measured peer copy per direction (B200_PROFILING.md); nominal 900",
-                      "what": "bytes the scatter kernel stores into other owners' HBM (NVLink stores) / scatter phase time "
-                              "(kernel + the 4-byte all-reduce that orders 'all scatters have landed')"}
+                      "what": ("bytes the place pass reads out of the other ranks' staging buffers (large NVLink reads) / scatter "
+                               "phase time (bucket plan + pass A into the local staging buffer + the 4-byte all-reduce 'every "
+                               "rank has staged' + place pass)") if backend.staged else
+                              ("bytes the scatter kernel stores into other owners' HBM (NVLink stores) / scatter phase time "
+                               "(kernel + the 4-byte all-reduce that orders 'all scatters have landed')")}
     if world == 1:
         # per-kernel times of the reduce phase: three extra steps OUTSIDE the timed region with the library's event
         # bracketing on (profiled calls run the block kernels back to back instead of concurrently)
@@ -627,6 +635,8 @@ def run_b200(args):
                     "peak_source": peak_src, "algorithmic_bytes": bytes_all,
                     "exchange": {"transport": ("nccl all_to_all" if args.nccl_exchange else "peer read (owners read the senders' slabs over NVLink)"
                                                if not backend.owner_direct else
+                                               "staged scatter (runs combined in coarse buckets of the sender's staging buffer, "
+                                               "owners pull their buckets over NVLink and place the records)" if backend.staged else
                                                "owner-direct scatter (records stored into the owner's buffer over NVLink)"),
                                  "record_bytes_total": sent, "per_gpu_per_step": sent / world,
                                  "note": "record_bytes_total includes the records a rank keeps for itself; nvlink = off-rank only",

@@ -289,6 +289,33 @@ int otto_covisit_scatter_owned(const OttoEvents* ev, const OttoCovisitSpec* spec
 int otto_covisit_partition(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
                            void* records, int64_t records_capacity, void* stream);
 
+/* Staged scatter (multi-GPU, sender-side combining): the alternative to otto_covisit_scatter_owned for links that
+ * punish short stores.  The direct scatter crosses NVLink as ~63-byte runs (one run = the pairs of one event);
+ * here a rank first appends its runs to COARSE buckets of its OWN staging buffer (bucket = 2^20 records of the
+ * global row order, each record packed into 64 bits as aid_y | v | row - first row of the bucket), and the owner of
+ * a row range then streams the segments of its buckets out of every rank's staging buffer (large contiguous reads
+ * through the peer mapping) and places the records (final position of an ordinary row, staging area of a hot row).
+ *   ... otto_covisit_count_finish_owned -> otto_covisit_stage_plan (one synchronisation; staged_records_host[g] =
+ *   records rank g stages, identical on every rank; or, to save the synchronisation: stage_plan with a NULL
+ *   staged_records_host BEFORE count_finish_owned and otto_covisit_stage_totals after it) -> peers map each other's
+ *   staging buffers ->
+ *   otto_covisit_scatter_staged -> any collective (orders "every rank has staged") -> otto_covisit_place_staged
+ *   into MY record buffer -> otto_covisit_partition -> otto_covisit_reduce as before.
+ * counts_all [n_ranks][n_aids]: the all-gathered per-row counts (NULL with one rank = the workspace's own).
+ * OTTO_EOVERFLOW: the 64-bit staged record cannot carry aid_y, v and the row (use the direct scatter).
+ * The reference has no distributed code; this replaces nothing of it. */
+int64_t otto_covisit_stage_plan_bytes(const OttoCovisitSpec* spec, int64_t n_sessions, int64_t n_events, int32_t n_ranks);
+int otto_covisit_stage_plan(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
+                            const uint32_t* counts_all, int32_t n_ranks, int32_t rank, void* plan, int64_t plan_bytes,
+                            int64_t* staged_records_host, void* stream);
+int otto_covisit_stage_totals(const OttoCovisitSpec* spec, int64_t n_sessions, int64_t n_events, void* plan, int32_t n_ranks,
+                              int64_t* staged_records_host, void* stream);
+int otto_covisit_scatter_staged(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
+                                void* plan, int32_t n_ranks, void* staged, void* stream);
+int otto_covisit_place_staged(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
+                              void* plan, int32_t n_ranks, const void* const* staged_host, int32_t aid_lo, int32_t aid_hi,
+                              void* records, int64_t records_capacity, void* stream);
+
 /* One-shot single-GPU build; the pair records and the reduce scratch are carved from the workspace after
  * the fixed part.  Returns OTTO_ENOSPC (stats_host->pairs / bins set) when the workspace cannot hold
  * them; otto_covisit_build_bytes (pairs = stats.pairs + stats.hot_pairs) gives the size to retry with. */

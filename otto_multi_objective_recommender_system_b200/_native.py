@@ -136,6 +136,11 @@ _SIGNATURES = {
     "otto_covisit_plan_scratch_bytes": (i64, [i32]),
     "otto_covisit_plan_owners": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, i64, P(i32), vp]),
     "otto_covisit_scatter_owned": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, P(OttoOwnerPlan), vp]),
+    "otto_covisit_stage_plan_bytes": (i64, [P(OttoCovisitSpec), i64, i64, i32]),
+    "otto_covisit_stage_plan": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, vp, i32, i32, vp, i64, P(i64), vp]),
+    "otto_covisit_stage_totals": (C.c_int, [P(OttoCovisitSpec), i64, i64, vp, i32, P(i64), vp]),
+    "otto_covisit_scatter_staged": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, vp, i32, vp, vp]),
+    "otto_covisit_place_staged": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, vp, i32, P(vp), i32, i32, vp, i64, vp]),
     "otto_covisit_partition": (C.c_int, [P(OttoEvents), P(OttoCovisitSpec), vp, i64, vp, i64, vp]),
     "otto_covisit_reduce_scratch_bytes": (i64, [P(OttoCovisitSpec), i64, i64]),
     "otto_covisit_reduce": (C.c_int, [P(OttoCovisitSpec), vp, vp, i64, i64, i32, i32, P(OttoPairSegment), i32, vp,

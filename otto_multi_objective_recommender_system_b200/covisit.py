@@ -381,6 +381,52 @@ class CovisitBuilder:
             N.check(self.lib.otto_covisit_scatter_owned(C.byref(self.ev), C.byref(self.cspec), self.workspace.data_ptr(),
                                                         self.workspace.numel(), C.byref(plan), self._st()))
 
+    # -- staged scatter (multi-GPU, sender-side combining; protocol in include/otto_covisit.h) ----
+    def stage_plan(self, counts_all: torch.Tensor | None, world: int, rank: int, sync: bool = True):
+        """Bucket plan from counts_all: [world, n_aids] per-row counts of every rank (None with one rank = the
+        workspace's own, after count_finish).  sync=True -> records every rank will stage (the same list on every
+        rank; one synchronisation); sync=False enqueues only - read the list with stage_totals() later, e.g. behind
+        the synchronisation of count_finish_owned."""
+        need = int(self.lib.otto_covisit_stage_plan_bytes(C.byref(self.cspec), self.csr.n_sessions, self.csr.n_events, world))
+        if need < 0:
+            raise ValueError(f"staged scatter supports 1..{N.MAX_OWNERS} ranks")
+        if getattr(self, "_stage_scratch", None) is None or self._stage_scratch.numel() < need:
+            self._stage_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        totals = (C.c_int64 * N.MAX_OWNERS)()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.otto_covisit_stage_plan(C.byref(self.ev), C.byref(self.cspec), self.workspace.data_ptr(),
+                                                     self.workspace.numel(), counts_all.data_ptr() if counts_all is not None else None,
+                                                     world, rank, self._stage_scratch.data_ptr(), self._stage_scratch.numel(),
+                                                     totals if sync else None, self._st()))
+        return [int(totals[g]) for g in range(world)] if sync else None
+
+    def stage_totals(self, world: int) -> list:
+        totals = (C.c_int64 * N.MAX_OWNERS)()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.otto_covisit_stage_totals(C.byref(self.cspec), self.csr.n_sessions, self.csr.n_events,
+                                                       self._stage_scratch.data_ptr(), world, totals, self._st()))
+        return [int(totals[g]) for g in range(world)]
+
+    def scatter_staged(self, world: int, staged_ptr: int) -> None:
+        """Pass A: this rank's pairs into the coarse buckets of its staging buffer (device pointer)."""
+        with torch.cuda.device(self.device):
+            N.check(self.lib.otto_covisit_scatter_staged(C.byref(self.ev), C.byref(self.cspec), self.workspace.data_ptr(),
+                                                         self.workspace.numel(), self._stage_scratch.data_ptr(), world, staged_ptr,
+                                                         self._st()))
+
+    def place_staged(self, staged_ptrs, aid_lo: int, aid_hi: int) -> torch.Tensor:
+        """Pass B at the owner of rows [aid_lo, aid_hi): every rank's staging buffer (as mapped here) -> self.records."""
+        P = int(self.stats.pairs) + int(self.stats.hot_pairs)
+        if self.records is None or self.records.numel() < max(P, 1):
+            self.records = torch.empty(max(P, 1), dtype=torch.int64, device=self.device)
+        world = len(staged_ptrs)
+        ptrs = (C.c_void_p * world)(*[int(q) for q in staged_ptrs])
+        with torch.cuda.device(self.device):
+            N.check(self.lib.otto_covisit_place_staged(C.byref(self.ev), C.byref(self.cspec), self.workspace.data_ptr(),
+                                                       self.workspace.numel(), self._stage_scratch.data_ptr(), world, ptrs,
+                                                       aid_lo, aid_hi, self.records.data_ptr(), max(P, 1), self._st()))
+        return self.records
+
     def partition(self) -> torch.Tensor:
         """Second half of scatter() on self.records (already filled, here by every rank of the box)."""
         P = int(self.stats.pairs) + int(self.stats.hot_pairs)

@@ -1359,6 +1359,382 @@ extern "C" int otto_covisit_partition(const OttoEvents* ev, const OttoCovisitSpe
   return partition_records(L, workspace, records, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------ staged scatter (sender-side combining)
+//
+// The direct scatter appends ~63-byte runs at 1.86 M row frontiers: on one GPU the partial sectors cost DRAM fills
+// (profiles/r02_experiments.md), across NVLink every run is a small store packet (330 GB/s per direction against
+// 550-590 GB/s for large transfers).  Staged form: pass A appends the same runs to COARSE buckets of this rank's own
+// staging buffer (a bucket = 2^STAGE_LOGA consecutive aid_x rows, ~900 write frontiers for OTTO: L2 combines the runs
+// into full lines), each record carrying its row relative to the bucket; pass B runs at the OWNER of the rows: it
+// streams the segments of its buckets out of every sender's staging buffer (large contiguous reads - over NVLink for
+// the peers' buffers) and places the records at their final position (ordinary rows) or in the staging area of the
+// hot rows, with one cursor atomic per run.  Everything behind it (hot-row partition, reduce) is unchanged.
+constexpr int PLACE_THREADS = 256, PLACE_PER_THREAD = 4, PLACE_TILE = PLACE_THREADS * PLACE_PER_THREAD;
+// info words: [2] tiles of the place pass, [STAGE_INFO_TOTAL + g] records rank g stages
+constexpr int STAGE_INFO_TOTAL = 8, STAGE_INFO_WORDS = STAGE_INFO_TOTAL + OTTO_MAX_OWNERS;
+
+struct StageLayout {
+  int64_t A, G, NB, Tmax;
+  int64_t bcnt, bo, bcur, tiles, info, total;
+};
+
+static StageLayout stage_layout(const OttoCovisitSpec* spec, int64_t n_sessions, int64_t n_events, int n_ranks) {
+  StageLayout S;
+  S.A = spec->n_aids;
+  S.G = n_ranks;
+  S.NB = ceil_div(S.A, (int64_t)1 << STAGE_LOGA);
+  int64_t Ecap = n_events < n_sessions * spec->tail_n ? n_events : n_sessions * spec->tail_n;
+  const int64_t Eg = spec->global_events > n_events ? spec->global_events : (Ecap > 1 ? Ecap : 1);
+  const int64_t Pmax = Eg * (spec->tail_n - 1);                  // every tail event pairs with at most tail_n - 1 others
+  S.Tmax = Pmax / PLACE_TILE + (int64_t)n_ranks * S.NB + 1;      // tiles of a place pass <= sum over (rank, bucket) of ceil(n / tile)
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { int64_t at = o; o = align_up(o + bytes, 256); return at; };
+  S.bcnt = take(S.G * (S.NB + 1) * 8);
+  S.bo = take(S.G * (S.NB + 1) * 8);
+  S.bcur = take((S.NB + 1) * 4 * STAGE_CUR_STRIDE);
+  S.tiles = take(S.Tmax * 16);
+  S.info = take(STAGE_INFO_WORDS * 8);
+  S.total = o;
+  return S;
+}
+#define SP(type, field) ((type*)((char*)plan + S.field))
+
+// bcnt[g][b] := records of bucket b that rank g stages = sum of its counts over the bucket's rows; one block per bucket
+__global__ void __launch_bounds__(256) stage_count_kernel(const uint32_t* __restrict__ counts, int G, int64_t A, int64_t nb_stride,
+                                                            unsigned long long* __restrict__ bo) {
+  const int64_t b = blockIdx.x;
+  const int64_t lo = b << STAGE_LOGA, hi = min(A, (b + 1) << STAGE_LOGA);
+  __shared__ unsigned long long s_part[8];
+  for (int g = 0; g < G; ++g) {
+    unsigned long long sum = 0;
+    for (int64_t x = lo + threadIdx.x; x < hi; x += 256) sum += counts[(int64_t)g * A + x];
+    for (int o = 16; o > 0; o >>= 1) sum += shfl_u64(sum, lane_id() ^ o);
+    if (lane_id() == 0) s_part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long t = 0;
+      for (int w = 0; w < 8; ++w) t += s_part[w];
+      bo[(int64_t)g * nb_stride + b] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// bo[g][b] := where rank g's segment of bucket b starts in its staging buffer: exclusive scan of the counts rounded up
+// to even (a segment starts on a 16-byte boundary, which the bulk copies of the place pass need); one block per rank;
+// bo[g][NB] and info[STAGE_INFO_TOTAL + g] = the size of the rank's staging buffer; the staging cursors of `rank`
+// start at its offsets
+__global__ void __launch_bounds__(1024) stage_scan_kernel(const unsigned long long* __restrict__ bcnt, unsigned long long* __restrict__ bo,
+                                                           int64_t nb, int rank, uint32_t* __restrict__ bcur, unsigned long long* info) {
+  __shared__ unsigned long long s_carry, s_warp[32];
+  const int g = blockIdx.x;
+  const unsigned long long* cnt = bcnt + (int64_t)g * (nb + 1);
+  unsigned long long* row = bo + (int64_t)g * (nb + 1);
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t b0 = 0; b0 <= nb; b0 += 1024) {
+    const int64_t b = b0 + threadIdx.x;
+    const unsigned long long v = b < nb ? (cnt[b] + 1ull) & ~1ull : 0ull;
+    unsigned long long inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long up = shfl_u64(inc, (int)lane_id() - o >= 0 ? (int)lane_id() - o : (int)lane_id());
+      if ((int)lane_id() >= o) inc += up;
+    }
+    if (lane_id() == 31) s_warp[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    unsigned long long base = s_carry;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) base += s_warp[w];
+    const unsigned long long excl = base + inc - v;
+    if (b <= nb) row[b] = excl;
+    if (b < nb && g == rank) bcur[b * STAGE_CUR_STRIDE] = (uint32_t)excl;
+    if (b == nb) info[STAGE_INFO_TOTAL + g] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = base + inc;
+    __syncthreads();
+  }
+}
+
+extern "C" int64_t otto_covisit_stage_plan_bytes(const OttoCovisitSpec* spec, int64_t n_sessions, int64_t n_events, int32_t n_ranks) {
+  if (check_spec(spec) || n_ranks < 1 || n_ranks > OTTO_MAX_OWNERS) return -1;
+  return stage_layout(spec, n_sessions, n_events, n_ranks).total;
+}
+
+// record packing: aid_y in y_bits, v in v_bits, the row inside its bucket in STAGE_LOGA bits
+static int stage_bits(const OttoCovisitSpec* spec, uint32_t* y_bits, uint32_t* v_bits) {
+  uint32_t yb = 1;
+  while (yb < 31 && (1ll << yb) < (int64_t)spec->n_aids) ++yb;
+  unsigned long long vmax = 1;
+  if (spec->weight_mode == OTTO_WEIGHT_TIME) vmax = (unsigned long long)((int64_t)spec->ts_max - spec->ts_min);
+  if (spec->weight_mode == OTTO_WEIGHT_TYPE)
+    for (int i = 0; i < 3; ++i)
+      if ((unsigned long long)spec->type_weight[i] > vmax) vmax = (unsigned long long)spec->type_weight[i];
+  uint32_t vb = 1;
+  while (vb < 32 && (1ull << vb) <= vmax) ++vb;
+  *y_bits = yb;
+  *v_bits = vb;
+  if (yb + vb + STAGE_LOGA > 64) {
+    otto_set_error("a staged record cannot carry %u + %u + %d bits: use the direct scatter", yb, vb, STAGE_LOGA);
+    return OTTO_EOVERFLOW;
+  }
+  return OTTO_OK;
+}
+
+// staged_records_host[g] := records rank g stages (the size of its staging buffer), from a plan that
+// otto_covisit_stage_plan has been enqueued for on `stream`.  Synchronises (cheap behind a synchronising call such as
+// otto_covisit_count_finish_owned).
+extern "C" int otto_covisit_stage_totals(const OttoCovisitSpec* spec, int64_t n_sessions, int64_t n_events, void* plan, int32_t n_ranks,
+                                         int64_t* staged_records_host, void* stream) {
+  int rc = check_spec(spec);
+  if (rc) return rc;
+  if (!plan || !staged_records_host || n_ranks < 1 || n_ranks > OTTO_MAX_OWNERS) { otto_set_error("bad argument"); return OTTO_EINVAL; }
+  const StageLayout S = stage_layout(spec, n_sessions, n_events, n_ranks);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long h[STAGE_INFO_WORDS];
+  CUDA_TRY(cudaMemcpyAsync(h, SP(char, info), sizeof(h), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (int g = 0; g < n_ranks; ++g) {
+    const unsigned long long total = h[STAGE_INFO_TOTAL + g];
+    if (total >= (1ull << 32)) { otto_set_error("rank %d would stage %llu records; the limit is 2^32 - 1", g, total); return OTTO_EINVAL; }
+    staged_records_host[g] = (int64_t)total;
+  }
+  return OTTO_OK;
+}
+
+// Plan of the staged scatter.  counts_all: [n_ranks][n_aids] pairs per row of every rank (one rank: NULL = the
+// workspace's own row counts).  staged_records_host[g] = records rank g will stage (every rank computes all of them,
+// so the staging buffers can be sized without a collective; NULL = do not synchronise, read them later with
+// otto_covisit_stage_totals); OTTO_EOVERFLOW when the packed record cannot carry the row (fall back to the direct
+// scatter).  Needs nothing of the workspace but the row counts, so it can be enqueued before otto_covisit_count_finish_owned.
+extern "C" int otto_covisit_stage_plan(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
+                                       const uint32_t* counts_all, int32_t n_ranks, int32_t rank, void* plan, int64_t plan_bytes,
+                                       int64_t* staged_records_host, void* stream) {
+  int rc = check_spec(spec);
+  if (rc) return rc;
+  if (!ev || n_ranks < 1 || n_ranks > OTTO_MAX_OWNERS || rank < 0 || rank >= n_ranks) { otto_set_error("bad argument"); return OTTO_EINVAL; }
+  const Layout L = make_layout(ev->n_sessions, ev->n_events, spec);
+  if ((rc = check_ws(L, workspace, workspace_bytes))) return rc;
+  const StageLayout S = stage_layout(spec, ev->n_sessions, ev->n_events, n_ranks);
+  if (!plan || plan_bytes < S.total) { otto_set_error("stage plan scratch too small: need %lld bytes", (long long)S.total); return OTTO_ENOSPC; }
+  uint32_t yb, vb;
+  if ((rc = stage_bits(spec, &yb, &vb))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!counts_all) {
+    if (n_ranks != 1) { otto_set_error("counts_all is NULL"); return OTTO_EINVAL; }
+    counts_all = WS(uint32_t, row_count);
+  }
+  stage_count_kernel<<<(unsigned)S.NB, 256, 0, st>>>(counts_all, n_ranks, L.A, S.NB + 1, SP(unsigned long long, bcnt));
+  LAUNCH_CHECK();
+  stage_scan_kernel<<<n_ranks, 1024, 0, st>>>(SP(unsigned long long, bcnt), SP(unsigned long long, bo), S.NB, rank, SP(uint32_t, bcur),
+                                              SP(unsigned long long, info));
+  LAUNCH_CHECK();
+  if (!staged_records_host) return OTTO_OK;     // asynchronous form: otto_covisit_stage_totals reads the sizes later
+  return otto_covisit_stage_totals(spec, ev->n_sessions, ev->n_events, plan, n_ranks, staged_records_host, stream);
+}
+
+// pass A: this rank's pairs into the coarse buckets of its staging buffer (`staged`: at least staged_records_host[rank]
+// records of 8 bytes)
+extern "C" int otto_covisit_scatter_staged(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
+                                           void* plan, int32_t n_ranks, void* staged, void* stream) {
+  Layout L;
+  int rc = scatter_args(ev, spec, workspace, workspace_bytes, &L);
+  if (rc) return rc;
+  if (!plan || !staged || n_ranks < 1 || n_ranks > OTTO_MAX_OWNERS) { otto_set_error("bad argument"); return OTTO_EINVAL; }
+  const StageLayout S = stage_layout(spec, ev->n_sessions, ev->n_events, n_ranks);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L.S > 0) {
+    PairGenParams p = make_pairgen(L, spec, workspace);
+    p.records = (uint2*)staged;
+    p.bcur = SP(uint32_t, bcur);
+    if ((rc = stage_bits(spec, &p.y_bits, &p.v_bits))) return rc;
+    const int64_t warps = ceil_div(L.S, 32);
+    pairgen_kernel<3><<<(unsigned)ceil_div(warps, PAIRGEN_WARPS), PAIRGEN_WARPS * 32, 0, st>>>(p);
+    LAUNCH_CHECK();
+  }
+  return OTTO_OK;
+}
+
+static int occupancy_blocks(const void* kernel, int threads, size_t smem);
+template <typename K>
+static int set_smem(K kernel, size_t bytes);
+
+struct StagedPtrs {
+  const uint2* rank[OTTO_MAX_OWNERS];
+};
+
+struct PlaceParams {
+  const uint4* tiles;                // {address of the tile's first record in its sender's buffer (lo, hi), records, bucket}
+  const unsigned long long* info;    // [2] tiles
+  int64_t tile_cap;
+  uint32_t aid_lo, aid_hi;
+  uint32_t y_bits, v_bits;
+  uint32_t* cursor;
+  uint2* records;
+};
+
+// one thread per bucket of my row range: the tiles of its G segments, appended to the tile list as ONE run, so that the
+// blocks of the place pass, which walk the list in order, write into a few buckets' worth of rows at a time (L2 then
+// combines the short runs into full lines)
+__global__ void place_tiles_kernel(const StagedPtrs staged, int G, int64_t b_lo, int64_t b_hi, const unsigned long long* __restrict__ bcnt,
+                                   const unsigned long long* __restrict__ bo, int64_t nb_stride, uint4* __restrict__ tiles,
+                                   unsigned long long* info, int64_t tile_cap) {
+  const int64_t b = b_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= b_hi) return;
+  unsigned long long nt = 0;
+  for (int g = 0; g < G; ++g) nt += (bcnt[(int64_t)g * nb_stride + b] + PLACE_TILE - 1) / PLACE_TILE;
+  if (nt == 0) return;
+  unsigned long long at = atomicAdd(&info[2], nt);
+  for (int g = 0; g < G; ++g) {
+    const unsigned long long beg = bo[(int64_t)g * nb_stride + b], n = bcnt[(int64_t)g * nb_stride + b];
+    for (unsigned long long i = 0; i < n && (int64_t)at < tile_cap; i += PLACE_TILE, ++at) {
+      const uint32_t m = (uint32_t)min((unsigned long long)PLACE_TILE, n - i);
+      const unsigned long long src = (unsigned long long)(staged.rank[g] + beg + i);       // 16-byte aligned: beg is even
+      tiles[at] = make_uint4((uint32_t)src, (uint32_t)(src >> 32), m, (uint32_t)b);
+    }
+  }
+}
+
+// Persistent blocks over the tile list.  A tile (1024 records, 8 KB) reaches shared memory by ONE bulk copy
+// (cp.async.bulk, completion on an mbarrier) issued PLACE_STAGES - 1 tiles ahead by thread 0: the pass is bound by the
+// latency of its loads - a few microseconds across NVLink - so the bytes in flight per SM decide its rate, and a ring
+// of bulk copies keeps them in flight without holding registers or issue slots.  Per tile: records to registers, the
+// stage goes back to the producer, then one cursor atomic per run of equal rows in the warp (the records of one
+// (session, row) were staged as one run), all atomics of the tile issued before the first result is needed.
+constexpr int PLACE_STAGES = 4;
+constexpr uint32_t PLACE_BUF_BYTES = PLACE_TILE * 8;
+constexpr size_t place_smem_bytes() { return (size_t)PLACE_STAGES * PLACE_BUF_BYTES; }
+
+__global__ void __launch_bounds__(PLACE_THREADS) place_kernel(const PlaceParams p) {
+  extern __shared__ __align__(128) unsigned char place_smem[];
+  __shared__ __align__(8) unsigned long long s_bar[PLACE_STAGES];
+  __shared__ uint2 s_meta[PLACE_STAGES];                       // {records of the tile, its bucket}
+  const uint32_t buf_s = (uint32_t)__cvta_generic_to_shared(place_smem);
+  const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(s_bar);
+  unsigned long long n_tiles = p.info[2];
+  if ((int64_t)n_tiles > p.tile_cap) n_tiles = (unsigned long long)p.tile_cap;
+  const uint32_t lane = lane_id();
+  const unsigned long long ymask = (1ull << p.y_bits) - 1ull, vmask = (1ull << p.v_bits) - 1ull;
+  const unsigned long long stride = gridDim.x;
+  const uint4 none = make_uint4(0u, 0u, 0u, 0u);
+  uint4 d_pref = none;                                          // thread 0: descriptor of the next tile to issue
+  auto issue = [&](const uint4 d, int st) {
+    s_meta[st] = make_uint2(d.z, d.w);
+    const uint32_t bytes = ((d.z + 1u) & ~1u) * 8u;            // an odd tile ends its segment: the pad record is there
+    mbar_expect_tx(bar_s + st * 8, bytes);
+    bulk_g2s(buf_s + st * PLACE_BUF_BYTES, (const void*)(((unsigned long long)d.y << 32) | d.x), bytes, bar_s + st * 8);
+  };
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < PLACE_STAGES; ++i) mbar_init(bar_s + i * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < PLACE_STAGES; ++i) {
+      const unsigned long long ti = blockIdx.x + i * stride;
+      if (ti < n_tiles) issue(p.tiles[ti], i);
+    }
+    const unsigned long long tp = blockIdx.x + PLACE_STAGES * stride;
+    if (tp < n_tiles) d_pref = p.tiles[tp];
+  }
+  __syncthreads();
+  uint32_t it = 0;
+  for (unsigned long long t = blockIdx.x; t < n_tiles; t += stride, ++it) {
+    const int st = it % PLACE_STAGES;
+    mbar_wait(bar_s + st * 8, (it / PLACE_STAGES) & 1u);
+    const uint2 meta = s_meta[st];
+    const uint32_t m = meta.x, x0 = meta.y << STAGE_LOGA;
+    const uint32_t tile_s = buf_s + st * PLACE_BUF_BYTES;
+    uint2 r[PLACE_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < PLACE_PER_THREAD; ++u) {
+      const uint32_t j = u * PLACE_THREADS + threadIdx.x;
+      r[u] = make_uint2(0xffffffffu, 0xffffffffu);
+      if (j < m) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r[u].x), "=r"(r[u].y) : "r"(tile_s + 8u * j) : "memory");
+    }
+    __syncthreads();                                            // the stage is free: refill it PLACE_STAGES tiles ahead
+    if (threadIdx.x == 0) {
+      const unsigned long long tn = t + PLACE_STAGES * stride;
+      if (tn < n_tiles) {
+        issue(d_pref, st);
+        d_pref = tn + stride < n_tiles ? p.tiles[tn + stride] : none;
+      }
+    }
+    uint32_t slot[PLACE_PER_THREAD], rel[PLACE_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < PLACE_PER_THREAD; ++u) {
+      const uint32_t j = u * PLACE_THREADS + threadIdx.x;
+      const unsigned long long rec = ((unsigned long long)r[u].y << 32) | r[u].x;
+      const uint32_t x = x0 + (uint32_t)(rec >> (p.y_bits + p.v_bits));
+      const bool mine = j < m && x >= p.aid_lo && x < p.aid_hi;      // a bucket across an owner cut is read by both owners
+      const uint32_t key = mine ? x : 0xffffffffu;
+      const uint32_t prev = __shfl_up_sync(FULL_MASK, key, 1);
+      const uint32_t heads = __ballot_sync(FULL_MASK, lane == 0 || key != prev);
+      const int head = 31 - __clz(heads & (FULL_MASK >> (31 - lane)));
+      const uint32_t above = lane == 31 ? 0u : heads & (FULL_MASK << (lane + 1));
+      const int next = above ? __ffs(above) - 1 : 32;
+      slot[u] = 0;
+      if (mine && (int)lane == head) slot[u] = atomicAdd(&p.cursor[x], (uint32_t)(next - head));
+      rel[u] = mine ? ((uint32_t)head << 8) | (lane - (uint32_t)head) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int u = 0; u < PLACE_PER_THREAD; ++u) {
+      const uint32_t at = __shfl_sync(FULL_MASK, slot[u], (rel[u] >> 8) & 31u);
+      if (rel[u] != 0xffffffffu) {
+        const unsigned long long rec = ((unsigned long long)r[u].y << 32) | r[u].x;
+        st_stream_u2(p.records + (at + (rel[u] & 0xffu)),
+                     make_uint2((uint32_t)(rec & ymask), (uint32_t)((rec >> p.y_bits) & vmask)));
+      }
+    }
+  }
+}
+
+// pass B at the owner of rows [aid_lo, aid_hi): the records every rank staged for them -> `records` (final positions of the
+// ordinary rows, staging area of the hot rows; otto_covisit_partition and otto_covisit_reduce follow).  staged_host[g] =
+// rank g's staging buffer as this process sees it (its own, or the peer mapping); every rank's otto_covisit_scatter_staged
+// must have completed (any collective between the two calls orders that).  `plan` is the caller's own plan scratch: every
+// rank computes the same bucket table.  No synchronisation.
+extern "C" int otto_covisit_place_staged(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
+                                         void* plan, int32_t n_ranks, const void* const* staged_host, int32_t aid_lo, int32_t aid_hi,
+                                         void* records, int64_t records_capacity, void* stream) {
+  Layout L;
+  int rc = scatter_args(ev, spec, workspace, workspace_bytes, &L);
+  if (rc) return rc;
+  if ((rc = check_records(records, records_capacity))) return rc;
+  if (!plan || !staged_host || n_ranks < 1 || n_ranks > OTTO_MAX_OWNERS || aid_lo < 0 || aid_hi > spec->n_aids || aid_lo > aid_hi) {
+    otto_set_error("bad argument");
+    return OTTO_EINVAL;
+  }
+  const StageLayout S = stage_layout(spec, ev->n_sessions, ev->n_events, n_ranks);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t A = L.A;
+  // cursors of MY layout: final position of an ordinary row, slice of the staging area of a hot row
+  init_cursor_kernel<<<(unsigned)ceil_div(A, 256), 256, 0, st>>>(WS(unsigned long long, row_off), WS(unsigned long long, hot_off),
+                                                                 WS(uint32_t, bin_base), A, WS(uint32_t, cursor));
+  LAUNCH_CHECK();
+  if (aid_hi == aid_lo) return OTTO_OK;
+  const int64_t b_lo = (int64_t)aid_lo >> STAGE_LOGA, b_hi = (((int64_t)aid_hi - 1) >> STAGE_LOGA) + 1;
+  CUDA_TRY(cudaMemsetAsync(SP(unsigned long long, info) + 2, 0, 8, st));
+  StagedPtrs sp;
+  for (int g = 0; g < OTTO_MAX_OWNERS; ++g) sp.rank[g] = (const uint2*)staged_host[g < n_ranks ? g : 0];
+  place_tiles_kernel<<<(unsigned)ceil_div(b_hi - b_lo, 256), 256, 0, st>>>(
+      sp, n_ranks, b_lo, b_hi, SP(unsigned long long, bcnt), SP(unsigned long long, bo), S.NB + 1, SP(uint4, tiles),
+      SP(unsigned long long, info), S.Tmax);
+  LAUNCH_CHECK();
+  PlaceParams pp;
+  pp.tiles = SP(uint4, tiles);
+  pp.info = SP(unsigned long long, info);
+  pp.tile_cap = S.Tmax;
+  pp.aid_lo = (uint32_t)aid_lo;
+  pp.aid_hi = (uint32_t)aid_hi;
+  if ((rc = stage_bits(spec, &pp.y_bits, &pp.v_bits))) return rc;
+  pp.cursor = WS(uint32_t, cursor);
+  pp.records = (uint2*)records;
+  int dev = 0, n_sm = 148;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  if ((rc = set_smem(place_kernel, place_smem_bytes()))) return rc;
+  static const int occ = occupancy_blocks((const void*)place_kernel, PLACE_THREADS, place_smem_bytes());
+  place_kernel<<<n_sm * occ, PLACE_THREADS, place_smem_bytes(), st>>>(pp);
+  LAUNCH_CHECK();
+  return OTTO_OK;
+}
+
 // ------------------------------------------------------------------ reduce
 
 struct ScratchLayout {

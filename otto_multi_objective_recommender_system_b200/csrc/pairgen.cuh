@@ -54,8 +54,16 @@ struct PairGenParams {
   int32_t n_owners;
   uint32_t cuts[OTTO_MAX_OWNERS + 1];
   uint2* owner_rec[OTTO_MAX_OWNERS];
+  // MODE 3 (staged scatter): the records of row x go to coarse bucket x >> STAGE_LOGA of this rank's staging buffer,
+  // packed into 64 bits as aid_y | v << y_bits | (x & (2^STAGE_LOGA - 1)) << (y_bits + v_bits); bcur[b] = next free slot
+  uint32_t* bcur;              // [buckets * STAGE_CUR_STRIDE]
+  uint32_t y_bits, v_bits;
 };
 
+constexpr int STAGE_LOGA = 11;      // staged scatter: 2048 aid_x rows per coarse bucket
+// every bucket cursor in its own 128-byte line: 125 M atomics on ~900 adjacent words serialise in ~30 L2 lines (11.5 ms
+// for pass A), spread over one line each they do not (profiles/r02_experiments.md)
+constexpr int STAGE_CUR_STRIDE = 32;
 constexpr int PAIRGEN_WARPS = 8;
 
 __device__ __forceinline__ uint32_t lowmask(int k) { return k >= 32 ? FULL_MASK : ((1u << k) - 1u); }
@@ -72,7 +80,7 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x) {
   return x;
 }
 
-// MODE 0: count pass, 1: scatter into p.records, 2: scatter into the owners' buffers
+// MODE 0: count pass, 1: scatter into p.records, 2: scatter into the owners' buffers, 3: staged scatter into coarse buckets
 template <int MODE>
 __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairGenParams p) {
   constexpr bool SCATTER = MODE != 0;
@@ -171,8 +179,13 @@ __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairG
     } else {
       const uint32_t mywm = active ? (p.winmask[e0 + lane] << base) : 0u;
       const uint32_t cnt = __popc(mywm);
-      uint32_t slot = 0;
-      if (active && cnt) slot = atomicAdd(&p.cursor[aid], cnt);
+      uint32_t slot = 0, xl = 0;
+      if (MODE == 3) {
+        xl = aid & ((1u << STAGE_LOGA) - 1u);
+        if (active && cnt) slot = atomicAdd(&p.bcur[(aid >> STAGE_LOGA) * STAGE_CUR_STRIDE], cnt);
+      } else if (active && cnt) {
+        slot = atomicAdd(&p.cursor[aid], cnt);
+      }
       uint2* dst = p.records;
       if (MODE == 2) {
         dst = p.owner_rec[0];
@@ -192,7 +205,12 @@ __global__ void __launch_bounds__(PAIRGEN_WARPS * 32) pairgen_kernel(const PairG
         const uint32_t val = time_mode ? (uint32_t)__shfl_sync(FULL_MASK, tv, src) : v;
         uint2* dsti = p.records;
         if (MODE == 2) dsti = (uint2*)__shfl_sync(FULL_MASK, (unsigned long long)dst, src);
-        if ((wmi >> lane) & 1u) st_stream_u2(dsti + (sloti + __popc(wmi & lt)), make_uint2(aid, val));
+        if (MODE == 3) {
+          const uint32_t xli = __shfl_sync(FULL_MASK, xl, src);
+          const unsigned long long rec = (unsigned long long)aid | ((unsigned long long)val << p.y_bits) |
+                                         ((unsigned long long)xli << (p.y_bits + p.v_bits));
+          if ((wmi >> lane) & 1u) st_stream_u2(dsti + (sloti + __popc(wmi & lt)), make_uint2((uint32_t)rec, (uint32_t)(rec >> 32)));
+        } else if ((wmi >> lane) & 1u) st_stream_u2(dsti + (sloti + __popc(wmi & lt)), make_uint2(aid, val));
       }
     }
   }

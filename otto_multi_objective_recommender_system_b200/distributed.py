@@ -44,6 +44,9 @@ from . import _native as N
 from .covisit import CovisitBuilder, CovisitSpec, EventCSR, TopKTable
 
 
+STAGED_DEFAULT = "0"      # set from the measurements in profiles/ (r02_staged_*.json)
+
+
 class _RawCuda:
     """__cuda_array_interface__ view of a raw device allocation (int64 elements)."""
 
@@ -178,6 +181,28 @@ class GpuRankBackend:
         self.b.records = self.peer.ensure_same(int(self.b.stats.owner_records_max))
         self.b.scatter_owned(aid_cuts, rank, self.peer.peers)
 
+    # -- staged scatter: sender-side combining, the owner pulls its buckets over NVLink in large reads --------
+    @property
+    def staged(self) -> bool:
+        """Transport of the owner-direct protocol: False = the scatter kernel stores every ~63-byte run straight into the
+        owner's buffer, True = runs are combined in coarse buckets of the sender's own (peer-mapped) staging buffer and
+        the owner places them (include/otto_covisit.h, "Staged scatter").  OTTO_STAGED=0/1 overrides the default."""
+        return self.owner_direct and os.environ.get("OTTO_STAGED", STAGED_DEFAULT) != "0"
+
+    def stage_plan(self, gathered: torch.Tensor, world: int, rank: int) -> None:
+        """Enqueued before count_finish_owned, whose synchronisation then covers the plan's kernels."""
+        self.b.stage_plan(gathered, world, rank, sync=False)
+
+    def scatter_staged(self, world: int) -> None:
+        totals = self.b.stage_totals(world)                            # the same list on every rank
+        self.peer.ensure_same(max(totals))                             # the peer-mapped buffer is the STAGING buffer here
+        self.b.scatter_staged(world, self.peer.ptr)
+
+    def place_staged(self, aid_cuts, rank: int) -> None:
+        if self.b.records is not None and self.b.records.data_ptr() == self.peer.ptr:
+            self.b.records = None                 # a direct-scatter build left the peer buffer here: it is the staging buffer now
+        self.b.place_staged(self.peer.peers, aid_cuts[rank], aid_cuts[rank + 1])
+
     def partition(self):
         records = self.b.partition()
         return records, self.b.views()["bin_offsets"]
@@ -254,12 +279,22 @@ def _build_owner_direct(backend, group, mark, world: int, rank: int):
     dist.all_gather(list(gathered.unbind(0)), local, group=group)
     aid_cuts, before = backend.plan_owners(gathered, world, rank)  # workspace row_total := totals over all ranks
     mark("allgather_rows+plan")
+    staged = getattr(backend, "staged", False)
+    if staged:
+        backend.stage_plan(gathered, world, rank)                    # bucket table of every rank (no synchronisation)
     stats, bin_base = backend.count_finish_owned(aid_cuts, rank, before)
     mark("count_finish")
-    backend.scatter_owned(aid_cuts, rank)
-    # "every rank's records have landed": a rank's part of this collective is ordered behind its scatter kernel
+    if staged:
+        backend.scatter_staged(world)                                # pass A: my pairs into my own staging buffer
+    else:
+        backend.scatter_owned(aid_cuts, rank)
+    # "every rank's records have landed" (staged: "every rank has staged"): a rank's part of this collective is ordered
+    # behind its scatter kernel.  The staging buffers are safe to overwrite in the next build because that build's
+    # all-gather of the row counts sits between a peer's place pass and my next pass A.
     landed = torch.zeros(1, dtype=torch.int32, device=local.device)
     dist.all_reduce(landed, group=group)
+    if staged:
+        backend.place_staged(aid_cuts, rank)                          # pass B: my buckets out of every rank's staging buffer
     mark("scatter")
     records, bin_off = backend.partition()
     mark("partition")

@@ -10,9 +10,11 @@ pytestmark = pytest.mark.gpu
 
 def _worker(rank, world, port, variant, split_ub, n_sessions, n_aids, transport):
     import torch.distributed as dist
-    # owner_direct: NVLink stores from the scatter kernel; peer_read: owners read the senders' slabs; nccl: all-to-all
+    # owner_direct: NVLink stores from the scatter kernel; staged: runs combined in the sender's staging buffer, owners pull
+    # their buckets; peer_read: owners read the senders' slabs; nccl: all-to-all
     use_peer = transport != "nccl"
-    os.environ["OTTO_OWNER_DIRECT"] = "1" if transport == "owner_direct" else "0"
+    os.environ["OTTO_OWNER_DIRECT"] = "1" if transport in ("owner_direct", "staged") else "0"
+    os.environ["OTTO_STAGED"] = "1" if transport == "staged" else "0"
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -26,7 +28,7 @@ def _worker(rank, world, port, variant, split_ub, n_sessions, n_aids, transport)
     shard = csr.slice_sessions(rank * S // world, (rank + 1) * S // world)
     peer = distributed.PeerRecords(dev) if use_peer else None     # NVLink peer memory vs NCCL all-to-all
     backend = distributed.GpuRankBackend(shard, spec, exact=True, peer=peer)
-    assert backend.owner_direct == (transport == "owner_direct")
+    assert backend.owner_direct == (transport in ("owner_direct", "staged")) and backend.staged == (transport == "staged")
     table, (lo, hi), stats, plan = distributed.build_topk_distributed(backend)
     distributed.gather_table(table, plan)
     single, sstats = covisit.build_topk(csr, spec, exact=True)
@@ -42,7 +44,7 @@ def _worker(rank, world, port, variant, split_ub, n_sessions, n_aids, transport)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("transport", ["owner_direct", "peer_read", "nccl"])
+@pytest.mark.parametrize("transport", ["owner_direct", "staged", "peer_read", "nccl"])
 @pytest.mark.parametrize("variant,split_ub", [("CLICKS", 0), ("CARTS_ORDERS", 64), ("BUY2BUY", 0)])
 def test_multi_gpu_equals_single_gpu(native_lib, variant, split_ub, transport):
     world = min(torch.cuda.device_count(), 8)      # every GPU of the box: the owner-direct scatter must hold at 8 ranks too
