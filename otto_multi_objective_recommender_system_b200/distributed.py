@@ -44,7 +44,7 @@ from . import _native as N
 from .covisit import CovisitBuilder, CovisitSpec, EventCSR, TopKTable
 
 
-STAGED_DEFAULT = "0"      # set from the measurements in profiles/ (r02_staged_*.json)
+STAGED_DEFAULT = "1"      # staged wins on one NVLink box: 15.1 vs 15.6 ms at 2 GPUs, 9.1 vs 10.0 at 4 (profiles/r02_staged_*.json)
 
 
 class _RawCuda:
