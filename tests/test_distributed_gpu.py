@@ -56,13 +56,14 @@ def test_multi_gpu_equals_single_gpu(native_lib, variant, split_ub, transport):
     torch.multiprocessing.spawn(_worker, args=(world, port, variant, split_ub, 20000, 2500, transport), nprocs=world, join=True)
 
 
-def test_eight_rank_owner_direct_full_width(native_lib):
-    """The default transport at the full width of a box (8 ranks, or whatever the box has beyond 4): a larger frame, so
-    that every owner holds hot rows and receives records from every peer."""
+@pytest.mark.parametrize("transport", ["staged", "owner_direct"])
+def test_eight_rank_owner_direct_full_width(native_lib, transport):
+    """The default transport (staged) and the direct scatter at the full width of a box (8 ranks, or whatever the box has
+    beyond 4): a larger frame, so that every owner holds hot rows and receives records from every peer."""
     world = min(torch.cuda.device_count(), 8)
     if world <= 4:
         pytest.skip("needs more than 4 GPUs")
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    torch.multiprocessing.spawn(_worker, args=(world, port, "CLICKS", 256, 60000, 4000, "owner_direct"), nprocs=world, join=True)
+    torch.multiprocessing.spawn(_worker, args=(world, port, "CLICKS", 256, 60000, 4000, transport), nprocs=world, join=True)
