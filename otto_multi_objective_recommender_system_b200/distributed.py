@@ -23,6 +23,17 @@ top-k - is local to the owner and identical to a single-GPU build of the owner's
     scatter_owned (records -> owners' HBM)   all-reduce  1 element: "every scatter has landed"
     partition + reduce (one local segment)
 
+Staged variant of the same protocol (default, `GpuRankBackend.staged`): the scatter kernel's short runs cross NVLink
+badly (~63-byte store packets), so a rank first combines them in coarse aid_x buckets of its OWN peer-mapped staging
+buffer and the owner pulls its buckets in large reads and places the records (include/otto_covisit.h, "Staged scatter"):
+
+    count_begin                              all-gather  row counts [G, A] uint32 -> totals, counts of lower ranks
+    stage_plan (bucket table of every rank)  - enqueued before count_finish_owned, whose synchronisation covers it
+    count_finish_owned (bins, my layout)
+    scatter_staged (pass A, local)           all-reduce  1 element: "every rank has staged"
+    place_staged (pass B: my buckets out of every rank's staging buffer -> my record buffer)
+    partition + reduce (one local segment)
+
 Every rank forms the same bins (the row totals are reduced before bins exist) and the accumulators are
 integers, so the G-GPU table equals the 1-GPU table byte for byte.  The reference has no distributed code
 (SURVEY.md §2.1); its only partitioning is the aid_x-range "part" files, which is what ownership mirrors.

@@ -151,6 +151,55 @@ class NumpyOwnerBackend(NumpyRankBackend):
         return torch.from_numpy(self.rec), torch.from_numpy(self.bin_off)
 
 
+class NumpyStagedBackend(NumpyOwnerBackend):
+    """Stand-in for the staged scatter (include/otto_covisit.h, "Staged scatter"): pass A appends my pairs to coarse
+    aid_x buckets of my own staging array (segments start on even slots, like the library's), "peers map each other's
+    staging buffers" is an object all-gather, pass B walks the segments of my buckets in every rank's staging array and
+    places the records with the cursors of my own layout."""
+    staged = True
+    LOGA = 3                                                        # 8 rows per bucket (the library: 2048)
+
+    def stage_plan(self, gathered, world, rank):
+        counts = (gathered.numpy().astype(np.int64) & 0xFFFFFFFF)   # [G, A]
+        nb = -(-self.n_aids // (1 << self.LOGA))
+        pad = np.zeros((world, nb << self.LOGA), dtype=np.int64)
+        pad[:, :self.n_aids] = counts
+        self.bcnt = pad.reshape(world, nb, 1 << self.LOGA).sum(2)
+        even = (self.bcnt + 1) & ~1
+        self.bo = np.concatenate([np.zeros((world, 1), dtype=np.int64), np.cumsum(even, 1)], 1)
+
+    def scatter_staged(self, world):
+        x, y = self.pairs["aid_x"].to_numpy().astype(np.int64), self.pairs["aid_y"].to_numpy().astype(np.int64)
+        me = dist.get_rank()
+        assert len(x) == int(self.bcnt[me].sum())
+        self.staging = np.full(int(self.bo[me, -1]), -1, dtype=np.int64)
+        cur = self.bo[me, :-1].copy()
+        for xi, yi in zip(x, y):                                    # runs in any order: the place pass must not care
+            b = xi >> self.LOGA
+            self.staging[cur[b]] = yi | (1 << 32) | ((xi & ((1 << self.LOGA) - 1)) << 40)
+            cur[b] += 1
+
+    def place_staged(self, aid_cuts, rank):
+        world = len(aid_cuts) - 1
+        every = [None] * world
+        dist.all_gather_object(every, self.staging)
+        lo, hi = aid_cuts[rank], aid_cuts[rank + 1]
+        self.buf = np.full(self.P_mine + self.H_mine, -1, dtype=np.int64)
+        hot = self.nb > 1
+        cursor = np.where(hot, self.P_mine + self.lay_hot[:-1], self.lay_off[:-1])
+        if hi > lo:
+            for b in range(lo >> self.LOGA, ((hi - 1) >> self.LOGA) + 1):
+                for g in range(world):
+                    seg = every[g][self.bo[g, b]:self.bo[g, b] + self.bcnt[g, b]]
+                    assert (seg >= 0).all(), "a staged segment has holes"
+                    for r in seg:
+                        xrow = (b << self.LOGA) + (int(r) >> 40)
+                        if lo <= xrow < hi:                             # a bucket across an owner cut is read by both owners
+                            self.buf[cursor[xrow]] = int(r) & ((1 << 40) - 1)
+                            cursor[xrow] += 1
+        assert int((self.buf == -1).sum()) == self.H_mine, "the owners' layout has holes"
+
+
 def _worker(rank, world, port, split_ub, out, owner_direct=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -160,7 +209,8 @@ def _worker(rank, world, port, split_ub, out, owner_direct=False):
     sessions = np.sort(df["session"].unique())
     mine = sessions[rank * len(sessions) // world:(rank + 1) * len(sessions) // world]     # contiguous session chunk
     spec = co.OracleSpec(co.WEIGHT_UNIT, k=7)
-    backend = (NumpyOwnerBackend if owner_direct else NumpyRankBackend)(df.loc[df["session"].isin(mine)], spec, 80, split_ub)
+    kind = {False: NumpyRankBackend, True: NumpyOwnerBackend, "staged": NumpyStagedBackend}[owner_direct]
+    backend = kind(df.loc[df["session"].isin(mine)], spec, 80, split_ub)
     table, (lo, hi), stats, plan = distributed.build_topk_distributed(backend)
     assert table["aid_x"].between(lo, hi - 1).all()
     gathered = [None] * world
@@ -174,7 +224,8 @@ def _worker(rank, world, port, split_ub, out, owner_direct=False):
 
 
 @pytest.mark.parametrize("world,split_ub,owner_direct", [(2, 1 << 30, False), (2, 40, False), (2, 1 << 30, True), (2, 40, True),
-                                                        (3, 40, True)])
+                                                        (3, 40, True), (2, 1 << 30, "staged"), (2, 40, "staged"),
+                                                        (3, 40, "staged")])
 def test_multi_rank_exchange_equals_single_process(world, split_ub, owner_direct):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
