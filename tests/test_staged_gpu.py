@@ -77,3 +77,29 @@ def test_staged_scatter_tiny_frame(native_lib):
         for name in ("aid_y", "wgt", "len"):
             assert torch.equal(getattr(t, name)[lo:hi], getattr(single, name)[lo:hi]), (g, name)
     assert sum(s["distinct"] for s in stats) == sstats["distinct"]
+
+
+def test_staged_scatter_argument_errors(native_lib):
+    """The error behaviour the header promises: -1 for an impossible rank count, OTTO_ENOSPC for a plan scratch that is too
+    small (nothing launched), OTTO_EINVAL for a rank outside the box."""
+    import ctypes as C
+    from otto_multi_objective_recommender_system_b200 import _native as N, covisit, synth
+    dev = torch.device("cuda", 0)
+    frame = synth.generate(synth.SynthSpec("train", 200, 60, seed=5), device=dev)
+    csr = covisit.ingest(frame, "desc", device=dev)
+    b = covisit.CovisitBuilder(csr, covisit.CLICKS)
+    b.count_begin()
+    b.count_finish()
+    lib = N.lib()
+    assert lib.otto_covisit_stage_plan_bytes(C.byref(b.cspec), csr.n_sessions, csr.n_events, 0) == -1
+    assert lib.otto_covisit_stage_plan_bytes(C.byref(b.cspec), csr.n_sessions, csr.n_events, N.MAX_OWNERS + 1) == -1
+    need = lib.otto_covisit_stage_plan_bytes(C.byref(b.cspec), csr.n_sessions, csr.n_events, 1)
+    small = torch.empty(need - 1, dtype=torch.uint8, device=dev)
+    totals = (C.c_int64 * N.MAX_OWNERS)()
+    args = (C.byref(b.ev), C.byref(b.cspec), b.workspace.data_ptr(), b.workspace.numel(), None)
+    assert lib.otto_covisit_stage_plan(*args, 1, 0, small.data_ptr(), small.numel(), totals, b._st()) == N.OTTO_ENOSPC
+    full = torch.empty(need, dtype=torch.uint8, device=dev)
+    assert lib.otto_covisit_stage_plan(*args, 1, 1, full.data_ptr(), need, totals, b._st()) == N.OTTO_EINVAL      # rank >= n_ranks
+    assert lib.otto_covisit_stage_plan(*args, 2, 0, full.data_ptr(), need, totals, b._st()) in (N.OTTO_EINVAL, N.OTTO_ENOSPC)  # counts_all NULL with 2 ranks
+    assert lib.otto_covisit_stage_plan(*args, 1, 0, full.data_ptr(), need, totals, b._st()) == N.OTTO_OK
+    assert totals[0] >= b.stats.pairs and totals[0] - b.stats.pairs <= 2 * ((csr.n_aids >> 11) + 1)                # even-padded segments
