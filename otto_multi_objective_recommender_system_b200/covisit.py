@@ -401,6 +401,8 @@ class CovisitBuilder:
         return [int(totals[g]) for g in range(world)] if sync else None
 
     def stage_totals(self, world: int) -> list:
+        if getattr(self, "_stage_scratch", None) is None:
+            raise RuntimeError("stage_totals() before stage_plan()")
         totals = (C.c_int64 * N.MAX_OWNERS)()
         with torch.cuda.device(self.device):
             N.check(self.lib.otto_covisit_stage_totals(C.byref(self.cspec), self.csr.n_sessions, self.csr.n_events,
@@ -408,7 +410,10 @@ class CovisitBuilder:
         return [int(totals[g]) for g in range(world)]
 
     def scatter_staged(self, world: int, staged_ptr: int) -> None:
-        """Pass A: this rank's pairs into the coarse buckets of its staging buffer (device pointer)."""
+        """Pass A: this rank's pairs into the coarse buckets of its staging buffer (device pointer; at least
+        stage_totals()[rank] records - the library trusts the caller's allocation, as it does for the record buffer)."""
+        if getattr(self, "_stage_scratch", None) is None:
+            raise RuntimeError("scatter_staged() before stage_plan()")
         with torch.cuda.device(self.device):
             N.check(self.lib.otto_covisit_scatter_staged(C.byref(self.ev), C.byref(self.cspec), self.workspace.data_ptr(),
                                                          self.workspace.numel(), self._stage_scratch.data_ptr(), world, staged_ptr,

@@ -1700,6 +1700,8 @@ extern "C" int otto_covisit_place_staged(const OttoEvents* ev, const OttoCovisit
     otto_set_error("bad argument");
     return OTTO_EINVAL;
   }
+  for (int g = 0; g < n_ranks; ++g)
+    if (!staged_host[g]) { otto_set_error("staging buffer of rank %d is NULL", g); return OTTO_EINVAL; }
   const StageLayout S = stage_layout(spec, ev->n_sessions, ev->n_events, n_ranks);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t A = L.A;
