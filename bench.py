@@ -492,7 +492,8 @@ def run_b200(args):
     t_end.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    launches = (lib.otto_launch_count() - launches0) // max(1, args.steps)
+    launches_total = lib.otto_launch_count() - launches0          # this rank's kernels inside the timed region
+    launches = launches_total // max(1, args.steps)
     dist_phase_ms, nvlink = None, None
     if world > 1:
         # phase times at N > 1: three extra steps OUTSIDE the timed region with CUDA events recorded between the phases
@@ -746,7 +747,7 @@ def run_b200(args):
                        "cpu_sample": args.cpu_sample,
                        "note": "the reference arm (--impl reference) and cpu_baseline time the same recipe on cpu_sample of this frame"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "candidates": cand_info, "pipeline": pipeline,
-            "parity": parity, "gpu_launches": int(launches), "clocks": clocks}))
+            "parity": parity, "gpu_launches": int(launches_total), "gpu_launches_per_step": int(launches), "clocks": clocks}))
     if world > 1:
         if peer is not None:
             peer.close()
