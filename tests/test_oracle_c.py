@@ -125,3 +125,20 @@ def test_c_oracle_config_1_scale():
     df = synth.generate(synth.SynthSpec.scaled("train", 0.01)).to_pandas()
     got, want = _assert_same_accumulators(df, co.CLICKS)
     assert len(got) > 1_000_000
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_c_oracle_through_the_gpu_comparison_helpers(variant):
+    """tests/test_build_gpu.py::test_build_matches_c_oracle holds the CUDA tables to the C oracle through
+    parity_helpers; here the same helper calls are fed by both oracles and must produce identical expected tables."""
+    import parity_helpers as H
+    spec = VARIANTS[variant]
+    df = _synth_df(20000, 3000, 42)
+    acc_c, acc_p = cc.accumulate(df, spec), co.accumulate(df, spec, exact=True)
+    if spec.weight_mode == co.WEIGHT_TIME:
+        a, b = H.gpu_formula_topk(acc_c, spec), H.gpu_formula_topk(acc_p, spec)
+    else:
+        a = co.topk(acc_c.assign(wgt=cc.weights(acc_c, spec))[["aid_x", "aid_y", "wgt", "cnt", "tsum"]], spec.k)
+        b = co.topk(acc_p, spec.k)
+    H.assert_int_table_equal(a, b, variant)
+    assert np.array_equal(a["cnt"].to_numpy(), b["cnt"].to_numpy()) and np.array_equal(a["tsum"].to_numpy(), b["tsum"].to_numpy())
