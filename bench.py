@@ -186,9 +186,21 @@ def cpu_baseline(args, workers: int) -> dict:
     t0 = time.perf_counter()
     cpu_build(df, args.variant, workers)
     dt = time.perf_counter() - t0
-    return {"value": len(df) / dt, "unit": UNIT, "cores": workers, "kind": "port", "seconds": dt,
-            "sample": f"pandas oracle (oracle/covisit_oracle.py), {args.variant}, {args.cpu_sample:g} of full scale = "
-                      f"{len(df)} events, one build"}
+    out = {"value": len(df) / dt, "unit": UNIT, "cores": workers, "kind": "port", "seconds": dt,
+           "sample": f"pandas oracle (oracle/covisit_oracle.py), {args.variant}, {args.cpu_sample:g} of full scale = "
+                     f"{len(df)} events, one build"}
+    try:
+        # context beside the pandas figure: the plain-C restatement of the same recipe (oracle/covisit_oracle.c), one core
+        from oracle import covisit_oracle_c as cc
+        cc.lib()
+        t0 = time.perf_counter()
+        cc.build(df, _oracle_spec(args.variant))
+        dtc = time.perf_counter() - t0
+        out["c_port"] = {"value": len(df) / dtc, "unit": UNIT, "cores": 1, "seconds": dtc,
+                         "sample": "plain-C oracle (oracle/covisit_oracle.c) on the same frame, one build"}
+    except Exception as e:              # no compiler on the box: the pandas figure stands alone
+        out["c_port"] = {"unavailable": str(e)[:200]}
+    return out
 
 
 def run_reference(args):
