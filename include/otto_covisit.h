@@ -303,6 +303,8 @@ int otto_covisit_partition(const OttoEvents* ev, const OttoCovisitSpec* spec, vo
  *   into MY record buffer -> otto_covisit_partition -> otto_covisit_reduce as before.
  * counts_all [n_ranks][n_aids]: the all-gathered per-row counts (NULL with one rank = the workspace's own).
  * OTTO_EOVERFLOW: the 64-bit staged record cannot carry aid_y, v and the row (use the direct scatter).
+ * Like the bin arrays of the workspace, the plan scratch (its tile list) is sized from spec->global_events: with more
+ * than one rank it must be the event count of ALL ranks (a smaller value under-sizes the list).
  * The reference has no distributed code; this replaces nothing of it. */
 int64_t otto_covisit_stage_plan_bytes(const OttoCovisitSpec* spec, int64_t n_sessions, int64_t n_events, int32_t n_ranks);
 int otto_covisit_stage_plan(const OttoEvents* ev, const OttoCovisitSpec* spec, void* workspace, int64_t workspace_bytes,
