@@ -1,7 +1,7 @@
 """The CUDA tables against the plain-C restatement of the build half (oracle/covisit_oracle.c) at 2 % of full scale - a
 size the pandas oracle needs minutes for: P, D, every kept pair, its exact integers and its weight bits.  The helper
 calls used here are held to the pandas oracle on the CPU by tests/test_oracle_c.py::test_c_oracle_through_the_gpu_comparison_helpers.
-(Sorted last on purpose: it was added after the round's GPU budget was spent.)"""
+(Sorted last on purpose: it was added when the round's GPU budget was all but spent - the buy2buy case ran on a B200.)"""
 import subprocess
 
 import numpy as np
