@@ -40,6 +40,8 @@ typedef struct {
   int32_t tail_n;
   int32_t ts_min;
   int32_t type_weight[3];   /* integer weights of type_y (wsum) */
+  int32_t x_lo, x_hi;       /* only pairs with x_lo <= aid_x < x_hi are produced: a row of the matrix depends on nothing
+                               else, so a large frame can be accumulated one aid_x range at a time */
 } OracleRecipe;
 
 typedef struct {
@@ -58,17 +60,15 @@ typedef struct {
   int64_t* wsum;
 } OracleResult;
 
-typedef struct {
-  int32_t session, ts;
-  int64_t row;
-} OrderKey;
+/* step 2 orders ROW NUMBERS; the comparator reads the columns through these (one oracle call at a time per process) */
+static const int32_t* g_session;
+static const int32_t* g_ts;
 
 static int order_cmp(const void* a, const void* b) {
-  const OrderKey* p = (const OrderKey*)a;
-  const OrderKey* q = (const OrderKey*)b;
-  if (p->session != q->session) return p->session < q->session ? -1 : 1;
-  if (p->ts != q->ts) return p->ts > q->ts ? -1 : 1;             /* ts descending */
-  return p->row < q->row ? -1 : (p->row > q->row ? 1 : 0);      /* stable: ties keep the row order */
+  const int32_t p = *(const int32_t*)a, q = *(const int32_t*)b;
+  if (g_session[p] != g_session[q]) return g_session[p] < g_session[q] ? -1 : 1;
+  if (g_ts[p] != g_ts[q]) return g_ts[p] > g_ts[q] ? -1 : 1;      /* ts descending */
+  return p < q ? -1 : (p > q ? 1 : 0);                            /* stable: ties keep the row order */
 }
 
 /* LSD radix sort of the pair records by key, 16 bits per pass, only as many passes as the largest key needs */
@@ -100,19 +100,30 @@ void covisit_oracle_free(OracleResult* r) {
 
 /* steps 1-7; NULL when memory runs out or an argument is unusable */
 OracleResult* covisit_oracle_accumulate(const OracleFrame* f, const OracleRecipe* rc) {
-  if (!f || !rc || f->n_events < 0 || rc->tail_n < 1 || rc->tail_n > 512) return NULL;
+  if (!f || !rc || f->n_events < 0 || rc->tail_n < 1 || rc->tail_n > 512 || rc->x_hi < rc->x_lo) return NULL;
   const int64_t n = f->n_events;
-  OrderKey* order = (OrderKey*)malloc((size_t)(n > 0 ? n : 1) * sizeof(OrderKey));
+  if (n >= (1ll << 31)) return NULL;
+  int32_t* order = (int32_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(int32_t));
   if (!order) return NULL;
   int64_t m = 0;
+  int grouped = 1;                                                   /* rows of a session adjacent, sessions ascending */
   for (int64_t i = 0; i < n; ++i) {                                  /* step 1 */
     if (f->type[i] > 2 || !((rc->event_type_mask >> f->type[i]) & 1u)) continue;
-    order[m].session = f->session[i];
-    order[m].ts = f->ts[i];
-    order[m].row = i;
-    ++m;
+    if (m > 0 && f->session[i] < f->session[order[m - 1]]) grouped = 0;
+    order[m++] = (int32_t)i;
   }
-  qsort(order, (size_t)m, sizeof(OrderKey), order_cmp);             /* step 2 */
+  g_session = f->session;
+  g_ts = f->ts;
+  if (!grouped) {
+    qsort(order, (size_t)m, sizeof(int32_t), order_cmp);            /* step 2 */
+  } else {                                                           /* step 2, session by session (frames in file order) */
+    for (int64_t s0 = 0; s0 < m;) {
+      int64_t s1 = s0;
+      while (s1 < m && f->session[order[s1]] == f->session[order[s0]]) ++s1;
+      qsort(order + s0, (size_t)(s1 - s0), sizeof(int32_t), order_cmp);
+      s0 = s1;
+    }
+  }
 
   int64_t cap = 1 << 16, np = 0;
   PairRec* pairs = (PairRec*)malloc((size_t)cap * sizeof(PairRec));
@@ -128,15 +139,15 @@ OracleResult* covisit_oracle_accumulate(const OracleFrame* f, const OracleRecipe
 
   for (int64_t s0 = 0; s0 < m && !fail;) {
     int64_t s1 = s0;
-    while (s1 < m && order[s1].session == order[s0].session) ++s1;
+    while (s1 < m && f->session[order[s1]] == f->session[order[s0]]) ++s1;
     const int64_t t = s1 - s0 < rc->tail_n ? s1 - s0 : rc->tail_n;   /* step 3 */
     int64_t n_used = 0;
     for (int64_t i = 0; i < t; ++i) {                                /* step 4: i-major ... */
-      const int64_t ri = order[s0 + i].row;
+      const int64_t ri = order[s0 + i];
       const int32_t ax = f->aid[ri], tx = f->ts[ri];
-      if (!((rc->x_type_mask >> f->type[ri]) & 1u)) continue;
+      if (!((rc->x_type_mask >> f->type[ri]) & 1u) || ax < rc->x_lo || ax >= rc->x_hi) continue;
       for (int64_t j = 0; j < t; ++j) {                              /* ... then j */
-        const int64_t rj = order[s0 + j].row;
+        const int64_t rj = order[s0 + j];
         const int32_t ay = f->aid[rj];
         int64_t dt = (int64_t)tx - (int64_t)f->ts[rj];
         if (dt < 0) dt = -dt;
@@ -206,4 +217,51 @@ void covisit_oracle_fetch(const OracleResult* r, int32_t* aid_x, int32_t* aid_y,
   memcpy(cnt, r->cnt, (size_t)r->n * 8);
   memcpy(tsum, r->tsum, (size_t)r->n * 8);
   memcpy(wsum, r->wsum, (size_t)r->n * 8);
+}
+
+/* Steps 6-8 over the accumulators: one float32 weight per distinct pair, formed ONCE from the exact integers
+ * (weight_mode 2, time: cnt + w_scale * tsum evaluated in double, w_scale = 3 / (ts_max - ts_min); 1, type: wsum;
+ * 0, unit: cnt), then per aid_x the k best by (weight descending, aid_y ascending) - the stable sort of Appendix A step 8
+ * on rows that arrive in aid_y order.  Writes at most k rows per aid_x into the caller's arrays (capacity
+ * covisit_oracle_count()), rows of an aid_x best first; returns the number of rows written. */
+int64_t covisit_oracle_topk(const OracleResult* r, int32_t weight_mode, int32_t k, double w_scale, int32_t* aid_x, int32_t* aid_y,
+                            float* wgt, int64_t* cnt, int64_t* tsum) {
+  if (!r || k < 1 || k > 64) return -1;
+  int64_t out = 0;
+  for (int64_t g0 = 0; g0 < r->n;) {
+    int64_t g1 = g0;
+    while (g1 < r->n && r->aid_x[g1] == r->aid_x[g0]) ++g1;
+    int64_t best[64];
+    float bw[64];
+    int kept = 0;
+    for (int64_t i = g0; i < g1; ++i) {
+      float w;
+      if (weight_mode == 2) {
+        volatile double prod = w_scale * (double)r->tsum[i];      /* no fused multiply-add: numpy rounds the product first */
+        w = (float)((double)r->cnt[i] + prod);
+      } else if (weight_mode == 1) {
+        w = (float)(double)r->wsum[i];
+      } else {
+        w = (float)(double)r->cnt[i];
+      }
+      /* insertion into the k best; an equal weight stays behind the earlier (smaller aid_y) entry */
+      int pos = kept;
+      while (pos > 0 && bw[pos - 1] < w) --pos;
+      if (pos >= k) continue;
+      const int last = kept < k ? kept : k - 1;
+      for (int q = last; q > pos; --q) { best[q] = best[q - 1]; bw[q] = bw[q - 1]; }
+      best[pos] = i;
+      bw[pos] = w;
+      if (kept < k) ++kept;
+    }
+    for (int q = 0; q < kept; ++q, ++out) {
+      aid_x[out] = r->aid_x[best[q]];
+      aid_y[out] = r->aid_y[best[q]];
+      wgt[out] = bw[q];
+      cnt[out] = r->cnt[best[q]];
+      tsum[out] = r->tsum[best[q]];
+    }
+    g0 = g1;
+  }
+  return out;
 }

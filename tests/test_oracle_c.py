@@ -142,3 +142,38 @@ def test_c_oracle_through_the_gpu_comparison_helpers(variant):
         b = co.topk(acc_p, spec.k)
     H.assert_int_table_equal(a, b, variant)
     assert np.array_equal(a["cnt"].to_numpy(), b["cnt"].to_numpy()) and np.array_equal(a["tsum"].to_numpy(), b["tsum"].to_numpy())
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_c_topk_equals_pandas_topk_and_splits_by_aid_range(variant):
+    """Steps 1-8 entirely in C (build_c) == C accumulators + pandas' stable top-K, weight bits included; and the matrix
+    built one aid_x range at a time is the matrix (what tools/verify_digest_cpu.py relies on at full scale)."""
+    spec = VARIANTS[variant]
+    df = _synth_df(20000, 2500, 31)
+    whole, via_pandas = cc.build_c(df, spec), cc.build(df, spec)
+    assert len(whole) == len(via_pandas)
+    for c in ("aid_x", "aid_y", "cnt", "tsum"):
+        assert np.array_equal(whole[c].to_numpy(), via_pandas[c].to_numpy()), c
+    assert np.array_equal(whole["wgt"].to_numpy().view(np.uint32), via_pandas["wgt"].to_numpy().view(np.uint32))
+    parts = [cc.build_c(df, spec, x_range=r) for r in ((0, 700), (700, 701), (701, 2500))]
+    glued = pd.concat(parts, ignore_index=True)
+    assert np.array_equal(glued["aid_x"].to_numpy(), whole["aid_x"].to_numpy())
+    assert np.array_equal(glued["aid_y"].to_numpy(), whole["aid_y"].to_numpy())
+    assert sum(p.attrs["pairs"] for p in parts) == whole.attrs["pairs"]
+    assert sum(p.attrs["distinct"] for p in parts) == whole.attrs["distinct"]
+    assert cc.table_digest(glued, spec.k) == cc.table_digest(whole, spec.k)
+
+
+def test_cpu_digest_equals_the_digest_a_gpu_run_committed():
+    """tests/golden/bench_digest.json was written by `bench.py --write-digest` on a B200 (and every multi-GPU bench line
+    is compared with it).  Recomputed here from the C oracle at 5 % of full scale (10.6 M events, 52.7 M pairs): equal
+    digests mean every row of the CUDA table - each aid_y, its rank, every weight bit - equals the oracle's.  Full
+    scale: tools/verify_digest_cpu.py (profiles/r02_cpu_digest_full_scale.json)."""
+    from otto_multi_objective_recommender_system_b200 import synth
+    golden = json.load(open(GOLDEN / "bench_digest.json"))["clicks@0.05"]
+    df = synth.generate(synth.SynthSpec.scaled("train", 0.05)).to_pandas()
+    table = cc.build_c(df, co.CLICKS)
+    digest = cc.table_digest(table, co.CLICKS.k)
+    assert digest["rows"] == golden["rows"] and digest["row_len_sum"] == golden["row_len_sum"]
+    assert table.attrs["pairs"] == golden["pairs"] == golden["pair_checksum"]
+    assert table.attrs["distinct"] == golden["distinct"]
