@@ -203,6 +203,37 @@ def cpu_baseline(args, workers: int) -> dict:
     return out
 
 
+def _c_range(args):
+    from oracle import covisit_oracle_c as cc
+    variant, lo, hi = args
+    return len(cc.build_c(_CPU_DF, _oracle_spec(variant), x_range=(lo, hi)))
+
+
+def c_port_rate(df, variant: str, workers: int) -> dict:
+    """Context beside the pandas figure: the plain-C restatement of the same recipe (oracle/covisit_oracle.c) on the same
+    frame, one aid_x range per process.  Never the line's `value`: the reference's idiom is pandas."""
+    global _CPU_DF
+    try:
+        import multiprocessing as mp
+        import numpy as np
+        from oracle import covisit_oracle_c as cc
+        cc.lib()
+        _CPU_DF = df
+        edges = np.linspace(0, int(df["aid"].max()) + 1, max(1, workers) + 1).astype(np.int64)
+        jobs = [(variant, int(edges[r]), int(edges[r + 1])) for r in range(len(edges) - 1)]
+        t0 = time.perf_counter()
+        if workers > 1:
+            with mp.get_context("fork").Pool(workers) as pool:
+                pool.map(_c_range, jobs, chunksize=1)
+        else:
+            _c_range(jobs[0])
+        dt = time.perf_counter() - t0
+        return {"value": len(df) / dt, "unit": UNIT, "cores": workers, "seconds": dt,
+                "sample": f"plain-C oracle (oracle/covisit_oracle.c) on the same frame, {len(jobs)} aid_x ranges in {workers} processes, one build"}
+    except Exception as e:              # no compiler on the box: the pandas figure stands alone
+        return {"unavailable": str(e)[:200]}
+
+
 def run_reference(args):
     """--impl reference: the CPU path on the host cores.  The reference repo has no builder to run (SURVEY.md
     §0.1), so this is the oracle port, with every host core, on a bounded sample of the same workload."""
@@ -223,6 +254,7 @@ def run_reference(args):
     value = len(df) / dt
     sample = (f"pandas oracle port, {workers} worker processes (session ranges accumulated in parallel, aid_x buckets "
               f"merged in parallel), {args.variant}, {args.cpu_sample:g} of full scale = {len(df)} events per step")
+    c_port = c_port_rate(df, args.variant, workers)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -230,7 +262,7 @@ def run_reference(args):
         "config": {"workload": workload_name(args), "cpu_sample": args.cpu_sample, "events_per_step": len(df),
                    "note": "same generator, recipe and metric as the b200 arm; the CPU arm times a bounded sample of the "
                            "frame (cpu_sample of full scale), the b200 arm the whole frame"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample, "c_port": c_port},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
